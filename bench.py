@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json:
+    metric  = MPC-loss fwd+bwd trajectory-steps/s (horizon N=10)
+    step    = one fused MPC-loss forward + reverse sweep (fc_mpc_loss) over one synthetic batch
+    workload= config 5 of BASELINE.json per GPU: N=10, 4 194 304 / 8 = 524 288 trajectories per GPU
+              (weak scaling: every rank owns 524 288 trajectories; no data-path collective, one
+              all-reduce of the 251-float [gradients | loss] buffer per step when N_gpus > 1)
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: launched by torchrun, one rank per GPU; RANK/LOCAL_RANK/WORLD_SIZE from the env)
+
+`value`    : device-resident inputs, CUDA-event timed on the launching stream, max over ranks.
+`e2e`      : the same metric through the public drop-in API (pinned host tensors -> H2D -> controller
+             -> MPCLoss -> backward -> loss.item()), copies inside the timed region.
+`roofline` : FP32-FMA bound: achieved = F_alg * trajectory-steps / kernel time with
+             F_alg = 2 041 600 FLOP per trajectory-step; peak measured in the same run by a
+             register-resident FFMA loop (fc_fp32_peak); HBM figures reported beside it.
+`cpu_baseline` / `--impl reference`: the oracle's torch restatement of the reference path
+             (oracle/mpc_loss_oracle.py::mpc_loss_torch, same ATen CPU kernels as the reference's
+             nn.Linear/LSTM maths + autograd) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+HORIZON = 10
+ALPHA = 20.0
+B_PER_GPU = 524288
+F_ALG = 2041600.0            # FLOP per trajectory-step, fwd + bwd
+ALG_BYTES_PER_TRAJ = 12 + 200 + 12 + 4 * HORIZON   # X + Z + three cost vectors + prediction
+CPU_SAMPLE_B = 4096
+
+
+def _golden_weights():
+    W = np.load(os.path.join(REPO, "tests", "golden", "weights.npz"))
+    lstm = {k[5:]: W[k] for k in W.files if k.startswith("lstm/")}
+    fnn = {k[len("fnn_c0/"):]: W[k] for k in W.files if k.startswith("fnn_c0/")}
+    return lstm, fnn
+
+
+def _synthetic(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(B, 3, generator=g) * 2 - 1
+    Z = torch.rand(B, 10, 5, generator=g) * 2 - 1
+    return X, Z
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_throughput(steps: int, warmup: int, B: int = CPU_SAMPLE_B):
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import mpc_loss_oracle as O      # bench.py's cpu_baseline / reference arm only
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    lstm, fnn = _golden_weights()
+    w = O.weights_from_state_dicts(lstm, fnn, np.float32)
+    tw = {k: ([torch.tensor(a) for a in v] if isinstance(v, list) else torch.tensor(v)) for k, v in w.items()}
+    for k in ("inp_w", "inp_b", "out_w"):
+        tw[k].requires_grad_()
+    X, Z = _synthetic(B, 1234)
+
+    def step():
+        for k in ("inp_w", "inp_b", "out_w"):
+            tw[k].grad = None
+        u0 = torch.clamp(torch.relu(X @ tw["inp_w"].t() + tw["inp_b"]) @ tw["out_w"].t(), -1.0, 1.0)[:, 0]
+        loss = O.mpc_loss_torch(tw, X, u0, Z, HORIZON, ALPHA)[0]
+        loss.backward()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return {"value": B * HORIZON / (sum(times) / len(times)), "best": B * HORIZON / min(times),
+            "ms_per_step": 1e3 * sum(times) / len(times), "cores": threads,
+            "sample": f"{steps} steps of B={B} trajectories, N={HORIZON}, fp32, torch {torch.__version__} CPU, "
+                      f"{threads} threads (oracle torch port of MPCLoss fwd + backward)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    r = cpu_port_throughput(steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "mpc_loss_fwd_bwd_trajectory_steps_per_s", "value": r["value"],
+        "unit": "trajectory-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MPC-loss fwd+bwd, N={HORIZON}, bounded CPU sample of B={CPU_SAMPLE_B} trajectories per step "
+                               f"(GPU arm: {B_PER_GPU} per GPU)", "horizon": HORIZON, "alpha": ALPHA},
+        "cpu_baseline": {"value": r["value"], "unit": "trajectory-steps/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import forging_control_b200 as fb
+    from forging_control_b200 import _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; forging_control_b200 has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch_per_gpu
+    N = HORIZON
+    B_global = B * world
+
+    lstm, fnn = _golden_weights()
+    sim = fb.LSTMModel(5, 50, 4, 3)
+    sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()})
+    ctl = fb.FNNModel(3, 50, 1, 1)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()})
+    sim, ctl = sim.to(dev), ctl.to(dev)
+    X_h, Z_h = _synthetic(B, 1234 + rank)
+    X_h, Z_h = X_h.pin_memory(), Z_h.pin_memory()
+    X, Z = X_h.to(dev), Z_h.to(dev)
+    with torch.no_grad():
+        u0 = ctl(X).reshape(-1).contiguous()
+    wpack = fb.pack_weights(sim, ctl)
+    params = [ctl.fc_inp.weight, ctl.fc_inp.bias, ctl.fc_out.weight]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- measured FP32 peak (same run, same device) ------------------------------------------------
+    import ctypes
+    flops = ctypes.c_double(0.0)
+    _native.check(_native.lib().fc_fp32_peak(4096, ctypes.byref(flops), _native.stream_ptr(dev)), "fc_fp32_peak")
+    fp32_peak = flops.value
+
+    # ---- device-resident timed region ------------------------------------------------------------------
+    def step_dev():
+        r = fb.mpc_loss_native(wpack, X, u0, Z, N, ALPHA, True, B_global)
+        if world > 1:
+            dist.all_reduce(r["gl"][:251])
+        return r
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        res = step_dev()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    loss_val = res["gl"][250].item()
+
+    # ---- end-to-end through the public API -----------------------------------------------------------
+    lf = fb.MPCLoss(prediction_horizon=N, alpha=ALPHA)
+    lf.global_batch = B_global
+
+    def step_e2e():
+        Xd = X_h.to(dev, non_blocking=True)
+        Zd = Z_h.to(dev, non_blocking=True)
+        for p in ctl.parameters():
+            p.grad = None
+        out = ctl(Xd)
+        loss, _ = lf(sim, ctl, Xd, out, Zd, dev)
+        loss.backward()
+        if world > 1:
+            loss = fb.allreduce_loss_and_grads(loss, params)
+        return loss.item()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        l_e2e = step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / e2e_steps
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = B_global * N / (ms_per_step * 1e-3)
+        kern_ms = float(np.mean(step_ms))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        achieved = F_ALG * B * N / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": "mpc_loss_fwd_bwd_trajectory_steps_per_s", "value": value, "unit": "trajectory-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fused MPC-loss fwd+bwd, N={N}, {B} synthetic trajectories per GPU "
+                                   f"(BASELINE config 5: 4194304 / 8), U(-1,1) inputs, shipped surrogate + controller weights",
+                       "horizon": N, "alpha": ALPHA, "batch_per_gpu": B, "global_batch": B_global,
+                       "parallelism": f"dp{world}", "l2": "inputs (105 MB Z + GBs of activation records) exceed the 126 MB L2"},
+            "loss": loss_val,
+            "e2e": {"value": B_global * N / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
+                    "h2d_bytes_per_step": int(X_h.numel() * 4 + Z_h.numel() * 4), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms, "loss": l_e2e,
+                    "path": "pinned host -> .to(device) -> FNNModel(X) -> MPCLoss.forward -> loss.backward() -> loss.item()"},
+            "gpu_launches": 2 * args.steps,
+            "gpu_launches_detail": "per step: fc::mpc_loss_kernel + fc::mpc_finalize_kernel (NCCL all-reduce extra when n_gpus>1)",
+            "roofline": {
+                "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / (fp32_peak / 1e12),
+                "peak_source": "fc_fp32_peak register-resident FFMA loop measured in this run; MEASURED_PEAKS.json holds no FP32 figure",
+                "peak_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+                "flop_per_trajectory_step": F_ALG,
+                "kernel_ms": kern_ms, "traffic": None,
+                "hbm": {"algorithmic_gbs": ALG_BYTES_PER_TRAJ * B / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            },
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_port_throughput(3, 1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "trajectory-steps/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

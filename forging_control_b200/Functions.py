@@ -1,0 +1,427 @@
+"""Drop-in mirror of the hot-path part of the reference ``Unsupervised Learning/Functions.py``.
+
+Same class names, constructor arguments, ``state_dict`` layout and call signatures as the
+reference (file:line citations are relative to ``/root/reference/Unsupervised Learning/``):
+
+* ``FNNModel``   (Functions.py:215-289)   controller 3 -> 50 -> (50)* -> 1, ReLU, Hardtanh
+* ``LSTMModel``  (Functions.py:295-379)   surrogate ``nn.LSTM(5,50,3,batch_first,bias=False)`` + ``Linear(50,4)``
+* ``MPCLoss``    (Functions.py:1336-1472) horizon roll-out loss -- here ONE fused sm_100a kernel that
+  also runs the reverse-time sweep, so ``loss.backward()`` only scales pre-computed gradients
+* ``NeuralNetwork.train_model`` / ``train_loop`` / ``validate_model`` (Functions.py:594-717, 825-923)
+* ``NeuralNetwork.tvp_fun`` (Functions.py:926-966), ``NeuralNetwork.loop`` (Functions.py:1014-1289)
+  -- the closed loop runs all ``N_traj`` trajectories as one batch of the RK4 plant kernel
+* ``FeasibilityRecovery.NN_make_step`` (Functions.py:1560-1613), ``Data.get_scaler`` (:407-442)
+
+Everything the hot path does not touch (datasets, plotting, NMPC teacher, IPOPT feasibility
+recovery) stays in the reference; ``forging_control_b200.install(reference_module)`` swaps the
+classes above into an imported reference module so that ``Main.py`` runs unchanged.
+
+There is no CPU fallback: ``MPCLoss`` and ``NeuralNetwork.loop`` require CUDA tensors / a CUDA
+device and raise otherwise.
+"""
+from __future__ import annotations
+
+import logging
+import random
+from time import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native
+from .closed_loop import ClosedLoopTimer, closed_loop_rollout, tvp_reference_table
+
+logger = logging.getLogger(__name__)
+
+LOOKBACK = 10  # hard-coded in the reference loss, Functions.py:1434
+
+
+# ----------------------------------------------------------------------------------------------
+# controller
+# ----------------------------------------------------------------------------------------------
+class FNNModel(nn.Module):
+    """Feed-forward controller, Functions.py:215-289 (same parameters / ``state_dict`` keys:
+    ``fc_inp.*``, ``fc_int.*`` (weight-shared hidden layer, unused when ``width_dim == 1``),
+    ``fc_out.weight``)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, width_dim: int,
+                 activation_fn=nn.ReLU, bias=True):
+        super().__init__()
+        self.width_dim = width_dim
+        self.activation = activation_fn()
+        self.constraint = nn.Hardtanh()
+        self.fc_inp = nn.Linear(input_dim, hidden_dim, bias=bias)
+        self.fc_int = nn.Linear(hidden_dim, hidden_dim, bias=bias)
+        self.fc_out = nn.Linear(hidden_dim, output_dim, bias=False)
+        for layer in (self.fc_inp, self.fc_int, self.fc_out):
+            nn.init.xavier_normal_(layer.weight)
+        nn.init.zeros_(self.fc_inp.bias)
+        nn.init.zeros_(self.fc_int.bias)
+
+    def forward(self, x):
+        out = self.activation(self.fc_inp(x))
+        for _ in range(self.width_dim - 1):
+            out = self.activation(self.fc_int(out))
+        return self.constraint(self.fc_out(out))
+
+
+# ----------------------------------------------------------------------------------------------
+# surrogate
+# ----------------------------------------------------------------------------------------------
+class LSTMModel(nn.Module):
+    """LSTM press surrogate, Functions.py:295-379.  ``state_dict`` keys ``lstm.weight_ih_l{k}``,
+    ``lstm.weight_hh_l{k}``, ``fc.weight``, ``fc.bias``.  Stand-alone ``forward`` (used by the
+    reference for the shadow prediction, Functions.py:999) runs the stock ``nn.LSTM``; inside
+    ``MPCLoss`` the weights are consumed by the fused kernel instead."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, layer_dim: int, bias=False,
+                 device: torch.device = "cpu"):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.layer_dim = layer_dim
+        self.lstm = nn.LSTM(input_dim, hidden_dim, layer_dim, batch_first=True, bias=bias)
+        self.fc = nn.Linear(hidden_dim, output_dim)
+
+    def initialize_hidden_states(self, batch_size: int, device: torch.device):
+        shape = (self.layer_dim, batch_size, self.hidden_dim)
+        return (torch.zeros(shape, device=device).requires_grad_(),
+                torch.zeros(shape, device=device).requires_grad_())
+
+    def forward(self, x: torch.Tensor, device: torch.device):
+        h0, c0 = self.initialize_hidden_states(x.size(0), device)
+        out, _ = self.lstm(x, (h0.detach(), c0.detach()))
+        return self.fc(out[:, -1, :])
+
+
+# ----------------------------------------------------------------------------------------------
+# packed-weight cache (per device, keyed by parameter storage + version)
+# ----------------------------------------------------------------------------------------------
+_PACK_CACHE: dict = {}
+_WORKSPACE: dict = {}
+
+
+def _check_models(simulator: nn.Module, controller: nn.Module):
+    lstm = getattr(simulator, "lstm", None)
+    fc = getattr(simulator, "fc", None)
+    if lstm is None or fc is None:
+        raise TypeError("MPCLoss: simulator must be an LSTMModel (attributes .lstm / .fc)")
+    if (lstm.input_size, lstm.hidden_size, lstm.num_layers) != (5, 50, 3) or lstm.bias or not lstm.batch_first \
+            or lstm.bidirectional or tuple(fc.weight.shape) != (4, 50) or fc.bias is None:
+        raise NotImplementedError(
+            "MPCLoss (fused sm_100a kernel) supports the reference surrogate LSTMModel(5, 50, 4, 3, bias=False) only")
+    for name in ("fc_inp", "fc_out"):
+        if not hasattr(controller, name):
+            raise TypeError("MPCLoss: controller must be an FNNModel")
+    if tuple(controller.fc_inp.weight.shape) != (50, 3) or tuple(controller.fc_out.weight.shape) != (1, 50) \
+            or controller.fc_inp.bias is None:
+        raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports FNNModel(3, 50, 1, width_dim, bias=True) only")
+    if getattr(controller, "width_dim", 1) != 1:
+        raise NotImplementedError("MPCLoss (fused sm_100a kernel): width_dim > 1 is not implemented yet")
+    if not isinstance(getattr(controller, "activation", None), nn.ReLU):
+        raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports the ReLU controller only")
+
+
+def _weight_tensors(simulator, controller):
+    l = simulator.lstm
+    return [l.weight_ih_l0, l.weight_hh_l0, l.weight_ih_l1, l.weight_hh_l1, l.weight_ih_l2, l.weight_hh_l2,
+            simulator.fc.weight, simulator.fc.bias,
+            controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight]
+
+
+def pack_weights(simulator: nn.Module, controller: nn.Module) -> torch.Tensor:
+    """Device buffer with the tiled weight layouts of the kernels (``fc_pack_weights``); re-packed
+    only when a parameter changed (optimizer steps bump ``_version``)."""
+    ws = _weight_tensors(simulator, controller)
+    dev = ws[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("MPCLoss: models must live on a CUDA device (no CPU fallback); call .to('cuda')")
+    for w in ws:
+        if w.device != dev or w.dtype != torch.float32:
+            raise RuntimeError("MPCLoss: all weights must be float32 tensors on the same CUDA device")
+    key = (dev.index, tuple((w.data_ptr(), w._version) for w in ws))
+    slot = _PACK_CACHE.get(dev.index)
+    if slot is not None and slot[0] == key:
+        return slot[1]
+    L = _native.lib()
+    buf = slot[1] if slot is not None else torch.empty(int(L.fc_pack_floats()), dtype=torch.float32, device=dev)
+    ws_c = [w.detach().contiguous() for w in ws]
+    with torch.cuda.device(dev):
+        rc = L.fc_pack_weights(*[_native.ptr(w) for w in ws_c], _native.ptr(buf), _native.stream_ptr(dev))
+    _native.check(rc, "fc_pack_weights")
+    _PACK_CACHE[dev.index] = (key, buf)
+    return buf
+
+
+def _workspace(dev, nbytes: int) -> torch.Tensor:
+    buf = _WORKSPACE.get(dev.index)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _WORKSPACE.pop(dev.index, None)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACE[dev.index] = buf
+    return buf
+
+
+def mpc_loss_native(wpack, X, u0, Z, N: int, alpha: float, with_grad: bool, global_batch: int | None = None):
+    """Thin wrapper over ``fc_mpc_loss``.  X [B,3], u0 [B], Z [B,10,5] float32 CUDA, contiguous.
+    Returns dict(cost, command, error, pred [B,N], gl [256], du0 [B] or None)."""
+    B = X.shape[0]
+    dev = X.device
+    L = _native.lib()
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = {k: torch.empty(B, **f32) for k in ("cost", "command", "error")}
+    out["pred"] = torch.empty(B, N, **f32)
+    out["gl"] = torch.empty(256, **f32)
+    out["du0"] = torch.empty(B, **f32) if with_grad else None
+    with torch.cuda.device(dev):
+        nbytes = int(L.fc_mpc_loss_workspace_bytes(B, N, int(with_grad)))
+        if nbytes == 0:
+            raise RuntimeError("fc_mpc_loss_workspace_bytes failed: " + L.fc_last_error().decode())
+        work = _workspace(dev, nbytes)
+        rc = L.fc_mpc_loss(_native.ptr(X), _native.ptr(u0), _native.ptr(Z), _native.ptr(wpack), B, N, float(alpha),
+                           int(global_batch if global_batch is not None else B), int(with_grad),
+                           _native.ptr(out["cost"]), _native.ptr(out["command"]), _native.ptr(out["error"]),
+                           _native.ptr(out["pred"]), _native.ptr(out["du0"]), _native.ptr(out["gl"]),
+                           _native.ptr(work), nbytes, _native.stream_ptr(dev))
+    _native.check(rc, "fc_mpc_loss")
+    return out
+
+
+class _FusedMPCLoss(torch.autograd.Function):
+    """The kernel computes loss AND d loss/d(u0, fc_inp.*, fc_out.weight) in one launch (the loss is
+    linear in the upstream gradient, so ``backward`` only scales)."""
+
+    @staticmethod
+    def forward(ctx, u0, inp_w, inp_b, out_w, X, Z, wpack, N, alpha, with_grad, global_batch):
+        res = mpc_loss_native(wpack, X, u0.detach().reshape(-1).contiguous(), Z, N, alpha, with_grad, global_batch)
+        ctx.with_grad = with_grad
+        ctx.u0_shape = u0.shape
+        if with_grad:
+            ctx.save_for_backward(res["du0"], res["gl"])
+        loss = res["gl"][250].clone()
+        pred = res["pred"].reshape(-1)
+        ctx.mark_non_differentiable(res["cost"], res["command"], res["error"], pred)
+        return loss, res["cost"], res["command"], res["error"], pred
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        if not ctx.with_grad:
+            raise RuntimeError("MPCLoss: backward called but the forward ran without gradients")
+        du0, gl = ctx.saved_tensors
+        g_u0 = (du0 * g_loss).reshape(ctx.u0_shape)
+        g = gl * g_loss
+        return (g_u0, g[0:150].reshape(50, 3), g[150:200], g[200:250].reshape(1, 50),
+                None, None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# MPC LOSS
+# ----------------------------------------------------------------------------------------------
+class MPCLoss(nn.Module):
+    """Loss that mimics the MPC cost, Functions.py:1336-1472 (same constructor and ``forward``
+    signature, same ``(loss, loss_features)`` return).  ``global_batch`` (extension, default None)
+    is the batch size the mean runs over when the batch is sharded across ranks."""
+
+    def __init__(self, prediction_horizon=10, alpha=0.1):
+        super().__init__()
+        self.N = prediction_horizon
+        self.alpha = alpha
+        self.activation = nn.ReLU()
+        self.global_batch = None
+
+    def forward(self, simulator: nn.Module, controller: nn.Module, input_controller: torch.Tensor,
+                output_controller: torch.Tensor, states: torch.Tensor, device: torch.device, enable_noise=False):
+        if enable_noise:
+            raise NotImplementedError(
+                "MPCLoss (fused sm_100a kernel): enable_noise=True (Functions.py:1400-1402) is not implemented")
+        _check_models(simulator, controller)
+        X, Z, u0 = input_controller, states, output_controller
+        if X.device.type != "cuda" or Z.device.type != "cuda" or u0.device.type != "cuda":
+            raise RuntimeError("MPCLoss: inputs must be CUDA tensors (forging_control_b200 has no CPU fallback)")
+        B = X.shape[0]
+        if X.dim() != 2 or X.shape[1] != 3 or tuple(Z.shape) != (B, LOOKBACK, 5) or u0.numel() != B:
+            raise ValueError(f"MPCLoss: expected input_controller [B,3], output_controller [B,1], states [B,10,5]; "
+                             f"got {tuple(X.shape)}, {tuple(u0.shape)}, {tuple(Z.shape)}")
+        X = X.detach().to(torch.float32).contiguous()
+        Z = Z.detach().to(torch.float32).contiguous()
+        wpack = pack_weights(simulator, controller)
+        params = (controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight)
+        with_grad = torch.is_grad_enabled() and (u0.requires_grad or any(p.requires_grad for p in params))
+        loss, cost, command, error, pred = _FusedMPCLoss.apply(
+            u0, *params, X, Z, wpack, int(self.N), float(self.alpha), bool(with_grad), self.global_batch)
+        return loss, {"loss": cost, "command": command, "error": error, "prediction": pred}
+
+
+# ----------------------------------------------------------------------------------------------
+# NEURAL NETWORK (training / closed-loop orchestration)
+# ----------------------------------------------------------------------------------------------
+class NeuralNetwork:
+    """Static helpers with the reference's signatures (Functions.py:590-1330)."""
+
+    @staticmethod
+    def train_model(data_loader, simulator, model, loss_function, optimizer, device, enable_noise=False):
+        """One epoch of controller training, Functions.py:594-676."""
+        model.train()
+        running = 0.0
+        feats = {"loss": [], "command": [], "error": [], "prediction": []}
+        for X, _, z in data_loader:
+            X, z = X.to(device, non_blocking=True), z.to(device, non_blocking=True)
+            optimizer.zero_grad()
+            output = model(X)
+            loss, loss_features = loss_function(simulator, model, X, output, z, device, enable_noise)
+            for k in feats:
+                feats[k].append(loss_features[k])
+            loss.backward()
+            optimizer.step()
+            running += loss.item()
+        out = {k: torch.cat(v, dim=0) for k, v in feats.items()}
+        return running / len(data_loader), out
+
+    @staticmethod
+    def validate_model(data_loader, model, loss_function, device):
+        """Functions.py:679-717."""
+        model.eval()
+        total = 0.0
+        with torch.no_grad():
+            for X, y, _ in data_loader:
+                X, y = X.to(device), y.to(device)
+                total += loss_function(model(X), y).item()
+        return total / len(data_loader)
+
+    @staticmethod
+    def train_loop(controller, simulator, train_loader, val_loader, loss_function, optimizer, n_epochs, device,
+                   enable_noise=False):
+        """Functions.py:825-923: epoch loop, validation MSE, wall time, features of the last epoch."""
+        mse = nn.MSELoss()
+        vec_t, vec_v = [], []
+        per_epoch = {"loss": [], "command": [], "error": [], "prediction": []}
+        start = time()
+        for epoch in range(n_epochs):
+            t_loss, feats = NeuralNetwork.train_model(train_loader, simulator, controller, loss_function,
+                                                      optimizer, device, enable_noise)
+            v_loss = NeuralNetwork.validate_model(val_loader, controller, mse, device)
+            vec_t.append(t_loss)
+            vec_v.append(v_loss)
+            for k in per_epoch:
+                per_epoch[k].append(feats[k].detach())
+            logger.info(f"[{100 * (epoch + 1) / n_epochs:.1f}%] Training loss: {t_loss:.4f},  Validation loss: {v_loss:.4f}")
+        loss_features = {k: torch.stack(v, dim=0) for k, v in per_epoch.items()}   # [n_epochs, ...]
+        comp_time = time() - start
+        logger.info(f"Total time: {comp_time:.2f}s.")
+        return controller, vec_t, vec_v, comp_time, loss_features
+
+    @staticmethod
+    def tvp_fun(t_now: float, ref_step: float, bias_work: int, bias_return: int, epsilon=10 ** (-7)):
+        """Piece-wise constant seeded reference, Functions.py:926-966."""
+        phase = (t_now + epsilon) % ref_step
+        period = (t_now + epsilon) // ref_step
+        if phase < ref_step / 2:
+            random.seed(period + bias_work)
+            return 0.8 * random.random() + 0.1
+        random.seed(period + bias_return)
+        return -0.8 * random.random() - 0.1
+
+    @staticmethod
+    def simulator_make_step(X: np.ndarray, model: nn.Module, scalers: dict, noise: np.ndarray):
+        """LSTM shadow prediction for one window, Functions.py:969-1011 (stock ``nn.LSTM``)."""
+        model.eval()
+        with torch.no_grad():
+            dev = next(model.parameters()).device
+            y_star = model(torch.as_tensor(X).float().to(dev), dev).cpu() + torch.as_tensor(noise).float()
+            return scalers["output"].inverse_transform(y_star)
+
+    @staticmethod
+    def loop(N_traj: int, T_traj: int, Ts: float, controller: nn.Module, simulator, simulator_LSTM: nn.Module,
+             init_state: dict, scalers: dict, model_scalers: dict, bias_work: float, bias_return: float, lookback: int,
+             bar_title: str, process_std: np.ndarray, meas_std: np.ndarray, feasibility=False, device=None,
+             dtype=torch.float64, substeps: int = 4):
+        """Closed-loop deployment, Functions.py:1014-1289.
+
+        The ``N_traj`` trajectories of the reference restart from ``init_state`` and only differ by
+        their reference segment, so they run as ONE batch of the RK4 plant kernel (scaler -> FNN ->
+        Hardtanh -> inverse scaler -> 4 RK4 sub-steps of the press ODE per sample).  ``simulator`` (the
+        do-mpc CVODES object of the reference) is accepted for signature compatibility and returned
+        untouched.  Noise and the IPOPT feasibility branch are outside the hot path and raise.
+        Extensions: ``device`` (default ``cuda``), ``dtype`` (plant precision, default float64 like the
+        reference plant), ``substeps``."""
+        if feasibility:
+            raise NotImplementedError("NeuralNetwork.loop: the IPOPT feasibility-recovery branch is out of scope")
+        if np.any(np.asarray(process_std) != 0) or np.any(np.asarray(meas_std) != 0):
+            raise NotImplementedError("NeuralNetwork.loop: process / measurement noise is not implemented")
+        dev = torch.device(device) if device is not None else torch.device("cuda")
+        x0 = np.array([[init_state.get(k, 0) for k in ("y", "y_dot", "p1", "p2", "z")]] * N_traj, dtype=np.float64)
+        T_ref = Ts * T_traj
+        ref = tvp_reference_table(N_traj, T_traj, Ts, T_ref, bias_work, bias_return)      # [N_traj, T_traj]
+        scale_in = np.asarray(scalers["input"].scale_, dtype=np.float64).copy()
+        scale_in[2] = np.asarray(scalers["y_dot"].scale_, dtype=np.float64)[0]            # Functions.py:1597-1598
+        scale_out = np.asarray(scalers["output"].scale_, dtype=np.float64)
+        timer = ClosedLoopTimer()
+        timer.tic()
+        meas, u = closed_loop_rollout(controller, x0, ref, Ts, scale_in, scale_out, substeps=substeps,
+                                      device=dev, dtype=dtype)
+        timer.toc(n_steps=N_traj * T_traj)
+        names = ("y", "y_dot", "p1", "p2", "z")
+        results = {n: meas[:, :, i] for i, n in enumerate(names)}
+        results["ref"] = ref
+        results["u"] = u
+        results_LSTM = NeuralNetwork._lstm_shadow(simulator_LSTM, model_scalers, x0, meas, u, lookback)
+        return simulator, results, results_LSTM, timer, 0.0
+
+    @staticmethod
+    def _lstm_shadow(simulator_LSTM, model_scalers, x0, meas, u, lookback):
+        """Diagnostic LSTM prediction logged next to the plant (Functions.py:1196-1231): the window at
+        step t holds the shadow's own previous predictions and the applied commands; it is never fed
+        back to the controller, so it runs after the roll-out, batched over trajectories."""
+        if simulator_LSTM is None or model_scalers is None:
+            return {}
+        B, T1, _ = meas.shape
+        T = T1 - 1
+        s_in = np.asarray(model_scalers["input"].scale_, dtype=np.float64)
+        s_out = np.asarray(model_scalers["output"].scale_, dtype=np.float64)
+        dev = next(simulator_LSTM.parameters()).device
+        out = np.zeros((B, T + 1, 4))
+        out[:, 0] = x0[:, 1:5]
+        x_next = x0[:, 1:5].copy()
+        window = None
+        simulator_LSTM.eval()
+        with torch.no_grad():
+            for t in range(T):
+                row = np.concatenate((x_next, u[:, t:t + 1]), axis=1) / s_in
+                window = np.repeat(row[:, None], lookback, axis=1) if t == 0 else \
+                    np.concatenate((window[:, 1:lookback], row[:, None]), axis=1)
+                y = simulator_LSTM(torch.as_tensor(window).float().to(dev), dev).double().cpu().numpy()
+                x_next = y * s_out
+                out[:, t + 1] = x_next
+        return {"y_dot": out[:, :, 0], "p1": out[:, :, 1], "p2": out[:, :, 2], "z": out[:, :, 3]}
+
+
+# ----------------------------------------------------------------------------------------------
+# FEASIBILITY RECOVERY (controller step only)
+# ----------------------------------------------------------------------------------------------
+class FeasibilityRecovery:
+    @staticmethod
+    def NN_make_step(X: np.ndarray, model: nn.Module, scalers: dict, x_init=None, warm_start=None, feasibility=None):
+        """Scaler -> FNN -> inverse scaler for one measurement, Functions.py:1560-1613 (feasibility=None)."""
+        if feasibility:
+            raise NotImplementedError("NN_make_step: the IPOPT feasibility-recovery branch is out of scope")
+        model.eval()
+        with torch.no_grad():
+            X_new = np.asarray(X, dtype=np.float64) / np.asarray(scalers["input"].scale_)
+            X_new[0, -1] = X[0, -1] / np.asarray(scalers["y_dot"].scale_)[0]
+            dev = next(model.parameters()).device
+            y_star = model(torch.as_tensor(X_new).float().to(dev)).double().cpu().numpy()
+            output = y_star * np.asarray(scalers["output"].scale_)
+        return output, 0.0, warm_start
+
+
+class Data:
+    @staticmethod
+    def get_scaler(scaler: str):
+        """Functions.py:407-442."""
+        from sklearn.preprocessing import MaxAbsScaler, MinMaxScaler, RobustScaler, StandardScaler
+        table = {"minmax": MinMaxScaler, "standard": StandardScaler, "maxabs": MaxAbsScaler, "robust": RobustScaler}
+        try:
+            return table[scaler.lower()]()
+        except KeyError:
+            raise ValueError(f"Scaler '{scaler}' is not supported. Choose from {list(table.keys())}.") from None

@@ -1,0 +1,28 @@
+"""forging_control_b200 -- B200-native (sm_100a) implementation of the data-parallel hot path of
+marcowus/forging-control: the fused MPC-loss roll-out + reverse sweep and the closed-loop RK4
+deployment roll-out, behind the reference's own Python API (see ``Functions.py``)."""
+from . import _native
+from .Functions import (Data, FNNModel, FeasibilityRecovery, LSTMModel, MPCLoss, NeuralNetwork,
+                        mpc_loss_native, pack_weights)
+from .closed_loop import closed_loop_device, closed_loop_rollout, tvp_reference_table
+from .distributed import allreduce_loss_and_grads, shard_bounds, sharded_training_step
+
+__all__ = ["FNNModel", "LSTMModel", "MPCLoss", "NeuralNetwork", "FeasibilityRecovery", "Data",
+           "mpc_loss_native", "pack_weights", "closed_loop_device", "closed_loop_rollout",
+           "tvp_reference_table", "shard_bounds", "allreduce_loss_and_grads", "sharded_training_step",
+           "install"]
+
+
+def install(reference_functions_module) -> None:
+    """Swap the hot-path classes into an already imported reference ``Functions`` module so that the
+    reference ``Main.py`` (``from Functions import ...``, Main.py:19) picks up the CUDA path:
+
+        import Functions, forging_control_b200 as fb; fb.install(Functions)
+    """
+    ref = reference_functions_module
+    ref.FNNModel = FNNModel
+    ref.LSTMModel = LSTMModel
+    ref.MPCLoss = MPCLoss
+    ref.NeuralNetwork.train_model = staticmethod(NeuralNetwork.train_model)
+    ref.NeuralNetwork.loop = staticmethod(NeuralNetwork.loop)
+    ref.FeasibilityRecovery.NN_make_step = staticmethod(FeasibilityRecovery.NN_make_step)

@@ -1,0 +1,157 @@
+// 5-state hydraulic forging press (Unsupervised Learning/template_model.py:20-156) and the
+// fixed-step RK4 of FeasibilityRecovery.Ruge_Kuta (Unsupervised Learning/Functions.py:1759-1775),
+// one trajectory per thread, state in registers.  R = float or double.
+#pragma once
+#include <math.h>
+
+namespace fc {
+
+template <typename R> struct Mth;
+template <> struct Mth<float> {
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float log_(float x) { return logf(x); }
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+  static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+};
+template <> struct Mth<double> {
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double log_(double x) { return log(x); }
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+  static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+};
+
+// constants, template_model.py:20-62, 88-92 (evaluated in double, rounded once to R)
+namespace pc {
+constexpr double kPi = 3.14159265358979323846;
+constexpr double M = 90000.0, Bv = 25000.0, FT = 200000.0, D1 = 0.6, D2 = 0.5;
+constexpr double A1 = kPi * D1 * D1 / 4, A2 = kPi * D2 * D2 / 4, G = 9.81;
+constexpr double KB = 22e9, V1_0 = 0.3, V2_0 = 0.1, KL_1 = 8e-13, KL_2 = 14e-14;
+constexpr double CD = 0.63, RHO = 858.0, D = 0.006, PS = 32e6, PT = 101325.0;
+constexpr double MU = 0.3, K = 1.115, W0 = 0.2, H0 = 0.5, B0 = 0.1;
+constexpr double A = 0.14 + 0.36 * (B0 / W0) - 0.054 * (B0 / W0) * (B0 / W0);
+constexpr double T1 = 0.005;
+constexpr double M0 = 1200e6, M1 = -0.0025, M2 = -0.0587, M3 = 0.1165, M4 = -0.0065, TEMP = 900.0;
+constexpr double EXP_M1T = 0.10539922456186433;   // exp(M1*TEMP) = exp(-2.25)
+constexpr double FLOOR_EPS = 1e-6;
+}  // namespace pc
+
+template <typename R>
+__device__ __forceinline__ R smooth_floor(R p) {                 // template_model.py:107-112
+  return R(0.5) * (p + Mth<R>::sqrt_(p * p + R(pc::FLOOR_EPS)));
+}
+
+template <typename R>
+__device__ __forceinline__ R valve_flow(R kv, R dp) {            // template_model.py:120-125
+  R q = kv * Mth<R>::sqrt_(R(2.0 / pc::RHO) * Mth<R>::abs_(dp));
+  return dp > R(0) ? q : (dp < R(0) ? -q : R(0));
+}
+
+template <typename R>
+__device__ __forceinline__ void press_rhs(const R (&x)[5], R u, R (&dx)[5]) {
+  const R y = x[0], v = x[1], p1 = x[2], p2 = x[3], z = x[4];
+  R Fd = R(0);
+  if (y > R(0) && v >= R(0)) {                                    // template_model.py:74-99
+    const R h1 = R(pc::H0) - y;
+    const R ratio = R(pc::H0) / h1;
+    const R w1 = R(pc::W0) * Mth<R>::pow_(ratio, R(pc::A));
+    const R b1 = R(pc::B0) * (R(1) + R(0.67) * (ratio * R(pc::W0) / w1 - R(1)));
+    const R Kd = R(pc::K) * (R(1) + R(pc::MU) * b1 / (R(2) * y) + y / (R(4) * b1));
+    const R Ad = w1 * b1;
+    const R e = Mth<R>::log_(ratio);
+    const R e_dot = v / h1;
+    Fd = Kd * Ad * R(pc::M0) * R(pc::EXP_M1T) * Mth<R>::pow_(e, R(pc::M2)) * Mth<R>::pow_(e_dot, R(pc::M3)) *
+         Mth<R>::exp_(R(pc::M4) / e);
+  }
+  const R p1e = smooth_floor(p1), p2e = smooth_floor(p2);
+  const R kv = R(pc::kPi * pc::D * pc::CD) * z;
+  R qPB, qAT;
+  if (z >= R(0)) {                                                // template_model.py:128-129
+    qPB = valve_flow(kv, R(pc::PS) - p1e);
+    qAT = valve_flow(kv, p2e - R(pc::PT));
+  } else {
+    qPB = valve_flow(kv, p1e - R(pc::PT));
+    qAT = valve_flow(kv, R(pc::PS) - p2e);
+  }
+  const R V1 = R(pc::V1_0 / 2) + R(pc::A1) * y;
+  const R V2 = R(pc::V2_0 / 2) - R(pc::A2) * y;
+  const R Ft = Mth<R>::abs_(v) <= R(0.5) ? R(pc::FT) * v / R(0.5) : R(pc::FT);   // template_model.py:142
+  dx[0] = v;
+  dx[1] = (R(3 * pc::kPi * pc::D1 * pc::D1 / 4) * p1e - R(pc::kPi * pc::D2 * pc::D2 / 2) * p2e - R(pc::Bv) * v - Ft - Fd) / R(pc::M) + R(pc::G);
+  dx[2] = R(pc::KB) / V1 * (qPB / R(3) - R(pc::A1) * v - R(pc::KL_1) * p1e);
+  dx[3] = R(pc::KB) / V2 * (-qAT / R(2) + R(pc::A2) * v - R(pc::KL_2) * p2e);
+  dx[4] = (u - z) / R(pc::T1);
+}
+
+template <typename R>
+__device__ __forceinline__ void rk4_substep(R (&x)[5], R u, R h) {            // Functions.py:1767-1775
+  R k1[5], k2[5], k3[5], k4[5], xt[5];
+  press_rhs(x, u, k1);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) xt[i] = x[i] + h / R(2) * k1[i];
+  press_rhs(xt, u, k2);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) xt[i] = x[i] + h / R(2) * k2[i];
+  press_rhs(xt, u, k3);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) xt[i] = x[i] + h * k3[i];
+  press_rhs(xt, u, k4);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) x[i] = x[i] + h / R(6) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + k4[i]);
+}
+
+// closed loop: scaler -> FNN (float32) -> saturation -> inverse scaler -> RK4 plant step
+template <typename R>
+__global__ void __launch_bounds__(128) closed_loop_kernel(
+    const R* __restrict__ x0, const R* __restrict__ ref, int n_ref, int steps_per_ref, int B, int T, R ts,
+    int substeps, const R* __restrict__ scale_in, const R* __restrict__ scale_out,
+    const float* __restrict__ inp_w, const float* __restrict__ inp_b, const float* __restrict__ out_w,
+    R* __restrict__ meas, R* __restrict__ ucmd, R* __restrict__ x_final) {
+  __shared__ float s_w[50 * 3], s_b[50], s_o[50];
+  for (int i = threadIdx.x; i < 150; i += blockDim.x) s_w[i] = inp_w[i];
+  for (int i = threadIdx.x; i < 50; i += blockDim.x) { s_b[i] = inp_b[i]; s_o[i] = out_w[i]; }
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const R si0 = scale_in[0], si1 = scale_in[1], so = scale_out[0];
+  R x[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) x[i] = x0[(size_t)b * 5 + i];
+  if (meas) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) meas[(size_t)i * B + b] = x[i];           // Functions.py:1134-1138
+  }
+  const R h = ts / R(substeps);
+  for (int t = 0; t < T; ++t) {
+    int ir = t / steps_per_ref;
+    ir = ir < n_ref ? ir : n_ref - 1;
+    const R r = ref[(size_t)ir * B + b];
+    // NN_make_step, Functions.py:1596-1604: MaxAbs scale, reference scaled by the y_dot scaler
+    const float f0 = (float)(x[1] / si0), f1 = (float)(x[4] / si1), f2 = (float)(r / si0);
+    float vv = 0.f;
+#pragma unroll 10
+    for (int k = 0; k < 50; ++k) {
+      float pre = fmaf(s_w[k * 3 + 2], f2, fmaf(s_w[k * 3 + 1], f1, fmaf(s_w[k * 3], f0, s_b[k])));
+      vv = fmaf(s_o[k], fmaxf(pre, 0.f), vv);
+    }
+    const float us = fminf(fmaxf(vv, -1.f), 1.f);                          // nn.Hardtanh
+    const R u = (R)us * so;
+    if (ucmd) ucmd[(size_t)t * B + b] = u;
+    for (int s = 0; s < substeps; ++s) rk4_substep(x, u, h);
+    if (meas) {
+      R* mp = meas + (size_t)(t + 1) * 5 * B + b;
+      mp[0] = x[0];
+      mp[(size_t)B] = x[1];
+      mp[(size_t)2 * B] = smooth_floor(x[2]);                              // template_model.py:154-155
+      mp[(size_t)3 * B] = smooth_floor(x[3]);
+      mp[(size_t)4 * B] = x[4];
+    }
+  }
+  if (x_final) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x_final[(size_t)b * 5 + i] = x[i];
+  }
+}
+
+}  // namespace fc

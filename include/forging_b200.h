@@ -1,0 +1,96 @@
+/* forging_b200 -- C ABI of the B200-native hot path of marcowus/forging-control.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below names the
+ * reference interface (file:line under "Unsupervised Learning/") whose arithmetic it replaces.  The
+ * Python host side (forging_control_b200/Functions.py) binds these with ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the library borrows it for
+ *     the duration of the call and never frees or retains caller memory;
+ *   - all calls are enqueue-only on `stream` (a cudaStream_t passed as void*), no hidden
+ *     synchronisation, re-entrant per device;
+ *   - every function returns 0 on success or a negative fc_status; fc_last_error() returns a
+ *     thread-local message for the last failure;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef FORGING_B200_H_
+#define FORGING_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum fc_status {
+  FC_OK = 0,
+  FC_ERR_BAD_SHAPE = -1,     /* B <= 0, N <= 0, T <= 0 ...                                  */
+  FC_ERR_UNSUPPORTED = -2,   /* dims other than LSTM(5,50,4,3) / FNN(3,50,1,width 1), ...   */
+  FC_ERR_NULL_POINTER = -3,
+  FC_ERR_MISALIGNED = -4,    /* pointer not 16-byte aligned where required                  */
+  FC_ERR_WORKSPACE = -5,     /* workspace too small                                         */
+  FC_ERR_CUDA = -6           /* CUDA runtime error, text in fc_last_error()                 */
+} fc_status;
+
+const char* fc_last_error(void);
+int fc_version(void);
+
+/* ---- weights ---------------------------------------------------------------------------------
+ * Packs the state_dict tensors of LSTMModel(5,50,4,3) (Functions.py:295-379: lstm.weight_ih_l{k}
+ * [200,in], lstm.weight_hh_l{k} [200,50], fc.weight [4,50], fc.bias [4]; gate rows i|f|g|o) and of
+ * FNNModel(3,50,1,width_dim=1) (Functions.py:215-289: fc_inp.weight [50,3], fc_inp.bias [50],
+ * fc_out.weight [1,50]) into the tiled layouts the kernels read (fc_pack_floats() floats).        */
+size_t fc_pack_floats(void);
+int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
+                    const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
+                    const float* fnn_inp_w, const float* fnn_inp_b, const float* fnn_out_w,
+                    float* wpack, void* stream);
+
+/* ---- fused MPC loss: replaces MPCLoss.forward (Functions.py:1353-1472) and the autograd sweep
+ * triggered by loss.backward() (Functions.py:655) ------------------------------------------------
+ *   X [B,3] controller input (reference = column 2), u0 [B] = output_controller.squeeze(),
+ *   Z [B,10,5] look-back window; N = prediction horizon; alpha = command-rate weight.
+ *   B_global: batch size the mean is taken over (== B on one GPU; the global batch when the batch
+ *   is sharded over ranks, so that summing gl over ranks gives the single-GPU result).
+ *   Outputs: cost/command/error [B], pred [B,N] (loss_features of the reference),
+ *   gl [256]: gl[0..149] d loss/d fc_inp.weight, gl[150..199] d/d fc_inp.bias, gl[200..249]
+ *   d/d fc_out.weight (contributions of the commands u_1..u_{N-1}; the u_0 path is returned as
+ *   du0 [B] = d loss / d output_controller), gl[250] = sum_b cost[b] / B_global (the loss).
+ *   with_grad = 0 computes the forward only (du0 may be NULL, gl[0..249] are zero).              */
+size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad);
+int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N,
+                float alpha, long long B_global, int with_grad, float* cost, float* command,
+                float* error, float* pred, float* du0, float* gl, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* ---- closed-loop deployment: replaces the body of NeuralNetwork.loop (Functions.py:1157-1237)
+ * = FeasibilityRecovery.NN_make_step (:1596-1604) + simulator.make_step on the plant of
+ * template_model.py:10-161, integrated with the fixed-step RK4 of Ruge_Kuta (:1759-1775) ----------
+ *   x0 [B,5] initial state (y, y_dot, p1, p2, z), row-major; ref [n_ref,B] reference, entry
+ *   min(t / steps_per_ref, n_ref-1) is used at step t; scale_in [3] MaxAbs scales of the controller
+ *   input (y_dot, z, ref) -- the reference is scaled by scale_in[0] like NN_make_step does
+ *   (:1597-1598); scale_out [1]; fnn_* = controller weights (raw state_dict layout, float32: the
+ *   controller is evaluated in float32 in both variants, Functions.py:1601); T steps of ts seconds,
+ *   `substeps` RK4 sub-steps per step (the reference scheme uses 4).
+ *   Outputs (each may be NULL): meas [T+1,5,B] measurements (y, y_dot, floored p1, floored p2, z;
+ *   template_model.py:152-156; meas[0] = x0), u [T,B] commands, x_final [B,5] raw final state.
+ *   Time-major structure-of-arrays output so that a warp writes 128-byte lines.
+ *   fc_closed_loop_rk4 integrates in float32, fc_closed_loop_rk4_f64 in float64 (reference dtype). */
+int fc_closed_loop_rk4(const float* x0, const float* ref, int n_ref, int steps_per_ref, int B, int T,
+                       float ts, int substeps, const float* scale_in, const float* scale_out,
+                       const float* fnn_inp_w, const float* fnn_inp_b, const float* fnn_out_w,
+                       float* meas, float* u, float* x_final, void* stream);
+int fc_closed_loop_rk4_f64(const double* x0, const double* ref, int n_ref, int steps_per_ref, int B,
+                           int T, double ts, int substeps, const double* scale_in,
+                           const double* scale_out, const float* fnn_inp_w, const float* fnn_inp_b,
+                           const float* fnn_out_w, double* meas, double* u, double* x_final,
+                           void* stream);
+
+/* ---- measurement helper: register-resident FFMA loop used by bench.py to measure the FP32
+ * roofline denominator on the device it runs on; writes achieved FLOP/s to *flops_host.           */
+int fc_fp32_peak(int iters, double* flops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORGING_B200_H_ */

@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library loads and exports every symbol include/forging_b200.h declares (no compute
+calls without a GPU), and the host-side mirror of the reference interface behaves like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import forging_control_b200 as fb
+from forging_control_b200 import _native
+from conftest import REPO, state_dicts
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "forging_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(fc_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(_native.EXPORTS)
+    _native.build()
+    L = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _native.lib().fc_version() == 100
+    assert _native.lib().fc_pack_floats() == 115456
+
+
+def test_state_dict_layout_loads_shipped_checkpoints_strictly(golden_weights):
+    lstm, fnn = state_dicts(golden_weights, "c0")
+    sim = fb.LSTMModel(5, 50, 4, 3)
+    sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()}, strict=True)
+    ctl = fb.FNNModel(3, 50, 1, 1, torch.nn.ReLU, bias=True)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()}, strict=True)
+    assert list(ctl.state_dict()) == ["fc_inp.weight", "fc_inp.bias", "fc_int.weight", "fc_int.bias", "fc_out.weight"]
+    assert [tuple(v.shape) for v in sim.state_dict().values()] == \
+        [(200, 5), (200, 50), (200, 50), (200, 50), (200, 50), (200, 50), (4, 50), (4,)]
+
+
+def test_models_match_reference_outputs_on_cpu(golden_cases, golden_weights):
+    """model(X) (Functions.py:643) reproduces the reference's recorded u0; LSTMModel.forward the oracle."""
+    import mpc_loss_oracle as O
+    C = golden_cases
+    lstm, fnn = state_dicts(golden_weights, "c0")
+    ctl = fb.FNNModel(3, 50, 1, 1)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()})
+    u0 = ctl(torch.tensor(C["n10_b15/X"])).detach().numpy()[:, 0]
+    assert np.abs(u0 - C["n10_b15/f32/u0"]).max() < 1e-6
+    sim = fb.LSTMModel(5, 50, 4, 3)
+    sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()})
+    y = sim(torch.tensor(C["n10_b15/Z"]), "cpu").detach().numpy()
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    assert np.abs(y - O.lstm_window_forward(w, C["n10_b15/Z"].astype(np.float64))).max() < 1e-5
+
+
+def test_no_cpu_fallback(golden_weights):
+    lstm, fnn = state_dicts(golden_weights, "c0")
+    sim, ctl = fb.LSTMModel(5, 50, 4, 3), fb.FNNModel(3, 50, 1, 1)
+    X, Z = torch.zeros(4, 3), torch.zeros(4, 10, 5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fb.MPCLoss(10, 20.0)(sim, ctl, X, ctl(X), Z, "cpu")
+    with pytest.raises(NotImplementedError):
+        fb.MPCLoss(10, 20.0)(sim, ctl, X, ctl(X), Z, "cpu", enable_noise=True)
+    with pytest.raises(NotImplementedError):
+        fb.MPCLoss(10, 20.0)(fb.LSTMModel(5, 64, 4, 3), ctl, X, ctl(X), Z, "cpu")
+    with pytest.raises(NotImplementedError):
+        fb.MPCLoss(10, 20.0)(sim, fb.FNNModel(3, 50, 1, 2), X, ctl(X), Z, "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fb.closed_loop_device(ctl, torch.zeros(2, 5), torch.zeros(3, 2), 1e-3, [1, 1, 1], [1])
+
+
+def test_tvp_fun_and_reference_table(golden_trace):
+    t = golden_trace["time"][:, 0]
+    mine = np.array([fb.NeuralNetwork.tvp_fun(float(tt), 0.3, 300, 20 ** 6) for tt in t])
+    assert np.array_equal(mine, golden_trace["tvp_fun"])
+    tab = fb.tvp_reference_table(2, 300, 1e-3, 0.3, 300, 20 ** 6)
+    assert np.array_equal(tab.reshape(-1), golden_trace["tvp"][:, 0])
+
+
+def test_nn_make_step_matches_reference(golden_trace, golden_weights):
+    from sklearn.preprocessing import MaxAbsScaler
+    _, fnn = state_dicts(golden_weights, "c0")
+    ctl = fb.FNNModel(3, 50, 1, 1)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()})
+    mk = lambda s: MaxAbsScaler().fit(np.asarray(s)[None, :])
+    scalers = {"input": mk(golden_weights["scale/scaler_input"]), "output": mk(golden_weights["scale/scaler_output"]),
+               "y_dot": mk(golden_weights["scale/scaler_input"][:1])}
+    g = golden_trace
+    for k in (0, 1, 150, 299, 300, 451, 599):
+        inp = np.array([[g["meas_prev"][k, 1], g["meas_prev"][k, 4], g["tvp"][k, 0]]])
+        u, sol, _ = fb.FeasibilityRecovery.NN_make_step(inp, ctl, scalers, None, None, None)
+        assert abs(u.item() - g["nn_make_step_u"][k]) < 1e-7 and sol == 0.0
+
+
+def test_get_scaler():
+    assert type(fb.Data.get_scaler("MaxAbs")).__name__ == "MaxAbsScaler"
+    assert type(fb.Data.get_scaler("robust")).__name__ == "RobustScaler"
+    with pytest.raises(ValueError):
+        fb.Data.get_scaler("quantile")
+
+
+def test_shard_bounds_cover_the_batch():
+    for total, ws in ((10, 3), (4194304, 8), (7, 8), (120, 1)):
+        spans = [fb.shard_bounds(total, ws, r) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_install_swaps_hot_path_into_a_reference_like_module():
+    import types
+    ref = types.SimpleNamespace(NeuralNetwork=type("NeuralNetwork", (), {}), FeasibilityRecovery=type("FR", (), {}))
+    fb.install(ref)
+    assert ref.MPCLoss is fb.MPCLoss and ref.FNNModel is fb.FNNModel and ref.LSTMModel is fb.LSTMModel
+    assert ref.NeuralNetwork.loop is fb.NeuralNetwork.loop

@@ -1,0 +1,121 @@
+"""GPU (-m gpu): the batched closed-loop RK4 kernel (fc_closed_loop_rk4[_f64]) against the fp64
+plant oracle at matched step (<= 1e-4 of scale, north_star), the reference's CVODES trace, and
+size-independent properties at large batch."""
+import numpy as np
+import pytest
+import torch
+
+import plant_oracle as P
+import forging_control_b200 as fb
+from conftest import state_dicts
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctl(W, tag="c0"):
+    _, fnn = state_dicts(W, tag)
+    ctl = fb.FNNModel(3, 50, 1, 1)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()})
+    return ctl, {"inp_w": fnn["fc_inp.weight"], "inp_b": fnn["fc_inp.bias"], "out_w": fnn["fc_out.weight"]}
+
+
+def _inputs(B, T, seed=4321):
+    """SURVEY.md section 8d synthetic closed-loop inputs: perturbed init state, piece-wise constant
+    references of alternating sign held for 150 steps."""
+    rng = np.random.default_rng(seed)
+    x0 = np.tile(P.INIT_STATE, (B, 1))
+    x0[:, 0] = rng.uniform(0, 0.02, B)
+    x0[:, 1] = rng.uniform(-0.1, 0.1, B)
+    x0[:, 2] = rng.uniform(1e6, 8e6, B)
+    x0[:, 3] = rng.uniform(1e6, 8e6, B)
+    n_seg = (T + 149) // 150
+    seg = rng.uniform(0.1, 0.9, (B, n_seg)) * np.where(np.arange(n_seg) % 2 == 0, 1.0, -1.0)
+    return x0, seg
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)])
+def test_closed_loop_matches_fp64_oracle(golden_weights, dtype, tol):
+    ctl, fnn = _ctl(golden_weights)
+    si, so = golden_weights["scale/scaler_input"], golden_weights["scale/scaler_output"]
+    B, T = 64, 300
+    x0, seg = _inputs(B, T)
+    ref = np.repeat(seg, 150, axis=1)[:, :T]
+    meas_o, u_o = P.closed_loop(fnn, si, so, x0, ref)
+    dev = torch.device("cuda:0")
+    meas, u, xf = fb.closed_loop_device(ctl, torch.tensor(x0, dtype=dtype).to(dev),
+                                        torch.tensor(seg.T.copy(), dtype=dtype).to(dev), 1e-3, si, so,
+                                        substeps=4, steps_per_ref=150)
+    meas = meas.permute(2, 0, 1).double().cpu().numpy()
+    err = np.abs(meas - meas_o) / P.STATE_SCALE
+    # trajectories can separate after a switching event (if_else kinks): bound the bulk tightly, the tail loosely
+    assert np.percentile(err, 99.9) < tol, np.percentile(err, 99.9)
+    assert np.median(err) < tol / 10
+    assert np.abs(u.t().double().cpu().numpy() - u_o).max() < max(tol, 1e-7) * 10
+
+
+def test_one_step_known_answers_from_cvodes_trace(golden_trace, golden_weights):
+    """600 plant steps recorded by the reference simulator: (x[k], u[k]) -> y[k]."""
+    g = golden_trace
+    dev = torch.device("cuda:0")
+    ctl, _ = _ctl(golden_weights)
+    # drive the kernel with the recorded commands: a controller with zero weights saturates at 0, so
+    # instead replay through the loop API from the recorded states with the real controller and T = 1
+    si, so = golden_weights["scale/scaler_input"], golden_weights["scale/scaler_output"]
+    x = torch.tensor(g["x"], dtype=torch.float64).to(dev)
+    ref = torch.tensor(g["tvp"][:, 0][None, :].copy(), dtype=torch.float64).to(dev)
+    meas, u, _ = fb.closed_loop_device(ctl, x, ref, 1e-3, si, so, substeps=4, steps_per_ref=1)
+    # controller known answers (measurement fed to the controller = state y_dot, z): 4.5e-8 in the survey
+    same_inputs = np.ones(600, bool)
+    same_inputs[300] = False      # the reference restarts the second trajectory from the init state
+    du = np.abs(u[0].cpu().numpy() - g["u"][:, 0])
+    assert du[same_inputs].max() < 5e-7
+    err = np.abs(meas[1].t().cpu().numpy() - g["y"]) / P.STATE_SCALE
+    err = err[same_inputs]
+    assert np.median(err) < 5e-7 and np.percentile(err, 99) < 1e-4 and err.max() < 6e-3
+
+
+def test_loop_api_replays_reference_closed_loop(golden_trace, golden_weights):
+    """NeuralNetwork.loop with the reference's arguments (UL/Main.py:676-689) against the shipped
+    closed-loop trace of the same controller (CVODES; RK4 here)."""
+    from sklearn.preprocessing import MaxAbsScaler
+    ctl, _ = _ctl(golden_weights)
+    mk = lambda s: MaxAbsScaler().fit(np.asarray(s)[None, :])
+    scalers = {"input": mk(golden_weights["scale/scaler_input"]), "output": mk(golden_weights["scale/scaler_output"]),
+               "y_dot": mk(golden_weights["scale/scaler_input"][:1])}
+    init = {"y": 0.0, "y_dot": 0.0, "p1": 2156275.6006012624, "p2": 2961363.827545376, "z": 0.0}
+    sim, res, res_lstm, timer, feas = fb.NeuralNetwork.loop(
+        N_traj=2, T_traj=300, Ts=1e-3, controller=ctl.cuda(), simulator=None, simulator_LSTM=None, init_state=init,
+        scalers=scalers, model_scalers=None, bias_work=300, bias_return=20 ** 6, lookback=10, bar_title="NN",
+        process_std=np.zeros(5), meas_std=np.zeros(5))
+    g = golden_trace
+    assert res["y"].shape == (2, 301) and res["u"].shape == (2, 300) and feas == 0.0
+    assert np.array_equal(res["ref"].reshape(-1), g["tvp"][:, 0])
+    y = g["y"].reshape(2, 300, 5)
+    for i, n in enumerate(("y", "y_dot", "p1", "p2", "z")):
+        err = np.abs(res[n][:, 1:] - y[:, :, i]) / P.STATE_SCALE[i]
+        assert err.max() < 2e-2 and np.median(err) < 2e-4, (n, err.max(), np.median(err))
+    assert np.abs(res["u"] - g["u"].reshape(2, 300)).max() < 5e-3
+
+
+def test_large_batch_properties(golden_weights):
+    """1M-trajectory style launch (scaled to fit the test budget): tiled copies give bit-identical
+    trajectories; final state equals the last logged raw state; fp32 and fp64 agree to 1e-4 on the
+    bulk at matched step."""
+    ctl, _ = _ctl(golden_weights)
+    si, so = golden_weights["scale/scaler_input"], golden_weights["scale/scaler_output"]
+    dev = torch.device("cuda:0")
+    B0, reps, T = 256, 1024, 450
+    x0, seg = _inputs(B0, T, seed=99)
+    x0_t = torch.tensor(np.tile(x0, (reps, 1)), dtype=torch.float32).to(dev)
+    seg_t = torch.tensor(np.tile(seg, (reps, 1)).T.copy(), dtype=torch.float32).to(dev)
+    meas, u, xf = fb.closed_loop_device(ctl, x0_t, seg_t, 1e-3, si, so, 4, 150, want_meas=False, want_u=False)
+    assert meas is None and u is None
+    xf = xf.view(reps, B0, 5)
+    assert torch.equal(xf, xf[0:1].expand(reps, B0, 5))
+    m2, u2, xf2 = fb.closed_loop_device(ctl, x0_t[:B0].contiguous(), seg_t[:, :B0].contiguous(), 1e-3, si, so, 4, 150)
+    assert torch.equal(xf2, xf[0])
+    assert torch.equal(m2[-1, 0], xf2[:, 0]) and torch.equal(m2[-1, 4], xf2[:, 4])
+    m64, _, _ = fb.closed_loop_device(ctl, torch.tensor(x0, dtype=torch.float64).to(dev),
+                                      torch.tensor(seg.T.copy(), dtype=torch.float64).to(dev), 1e-3, si, so, 4, 150)
+    err = (m2.double() - m64).abs().permute(2, 0, 1).cpu().numpy() / P.STATE_SCALE
+    assert np.percentile(err, 99) < 1e-4

@@ -1,0 +1,90 @@
+"""CPU: the CUDA kernel SOURCE of the fused MPC loss (forging_control_b200/csrc/fc_mpc_kernel.inl)
+compiled by g++ into a thread-block emulation (tests/emu/fc_emu.cpp: one OS thread per CUDA thread,
+std::barrier for __syncthreads) and checked against the oracle.  This validates tiling, index
+arithmetic and the reverse-sweep dataflow without a GPU; the GPU tests (-m gpu) validate the real
+kernel.  The emulation library is a test artefact and is never loaded by the product package."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mpc_loss_oracle as O
+from conftest import REPO, rel_max, state_dicts
+
+EMU_SRC = os.path.join(REPO, "tests", "emu", "fc_emu.cpp")
+EMU_LIB = os.path.join(REPO, "tests", "emu", "libfc_emu.so")
+DEPS = [EMU_SRC] + [os.path.join(REPO, "forging_control_b200", "csrc", f) for f in ("fc_mpc_kernel.inl", "fc_layout.h")]
+FP = ctypes.POINTER(ctypes.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.isfile(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(d) for d in DEPS):
+        subprocess.run(["g++", "-O2", "-std=c++20", "-shared", "-fPIC", "-pthread", "-o", EMU_LIB, EMU_SRC], check=True)
+    return ctypes.CDLL(EMU_LIB)
+
+
+def _p(a):
+    return a.ctypes.data_as(FP)
+
+
+def _pack(emu, lstm, fnn):
+    names = [("l", "lstm.weight_ih_l0"), ("l", "lstm.weight_hh_l0"), ("l", "lstm.weight_ih_l1"), ("l", "lstm.weight_hh_l1"),
+             ("l", "lstm.weight_ih_l2"), ("l", "lstm.weight_hh_l2"), ("l", "fc.weight"), ("l", "fc.bias"),
+             ("f", "fc_inp.weight"), ("f", "fc_inp.bias"), ("f", "fc_out.weight")]
+    arrs = [np.ascontiguousarray((lstm if s == "l" else fnn)[n], dtype=np.float32) for s, n in names]
+    out = np.zeros(emu.fc_emu_pack_floats(), np.float32)
+    emu.fc_emu_pack_weights(*[_p(a) for a in arrs], _p(out))
+    return out
+
+
+def _run(emu, wp, X, u0, Z, N, alpha, with_grad=1, grid=2, b_global=None):
+    B = len(X)
+    o = {k: np.zeros(B, np.float32) for k in ("cost", "command", "error", "du0")}
+    o["pred"] = np.zeros((B, N), np.float32)
+    o["gl"] = np.zeros(256, np.float32)
+    emu.fc_emu_mpc_loss(_p(X), _p(u0), _p(Z), _p(wp), B, N, ctypes.c_float(alpha),
+                        ctypes.c_longlong(b_global or B), with_grad, grid, _p(o["cost"]), _p(o["command"]),
+                        _p(o["error"]), _p(o["pred"]), _p(o["du0"]), _p(o["gl"]))
+    return o
+
+
+@pytest.mark.parametrize("name", ["n1_b3", "n2_b5", "n5_b16", "n10_b15", "n10_b40_trace", "n12_b130_trace", "n10_b12_wide"])
+def test_emulated_kernel_matches_oracle(emu, golden_cases, golden_weights, name):
+    C = golden_cases
+    N, B, wd = (int(v) for v in C[f"{name}/meta"])
+    lstm, fnn = state_dicts(golden_weights, str(C[f"{name}/ctl"]))
+    wp = _pack(emu, lstm, fnn)
+    X, Z = C[f"{name}/X"], C[f"{name}/Z"]
+    u0 = np.ascontiguousarray(C[f"{name}/f32/u0"])
+    o = _run(emu, wp, X, u0, Z, N, 20.0)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
+    tol = 1e-5
+    assert abs(o["gl"][250] - out["loss"]) / abs(out["loss"]) < tol
+    assert abs(o["gl"][250] - C[f"{name}/f32/loss"]) / abs(C[f"{name}/f32/loss"]) < tol    # the reference itself
+    for k, ok in (("cost", "cost"), ("command", "command"), ("error", "error"), ("pred", "prediction")):
+        assert rel_max(o[k], out[ok]) < tol, k
+    assert rel_max(o["du0"], g["u0"]) < tol
+    assert rel_max(o["gl"][:150].reshape(50, 3), g["inp_w"]) < tol
+    assert rel_max(o["gl"][150:200], g["inp_b"]) < tol
+    assert rel_max(o["gl"][200:250], g["out_w"][0]) < tol
+
+
+def test_emulated_forward_only_and_sharding(emu, golden_cases, golden_weights):
+    """with_grad=0 gives the same forward; two shards with B_global sum to the full-batch result."""
+    C, name = golden_cases, "n5_b16"
+    N, B, wd = (int(v) for v in C[f"{name}/meta"])
+    lstm, fnn = state_dicts(golden_weights, "c0")
+    wp = _pack(emu, lstm, fnn)
+    X, Z, u0 = C[f"{name}/X"], C[f"{name}/Z"], np.ascontiguousarray(C[f"{name}/f32/u0"])
+    full = _run(emu, wp, X, u0, Z, N, 20.0)
+    fwd = _run(emu, wp, X, u0, Z, N, 20.0, with_grad=0)
+    assert np.array_equal(full["cost"], fwd["cost"]) and np.array_equal(full["pred"], fwd["pred"])
+    assert np.all(fwd["gl"][:250] == 0)
+    a = _run(emu, wp, np.ascontiguousarray(X[:9]), np.ascontiguousarray(u0[:9]), np.ascontiguousarray(Z[:9]), N, 20.0, b_global=B)
+    b = _run(emu, wp, np.ascontiguousarray(X[9:]), np.ascontiguousarray(u0[9:]), np.ascontiguousarray(Z[9:]), N, 20.0, b_global=B)
+    assert rel_max(a["gl"][:251] + b["gl"][:251], full["gl"][:251]) < 2e-6
+    assert rel_max(np.concatenate((a["du0"], b["du0"])), full["du0"]) < 1e-6
