@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import logging
 import random
+import weakref
 from time import time
 
 import numpy as np
@@ -139,9 +140,11 @@ def pack_weights(simulator: nn.Module, controller: nn.Module) -> torch.Tensor:
     for w in ws:
         if w.device != dev or w.dtype != torch.float32:
             raise RuntimeError("MPCLoss: all weights must be float32 tensors on the same CUDA device")
-    key = (dev.index, tuple((w.data_ptr(), w._version) for w in ws))
+    # The cache entry is valid only for the very same (still alive) parameter tensors at the same
+    # version: data_ptr alone is not enough, the caching allocator hands freed addresses to new models.
+    key = tuple((w.data_ptr(), w._version) for w in ws)
     slot = _PACK_CACHE.get(dev.index)
-    if slot is not None and slot[0] == key:
+    if slot is not None and slot[0] == key and all(r() is w for r, w in zip(slot[2], ws)):
         return slot[1]
     L = _native.lib()
     buf = slot[1] if slot is not None else torch.empty(int(L.fc_pack_floats()), dtype=torch.float32, device=dev)
@@ -149,7 +152,7 @@ def pack_weights(simulator: nn.Module, controller: nn.Module) -> torch.Tensor:
     with torch.cuda.device(dev):
         rc = L.fc_pack_weights(*[_native.ptr(w) for w in ws_c], _native.ptr(buf), _native.stream_ptr(dev))
     _native.check(rc, "fc_pack_weights")
-    _PACK_CACHE[dev.index] = (key, buf)
+    _PACK_CACHE[dev.index] = (key, buf, [weakref.ref(w) for w in ws])
     return buf
 
 
