@@ -28,9 +28,10 @@ constexpr float kP1Max = 2.122366f;   // Functions.py:1411
 constexpr float kP2Max = 1.036233f;
 
 // ---- CTA tiling ---------------------------------------------------------------------------------
-// 256 threads = 8 warps.  In every warp lanes 0..29 are compute lanes: lane = tg*10 + cg with
-// tg in [0,3) (trajectory group of 5) and cg in [0,10) (hidden-unit group of 5 = 20 gate columns).
-// A CTA tile is 8 warps * 3 tg * 5 = 120 trajectories.
+// 256 threads = 8 warps.  In every warp lanes 0..29 are compute lanes: lane = tg*5 + cgl with
+// tg in [0,6) (trajectory block of 5) and cgl in [0,5) (hidden-unit group of 5 = 20 gate columns);
+// warp w covers trajectory blocks (w/2)*6.. and unit groups (w%2)*5..  A CTA tile is 24 trajectory
+// blocks * 5 = 120 trajectories x 10 unit groups.
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kTile = 120;        // trajectories per CTA tile
@@ -48,22 +49,22 @@ FC_HD int plane_of(int traj) {
 // forward:  WF_l[k][cg][q][uu]      k = input feature (ih rows first, then hh), col = cg*20+q*5+uu
 // backward: WB_l[g'][cg][c]         g' = cg_g*20+q*5+uu (same permuted gate order),
 //           layers 1,2: c<5 -> d(input unit cg*5+c), 5<=c<10 -> d(h_prev unit cg*5+c-5), 10,11 pad
-//           layer 0:    c<5 -> d(h_prev unit cg*5+c), c==5 -> d(row feature cg) for cg<5, 6,7 pad
+//           layer 0:    c<5 -> d(h_prev unit cg*5+c), c==5 -> d(row feature cg) for cg<5, 6..11 pad
 constexpr int kKin0 = kFeat, kKin = kHid;
 constexpr int kWF0 = 0;
 constexpr int kWF1 = kWF0 + (kKin0 + kHid) * kGates;   // 11000
 constexpr int kWF2 = kWF1 + (kKin + kHid) * kGates;    // 31000
 constexpr int kWB0 = kWF2 + (kKin + kHid) * kGates;    // 51000
-constexpr int kWB0Stride = 80;                          // 10 cg * 8
+constexpr int kWB0Stride = 120;                         // 10 cg * 12 (same layout as layers 1,2)
 constexpr int kWBStride = 120;                          // 10 cg * 12
-constexpr int kWB1 = kWB0 + kGates * kWB0Stride;        // 67000
-constexpr int kWB2 = kWB1 + kGates * kWBStride;         // 91000
-constexpr int kFCW = kWB2 + kGates * kWBStride;         // 115000  fc.weight [4][50]
-constexpr int kFCB = kFCW + kOut * kHid;                // 115200  fc.bias [4]
-constexpr int kINPW = kFCB + kOut;                      // 115204  fc_inp.weight [50][3]
-constexpr int kINPB = kINPW + kFnnHid * 3;              // 115354  fc_inp.bias [50]
-constexpr int kOUTW = kINPB + kFnnHid;                  // 115404  fc_out.weight [50]
-constexpr int kPackFloats = ((kOUTW + kFnnHid + 3) / 4) * 4;   // 115456
+constexpr int kWB1 = kWB0 + kGates * kWB0Stride;        // 75000
+constexpr int kWB2 = kWB1 + kGates * kWBStride;         // 99000
+constexpr int kFCW = kWB2 + kGates * kWBStride;         // 123000  fc.weight [4][50]
+constexpr int kFCB = kFCW + kOut * kHid;                // 123200  fc.bias [4]
+constexpr int kINPW = kFCB + kOut;                      // 123204  fc_inp.weight [50][3]
+constexpr int kINPB = kINPW + kFnnHid * 3;              // 123354  fc_inp.bias [50]
+constexpr int kOUTW = kINPB + kFnnHid;                  // 123404  fc_out.weight [50]
+constexpr int kPackFloats = ((kOUTW + kFnnHid + 3) / 4) * 4;   // 123456
 constexpr int kSmallFloats = kPackFloats - kFCW;        // 456: fc + fnn block copied to smem
 
 FC_HD int wf_offset(int l) { return l == 0 ? kWF0 : (l == 1 ? kWF1 : kWF2); }
@@ -94,7 +95,7 @@ FC_HD float packed_value(const RawWeights& w, int idx) {
   if (idx < kFCW) {                                     // backward blocks
     int l = idx < kWB1 ? 0 : (idx < kWB2 ? 1 : 2);
     int r = idx - wb_offset(l);
-    int stride = l == 0 ? kWB0Stride : kWBStride, cw = l == 0 ? 8 : 12;
+    int stride = kWBStride, cw = 12;
     int g = r / stride, rem = r - g * stride;
     int cgo = rem / cw, c = rem - cgo * cw;
     int cgg = g / 20, q = (g % 20) / 5, uu = g % 5;

@@ -7,8 +7,8 @@
 // source is compiled (a) by nvcc into the sm_100a kernel and (b) by g++ into the CPU thread
 // emulation used by the CPU test-suite to check the index arithmetic (tests/emu).
 //
-// Thread mapping (see fc_layout.h): lane = tg*10+cg; thread owns trajectories tb*5+j (tb=warp*3+tg,
-// j<5) and hidden units cg*5+uu (uu<5): 25 (trajectory, unit) elements, all four gates of each.
+// Thread mapping (see fc_layout.h): lane = tg*5+cgl; thread owns trajectories tb*5+j (tb=(warp/2)*6+tg,
+// j<5) and hidden units cg*5+uu (cg=(warp%2)*5+cgl, uu<5): 25 (trajectory, unit) elements, all four gates of each.
 //   forward GEMM   acc[5 traj][20 gate cols]  over K = 5|50 (+50 recurrent) with FP32 FFMA
 //   backward GEMM  acc[5 traj][10 cols]       over the 200 gate gradients
 // Cell state c / dc and the recurrent dh stay in registers; h and dGates are exchanged through
@@ -45,9 +45,13 @@ struct MpcTile {
     lane = tid & 31;
     act = lane < 30;
     int l2 = act ? lane : lane - 30;   // idle lanes shadow lanes 0,1 (loads only, never store)
-    tg = l2 / 10;
-    cg = l2 - tg * 10;
-    tb = warp * 3 + tg;
+    // warp = 6 trajectory blocks x 5 unit groups (4 x 2 warps cover 24 x 10): per k-step a warp reads
+    // 30 activations and 100 weights.  Measured on B200 (scripts/micro/lds_bench.cu): an LDS.128 whose
+    // lanes touch <= 8 distinct 16-byte chunks without bank overlap costs ~2 SM cycles, the previous
+    // 3 x 10 arrangement (10 chunks at an 80-byte stride) 3.5 cycles and made the kernel smem-bound.
+    tg = l2 / 5;                       // trajectory block within the warp, 0..5
+    cg = (warp & 1) * 5 + (l2 - tg * 5);
+    tb = (warp >> 1) * 6 + tg;
     WorkLayout wl = work_layout(p.N, p.with_grad);
     float* base = p.work + (size_t)ctx.bid() * p.work_stride;
     rows = base + wl.rows;
@@ -298,7 +302,7 @@ struct MpcTile {
       float a5 = a1p[g * kTile];
       float w[CW];
 #pragma unroll
-      for (int i = 0; i < CW / 4; ++i) {
+      for (int i = 0; i < (NC + 3) / 4; ++i) {
         F4 t = Ctx::lds4(wp + g * stride + i * 4);
         w[i * 4 + 0] = t.x; w[i * 4 + 1] = t.y; w[i * 4 + 2] = t.z; w[i * 4 + 3] = t.w;
       }
@@ -465,7 +469,7 @@ struct MpcTile {
     bwd_glue(tile, m);                                // ends after a barrier-protected smem write phase
     for (int l = kLayers - 1; l >= 0; --l) {
       ctx.sync();                                     // previous GEMM done with W and G
-      const int wn = kGates * (l == 0 ? kWB0Stride : kWBStride);
+      const int wn = kGates * kWBStride;
       copy_async(W, p.wpack + wb_offset(l), wn);
       Ctx::cp_commit();
 #pragma unroll
@@ -496,7 +500,7 @@ struct MpcTile {
           for (int j = 0; j < 5; ++j)
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) acc[j][cc] = 0.f;
-          bwd_gemm<8, 6>(acc, G, W);
+          bwd_gemm<12, 6>(acc, G, W);
 #pragma unroll
           for (int e = 0; e < kElems; ++e) hrec[e] = acc[e % 5][e / 5];
           const int kr = m + t - (kLook - 1);         // gradient of row rho_{9+kr}

@@ -88,13 +88,23 @@ def test_native_call_matches_fp64_oracle(dev, golden_weights, N, B, tag):
     d = np.abs(r["du0"].cpu().numpy() - g["u0"]) / np.abs(g["u0"]).max()
     n_flip = int((d > TOL).sum())
     assert n_flip <= 5e-4 * B, (n_flip, d.max())
-    # a flipped trajectory moves the batch-summed gradients by O(1/B) of a per-trajectory gradient, which
-    # can exceed 1e-5 of the (partly cancelling) sum: widen the bound only when a flip was observed.
-    # (measured: torch float32 vs float64 shows the same effect; scripts/diag_precision.py)
-    tol_sum = TOL if n_flip == 0 else 1e-4
-    assert rel_max(gl[:150].reshape(50, 3), g["inp_w"]) < tol_sum
-    assert rel_max(gl[150:200], g["inp_b"]) < tol_sum
-    assert rel_max(gl[200:250], g["out_w"][0]) < tol_sum
+    if n_flip:
+        # A flipped trajectory moves the batch-summed gradients by O(1/B) of a per-trajectory gradient,
+        # which can exceed 1e-5 of the (partly cancelling) sums -- torch float32 vs float64 shows the same
+        # effect (scripts/diag_precision.py).  Remove the flipped trajectories from BOTH sides: the kernel
+        # is re-run without them, the oracle sums are corrected by linearity (sum_b = B * mean_b).
+        keep = d <= TOL
+        B2 = int(keep.sum())
+        kt = torch.tensor(keep)
+        r = fb.mpc_loss_native(wp, X[kt].contiguous().to(dev), torch.tensor(u0[keep], dtype=torch.float32).to(dev),
+                               Z[kt].contiguous().to(dev), N, ALPHA, True)
+        gl = r["gl"].cpu().numpy()
+        _, gf = O.mpc_loss_forward_backward(w, X[~kt].double().numpy(), u0[~keep].astype(np.float32).astype(np.float64),
+                                            Z[~kt].double().numpy(), N, ALPHA)
+        g = {k: (g[k] * B - gf[k] * n_flip) / B2 for k in ("inp_w", "inp_b", "out_w")}
+    assert rel_max(gl[:150].reshape(50, 3), g["inp_w"]) < TOL
+    assert rel_max(gl[150:200], g["inp_b"]) < TOL
+    assert rel_max(gl[200:250], g["out_w"][0]) < TOL
     assert np.all(gl[251:] == 0)
 
 
