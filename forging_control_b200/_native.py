@@ -15,13 +15,13 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libforging_b200.so")
 SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in
-           ("fc_api.cu", "fc_mpc_kernel.inl", "fc_layout.h", "fc_plant.cuh")]
+           ("fc_api.cu", "fc_mpc_kernel.inl", "fc_layout.h", "fc_plant.cuh", "fc_mpc_tc_kernel.inl", "fc_tc_layout.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 # every symbol include/forging_b200.h declares
 EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
-           "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_closed_loop_rk4",
+           "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_closed_loop_rk4",
            "fc_closed_loop_rk4_f64", "fc_fp32_peak")
 
 _c_float_p = ctypes.c_void_p   # raw device pointers are passed as integers
@@ -64,6 +64,8 @@ def lib() -> ctypes.CDLL:
     L.fc_pack_weights.argtypes = [vp] * 12 + [vp]
     L.fc_mpc_loss_workspace_bytes.restype = sz
     L.fc_mpc_loss_workspace_bytes.argtypes = [i32, i32, i32]
+    L.fc_mpc_select_kernel.restype = i32
+    L.fc_mpc_select_kernel.argtypes = [i32]
     L.fc_mpc_loss.restype = i32
     L.fc_mpc_loss.argtypes = [vp, vp, vp, vp, i32, i32, f32, i64, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.fc_closed_loop_rk4.restype = i32

@@ -146,7 +146,8 @@ FC_HD WorkLayout work_layout(int N, int with_grad) {
   return w;
 }
 
-// per-CTA partial results: controller gradients then loss sum
+// per-CTA partial results (double precision: the batch reductions are cancellation-heavy): controller
+// gradients then loss sum
 constexpr int kNumFnnGrad = 250;            // inp_w[150] | inp_b[50] | out_w[50]
 constexpr int kPartialStride = 256;         // [0..249] grads, [250] sum of per-trajectory cost
 
@@ -160,8 +161,9 @@ constexpr int kSmCost = kSmUprev + kTile;                 // [3][120] cost, comm
 constexpr int kSmGx = kSmCost + 3 * kTile;                // [4][120] d loss / d x_{m+1} (plane layout)
 constexpr int kSmDv = kSmGx + 4 * kTile;                  // [120] d loss / d v (pre-saturation command)
 constexpr int kSmFin = kSmDv + kTile;                     // [2][120] controller inputs x[0], x[3]
-constexpr int kSmPg = kSmFin + 2 * kTile;                 // [4][250] controller gradient partials
-constexpr int kSmRed = kSmPg + 4 * kNumFnnGrad;           // [8] scratch
+constexpr int kSmPg = kSmFin + 2 * kTile;                 // double [4][250] controller gradient partials (8-byte aligned)
+constexpr int kSmRed = kSmPg + 8 * kNumFnnGrad;           // double [4] scratch (loss sum)
+static_assert(kSmPg % 2 == 0, "double alignment");
 constexpr int kSmBig = ((kSmRed + 8 + 3) / 4) * 4;        // start of the phase-dependent area
 // forward: W [100][200] | ain [2][50][120] | ah [2][50][120]
 constexpr int kSmFwdW = kSmBig;
@@ -186,7 +188,7 @@ struct MpcParams {
   float* error;          // [B]
   float* pred;           // [B][N]
   float* du0;            // [B] d loss / d u0 (with_grad)
-  float* partial;        // [grid][kPartialStride]
+  double* partial;       // [grid][kPartialStride]
   float* work;           // [grid][work_stride]
   size_t work_stride;    // floats
   int B;
@@ -195,6 +197,7 @@ struct MpcParams {
   int num_tiles;
   float alpha;
   float grad_scale;      // 1 / (N * B_global)
+  float acc_comp;        // scale of the tensor-core accumulator compensation (1 = calibrated value)
 };
 
 }  // namespace fc

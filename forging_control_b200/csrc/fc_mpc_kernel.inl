@@ -65,7 +65,18 @@ struct MpcTile {
   // helpers
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX static float sigmoidf_(float x) { return Ctx::rcp(1.f + Ctx::ex2(-1.4426950408889634f * x)); }
-  FC_HD_CTX static float tanhf_(float x) { return 1.f - 2.f * Ctx::rcp(1.f + Ctx::ex2(2.8853900817779268f * x)); }
+  // tanh: 1 - 2/(1+e^{2x}) has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is a large
+  // relative error for the small gate / cell values that dominate here; below |x| = 0.3 use the odd
+  // Taylor polynomial (relative error < 2e-8) instead.  Branch-free select.
+  FC_HD_CTX static float tanhf_(float x) {
+    const float big = 1.f - 2.f * Ctx::rcp(1.f + Ctx::ex2(2.8853900817779268f * x));
+    const float x2 = x * x;
+    float pl = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);
+    pl = fmaf(x2, pl, 0.13333333333333333f);
+    pl = fmaf(x2, pl, -0.33333333333333331f);
+    pl = fmaf(x2 * x, pl, x);
+    return fabsf(x) < 0.3f ? pl : big;
+  }
 
   // cooperative global -> shared copy of n floats (n % 4 == 0, 16-byte aligned both sides)
   FC_HD_CTX void copy_async(float* dst, const float* src, int n) {
@@ -437,20 +448,20 @@ struct MpcTile {
     ctx.sync();
     if (has_u && tid < 4 * kFnnHid) {                  // controller weight gradients, unit-parallel
       const int u = tid % kFnnHid, part = tid / kFnnHid;
-      float a_ow = 0.f, a_b = 0.f, a_w0 = 0.f, a_w1 = 0.f, a_w2 = 0.f;
+      double a_ow = 0.0, a_b = 0.0, a_w0 = 0.0, a_w1 = 0.0, a_w2 = 0.0;   // batch sums cancel heavily: fp64
       const float w0 = iw[u * 3 + 0], w1 = iw[u * 3 + 1], w2 = iw[u * 3 + 2], bb = ib[u], owu = ow[u];
       for (int traj = part * 30; traj < part * 30 + 30; ++traj) {
         float dv = sm[kSmDv + traj];
         float x0 = sm[kSmFin + traj], x3 = sm[kSmFin + kTile + traj], ref = sm[kSmRef + traj];
         float pre = fmaf(w2, ref, fmaf(w1, x3, fmaf(w0, x0, bb)));
-        a_ow = fmaf(dv, fmaxf(pre, 0.f), a_ow);
+        a_ow += (double)dv * (double)fmaxf(pre, 0.f);
         float dp = pre > 0.f ? dv * owu : 0.f;
         a_b += dp;
-        a_w0 = fmaf(dp, x0, a_w0);
-        a_w1 = fmaf(dp, x3, a_w1);
-        a_w2 = fmaf(dp, ref, a_w2);
+        a_w0 += (double)dp * (double)x0;
+        a_w1 += (double)dp * (double)x3;
+        a_w2 += (double)dp * (double)ref;
       }
-      float* pg = sm + kSmPg + part * kNumFnnGrad;
+      double* pg = reinterpret_cast<double*>(sm + kSmPg) + part * kNumFnnGrad;
       pg[u * 3 + 0] += a_w0;
       pg[u * 3 + 1] += a_w1;
       pg[u * 3 + 2] += a_w2;
@@ -536,9 +547,9 @@ struct MpcTile {
     }
     ctx.sync();
     if (tid == 0) {
-      float acc = 0.f;
-      for (int i = 0; i < kTile; ++i) acc += sm[kSmCost + i];
-      sm[kSmRed] += acc;
+      double acc = 0.0;
+      for (int i = 0; i < kTile; ++i) acc += (double)sm[kSmCost + i];
+      *reinterpret_cast<double*>(sm + kSmRed) += acc;
     }
   }
 
@@ -566,8 +577,8 @@ struct MpcTile {
   FC_HD_CTX void run() {
     copy_async(sm + kSmSmall, p.wpack + kFCW, kSmallFloats);
     Ctx::cp_commit();
-    for (int i = tid; i < 4 * kNumFnnGrad; i += kThreads) sm[kSmPg + i] = 0.f;
-    if (tid == 0) sm[kSmRed] = 0.f;
+    for (int i = tid; i < 4 * kNumFnnGrad; i += kThreads) reinterpret_cast<double*>(sm + kSmPg)[i] = 0.0;
+    if (tid == 0) *reinterpret_cast<double*>(sm + kSmRed) = 0.0;
     Ctx::template cp_wait<0>();
     ctx.sync();
     for (int tile = ctx.bid(); tile < p.num_tiles; tile += ctx.nblk()) {
@@ -587,10 +598,11 @@ struct MpcTile {
       ctx.sync();
     }
     // per-CTA partial results
-    float* part = p.partial + (size_t)ctx.bid() * kPartialStride;
+    double* part = p.partial + (size_t)ctx.bid() * kPartialStride;
+    const double* pgd = reinterpret_cast<const double*>(sm + kSmPg);
     for (int i = tid; i < kNumFnnGrad; i += kThreads)
-      part[i] = (sm[kSmPg + i] + sm[kSmPg + kNumFnnGrad + i]) + (sm[kSmPg + 2 * kNumFnnGrad + i] + sm[kSmPg + 3 * kNumFnnGrad + i]);
-    if (tid == 0) part[kNumFnnGrad] = sm[kSmRed];
+      part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
+    if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRed);
   }
 };
 

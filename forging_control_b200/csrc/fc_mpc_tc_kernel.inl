@@ -1,0 +1,643 @@
+// tcgen05 (3xTF32) variant of the fused MPC-loss forward + reverse sweep.  Same mathematics and the
+// same reference citations as fc_mpc_kernel.inl (MPCLoss.forward Functions.py:1353-1472,
+// LSTMModel.forward :353-379, FNNModel.forward :261-289, loss.backward() :655); what changes is where the
+// 99.9 % of the FLOPs run: the per-step gate contraction [128 trajectories x K] x [K x 200 gates] is a
+// real dense GEMM, so it goes to the 5th-generation tensor cores:
+//   * weights: tf32 hi/lo images resident in shared memory (B operand, K-major, no swizzle)
+//   * activations (A operand, hi/lo) and the fp32 accumulator live in TMEM, one trajectory per lane
+//   * error-compensated split  a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (same error as an fp32 FMA chain)
+//   * the thread that owns TMEM lane r does the cell update of trajectory r: no cross-thread exchange
+// Written against the same execution-context interface as the FFMA kernel (+ TMEM / MMA / mbarrier
+// operations) so that g++ can compile it into the CPU thread emulation of tests/emu.
+#pragma once
+#include "fc_tc_layout.h"
+
+namespace fc {
+namespace tc {
+
+template <class Ctx>
+struct MpcTileTC {
+  Ctx& ctx;
+  const MpcParams& p;
+  float* sm;
+  int tid, warp, lane, row, half, u_first;
+  float *rows, *seq, *dseq, *grow, *rec;
+  float c[kMaxOwn];      // forward: cell state, backward: d(cell state)
+  float hrec[kMaxOwn];   // backward: d(h) from step t+1
+  unsigned ph[8];        // completed phases per mbarrier
+
+  FC_HD_CTX MpcTileTC(Ctx& c_, const MpcParams& p_) : ctx(c_), p(p_) {
+    sm = ctx.smem();
+    tid = ctx.tid();
+    warp = tid >> 5;
+    lane = tid & 31;
+    row = 32 * (warp & 3) + lane;
+    half = warp >> 2;
+    u_first = half == 0 ? 0 : kUnits0;
+    WorkLayoutTC wl = work_layout_tc(p.N, p.with_grad);
+    float* base = p.work + (size_t)ctx.bid() * p.work_stride;
+    rows = base + wl.rows;
+    seq = base + wl.seq;
+    dseq = base + wl.dseq;
+    grow = base + wl.grow;
+    rec = base + wl.rec;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ph[i] = 0;
+  }
+
+  FC_HD_CTX static float sigmoidf_(float x) { return Ctx::rcp(1.f + Ctx::ex2(-1.4426950408889634f * x)); }
+  // tanh: 1 - 2/(1+e^{2x}) has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is a large
+  // relative error for the small gate / cell values that dominate here; below |x| = 0.3 use the odd
+  // Taylor polynomial (relative error < 2e-8) instead.  Branch-free select.
+  FC_HD_CTX static float tanhf_(float x) {
+    const float big = 1.f - 2.f * Ctx::rcp(1.f + Ctx::ex2(2.8853900817779268f * x));
+    const float x2 = x * x;
+    float pl = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);
+    pl = fmaf(x2, pl, 0.13333333333333333f);
+    pl = fmaf(x2, pl, -0.33333333333333331f);
+    pl = fmaf(x2 * x, pl, x);
+    return fabsf(x) < 0.3f ? pl : big;
+  }
+
+  FC_HD_CTX void wait_bar(int b) { ctx.bar_wait(b, ph[b]); ph[b] += 1; }
+
+  // hi/lo split and store of N consecutive A-operand columns of the own lane
+  template <int N>
+  FC_HD_CTX void st_split(int col_hi, int col_lo, const float* v) {
+    float hi[N], lo[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      hi[i] = Ctx::tf32(v[i]);
+      lo[i] = Ctx::tf32(v[i] - hi[i]);      // rounded (the MMA would truncate): unbiased, half the error
+    }
+    ctx.template tmem_st<N>(col_hi, hi);
+    ctx.template tmem_st<N>(col_lo, lo);
+  }
+  template <int NOWN>
+  FC_HD_CTX void st_own(int col_hi, int col_lo, const float* v) {   // NOWN = 24 or 26 columns
+    st_split<16>(col_hi, col_lo, v);
+    st_split<8>(col_hi + 16, col_lo + 16, v + 16);
+    if constexpr (NOWN == 26) st_split<2>(col_hi + 24, col_lo + 24, v + 24);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // operand images
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void request_weights(bool bwd, int l) {          // tid 0 only
+    const int n = 2 * (bwd ? bwd_img_floats(l) : fwd_img_floats(l));
+    ctx.bulk_load(sm + kSmWTC, p.wpack + (bwd ? wb_off(l) : wf_off(l)), n, kBarWeights);
+  }
+
+  // one accumulator chunk: 3 error-compensated terms, small ones first (tid 0 only)
+  FC_HD_CTX void issue_chunk(int d_col, int n, int n_img, int row0, int a_hi, int a_lo, int ksteps, int img_floats, int bar) {
+    const float* b_hi = sm + kSmWTC;
+    const float* b_lo = b_hi + img_floats;
+    ctx.mma(d_col, n, a_lo, b_hi, n_img, row0, ksteps, false);
+    ctx.mma(d_col, n, a_hi, b_lo, n_img, row0, ksteps, true);
+    ctx.mma(d_col, n, a_hi, b_hi, n_img, row0, ksteps, true);
+    ctx.commit(bar);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // tile set-up
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void load_tile(int tile) {
+    const int b = tile * kTileTC + row;
+    const bool ok = b < p.B;
+    if (half == 0) {
+      for (int r = 0; r < kLook; ++r)
+#pragma unroll
+        for (int f = 0; f < kFeat; ++f) {
+          float v = ok ? p.Z[(size_t)b * (kLook * kFeat) + r * kFeat + f] : 0.f;
+          if (r == kLook - 1 && f == kFeat - 1) v = ok ? p.u0[b] : 0.f;              // Functions.py:1396
+          rows[(size_t)(r * kFeat + f) * kTileTC + row] = v;
+        }
+      sm[kSmRefTC + row] = ok ? p.X[(size_t)b * 3 + 2] : 0.f;                        // :1392
+      sm[kSmUcurTC + row] = ok ? p.u0[b] : 0.f;
+      sm[kSmUprevTC + row] = ok ? p.Z[(size_t)b * (kLook * kFeat) + (kLook - 2) * kFeat + 4] : 0.f;
+      sm[kSmCostTC + row] = 0.f;
+      sm[kSmCostTC + kTileTC + row] = 0.f;
+      sm[kSmCostTC + 2 * kTileTC + row] = 0.f;
+      if (ok) p.pred[(size_t)b * p.N] = p.u0[b];                                     // :1417-1418
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // forward: cell update of `nu` units starting at owned index j0 from 4*nu accumulator columns
+  // ---------------------------------------------------------------------------------------------
+  template <int NU>
+  FC_HD_CTX void fwd_units(int j0, const float* g, bool first, float* h, float* rp, int r0) {
+    float rv[NU * 5 + 3];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      float gi = sigmoidf_(g[i * 4 + 0]);
+      float gf = sigmoidf_(g[i * 4 + 1]);
+      float gg = tanhf_(g[i * 4 + 2]);
+      float go = sigmoidf_(g[i * 4 + 3]);
+      float cp = first ? 0.f : c[j0 + i];
+      float cn = fmaf(gf, cp, gi * gg);
+      c[j0 + i] = cn;
+      h[j0 + i] = go * tanhf_(cn);
+      rv[i * 5 + 0] = gi; rv[i * 5 + 1] = gf; rv[i * 5 + 2] = gg; rv[i * 5 + 3] = go; rv[i * 5 + 4] = cp;
+    }
+    if (rp) {
+#pragma unroll
+      for (int i = NU * 5; i < NU * 5 + 3; ++i) rv[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < (NU * 5 + 3) / 4; ++r) {
+        F4 v = {rv[r * 4], rv[r * 4 + 1], rv[r * 4 + 2], rv[r * 4 + 3]};
+        Ctx::stg4_stream(rp + (size_t)(r0 + r) * 32 * 4, v);
+      }
+    }
+  }
+
+  // all owned units of one step; waits for the accumulator chunks it needs
+  template <int HALF>
+  FC_HD_CTX void fwd_pointwise(bool first, float corr, float* h, float* rec_out) {
+    float* rp = rec_out ? rec_out + ((size_t)warp * 33 * 32 + lane) * 4 : nullptr;
+    constexpr int col0 = HALF == 0 ? 0 : kUnits0 * 4;
+    constexpr int NG = 6;                                  // groups of 4 units
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      if (HALF == 0) {
+        if (gi == 0) wait_bar(kBarChunk0 + 0);             // A0: units 0..11
+        if (gi == 3) wait_bar(kBarChunk0 + 2);             // A1: units 12..23
+      } else {
+        if (gi == 0) wait_bar(kBarChunk0 + 1);             // B0: units 24..39
+        if (gi == 4) wait_bar(kBarChunk0 + 3);             // B1: units 40..49
+      }
+      float g[16];
+      ctx.template tmem_ld<16>(kColD + col0 + gi * 16, g);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[i] = fmaf(g[i], corr, g[i]);
+      fwd_units<4>(gi * 4, g, first, h, rp, gi * 5);
+    }
+    if (HALF == 1) {
+      float g[8];
+      ctx.template tmem_ld<8>(kColD + col0 + NG * 16, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], corr, g[i]);
+      fwd_units<2>(NG * 4, g, first, h, rp, NG * 5);
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // forward window
+  // ---------------------------------------------------------------------------------------------
+  template <int HALF>
+  FC_HD_CTX void fwd_window(int tile, int m, bool more_after) {
+    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
+    const int tmin = t_min_of(m);
+    for (int l = 0; l < kLayers; ++l) {
+      const int kf = kf_of(l), rec0 = l == 0 ? kRec0 : kRec;
+      float h[kMaxOwn], xin[kMaxOwn];
+      // A(0): zero recurrent columns and padding, input of step 0
+      {
+        float z[kMaxOwn];
+#pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) z[i] = 0.f;
+        ctx.template tmem_st<16>(kColAhi + rec0 + u_first, z);
+        ctx.template tmem_st<8>(kColAhi + rec0 + u_first + 16, z);
+        ctx.template tmem_st<16>(kColAlo + rec0 + u_first, z);
+        ctx.template tmem_st<8>(kColAlo + rec0 + u_first + 16, z);
+        if (HALF == 1) {
+          ctx.template tmem_st<2>(kColAhi + rec0 + u_first + 24, z);
+          ctx.template tmem_st<2>(kColAlo + rec0 + u_first + 24, z);
+          // padding columns behind the recurrent block: layer 0 -> [58,64), layers 1,2 -> [100,104)
+          if (l == 0) {
+            ctx.template tmem_st<4>(kColAhi + 58, z); ctx.template tmem_st<2>(kColAhi + 62, z);
+            ctx.template tmem_st<4>(kColAlo + 58, z); ctx.template tmem_st<2>(kColAlo + 62, z);
+          } else {
+            ctx.template tmem_st<4>(kColAhi + 100, z);
+            ctx.template tmem_st<4>(kColAlo + 100, z);
+          }
+        }
+      }
+      load_input<HALF>(l, m, 0, xin);
+      store_input<HALF>(l, xin);
+      ctx.tmem_st_wait();
+      wait_bar(kBarWeights);                               // operand image of this layer landed
+      ctx.tc_sync();
+      for (int t = 0; t < kLook; ++t) {
+        if (tid == 0) {
+          const int imgf = fwd_img_floats(l);
+#pragma unroll 1
+          for (int ck = 0; ck < kNumChunks; ++ck)
+            issue_chunk(kColD + chunk_col(ck), chunk_n(ck), kNF, chunk_col(ck), kColAhi, kColAlo, kf / 8, imgf, kBarChunk0 + ck);
+        }
+        if (t + 1 < kLook) load_input<HALF>(l, m, t + 1, xin);
+        float* rec_out = nullptr;
+        if (p.with_grad && t >= tmin) rec_out = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
+        // accumulation steps that add non-zero blocks: at t = 0 the recurrent columns are zero
+        const float corr = Ctx::kAccTruncates ? acc_correction(t == 0 ? (l == 0 ? 1 : 7) : kf / 8, p.acc_comp) : 0.0f;
+        fwd_pointwise<HALF>(t == 0, corr, h, rec_out);
+        // every MMA of this step must have completed before A is overwritten / the image is replaced
+        if (HALF == 0) { wait_bar(kBarChunk0 + 1); wait_bar(kBarChunk0 + 3); }
+        else           { wait_bar(kBarChunk0 + 0); wait_bar(kBarChunk0 + 2); }
+        if (t == kLook - 1 && tid == 0) {
+          if (l + 1 < kLayers) request_weights(false, l + 1);
+          else if (m + 1 < p.N) request_weights(false, 0);
+          else if (p.with_grad) request_weights(true, kLayers - 1);
+          else if (more_after) request_weights(false, 0);
+        }
+        if (l + 1 < kLayers) {
+          float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < NOWN; ++j) sq[j * 32] = h[j];
+        }
+        if (t + 1 < kLook) {
+          store_input<HALF>(l, xin);
+          st_own<NOWN>(kColAhi + rec0 + u_first, kColAlo + rec0 + u_first, h);
+          ctx.tmem_st_wait();
+        } else if (l == kLayers - 1) {
+          // read-out partial sums over the owned units (Functions.py:377)
+          const float* fw = sm + kSmSmallTC;
+          float xq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < NOWN; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xq[q] = fmaf(fw[q * kHid + u_first + j], h[j], xq[q]);
+          if (HALF == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sm[kSmFcpTC + q * kTileTC + row] = xq[q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hrec[q] = xq[q];   // parked until the barrier below
+          }
+        }
+        ctx.tc_sync();
+      }
+    }
+    if (HALF == 0) fwd_glue(tile, m);
+    ctx.sync();
+  }
+
+  // input of (layer l, step t) for the owned columns: layer 0 -> 5 row features (half 0 only)
+  template <int HALF>
+  FC_HD_CTX void load_input(int l, int m, int t, float* xin) {
+    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
+    if (l == 0) {
+      if (HALF == 0) {
+        const float* rp = rows + (size_t)(m + t) * kFeat * kTileTC + row;
+#pragma unroll
+        for (int f = 0; f < kFeat; ++f) xin[f] = Ctx::ldcg(rp + f * kTileTC);
+      }
+    } else {
+      const float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) xin[j] = Ctx::ldcg(sq + j * 32);
+    }
+  }
+  template <int HALF>
+  FC_HD_CTX void store_input(int l, const float* xin) {
+    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
+    if (l == 0) {
+      if (HALF == 0) {
+        float v[8] = {xin[0], xin[1], xin[2], xin[3], xin[4], 0.f, 0.f, 0.f};
+        st_split<8>(kColAhi, kColAlo, v);
+      }
+    } else {
+      st_own<NOWN>(kColAhi + u_first, kColAlo + u_first, xin);
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // after window m (half-0 thread of each trajectory): read-out, cost terms, next command
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void fwd_glue(int tile, int m) {
+    const float* sw = sm + kSmSmallTC;
+    float x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = (hrec[q] + sm[kSmFcpTC + q * kTileTC + row]) + sw[(kFCB - kFCW) + q];
+    const float ref = sm[kSmRefTC + row];
+    const float ucur = sm[kSmUcurTC + row], uprev = sm[kSmUprevTC + row];
+    float du = uprev - ucur;
+    float cmd = p.alpha * du * du;                                             // :1405 / :1446
+    float er = (x[0] - ref) * (x[0] - ref);                                    // :1408 / :1443
+    float con = fmaxf(-x[1], 0.f) + fmaxf(-x[2], 0.f) + fmaxf(x[1] - kP1Max, 0.f) + fmaxf(x[2] - kP2Max, 0.f);
+    sm[kSmCostTC + row] += (er + cmd) + con;                                   // :1414 / :1452
+    sm[kSmCostTC + kTileTC + row] += cmd;
+    sm[kSmCostTC + 2 * kTileTC + row] += er;
+    float* rnew = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;          // rho_{10+m} = [x_{m+1}, u_{m+1}]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rnew[q * kTileTC] = x[q];
+    float unext = 0.f;
+    if (m + 1 < p.N) {                                                         // :1424-1430
+      const float* iw = sw + (kINPW - kFCW);
+      const float* ib = sw + (kINPB - kFCW);
+      const float* ow = sw + (kOUTW - kFCW);
+      float v = 0.f;
+      for (int u = 0; u < kFnnHid; ++u) {
+        float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x[3], fmaf(iw[u * 3 + 0], x[0], ib[u])));
+        v = fmaf(ow[u], fmaxf(pre, 0.f), v);
+      }
+      unext = fminf(fmaxf(v, -1.f), 1.f);                                      // nn.Hardtanh
+      sm[kSmUprevTC + row] = ucur;
+      sm[kSmUcurTC + row] = unext;
+      int b = tile * kTileTC + row;
+      if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;                    // :1455
+    }
+    rnew[4 * kTileTC] = unext;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // backward: gate gradients of the owned units -> dG columns (A operand) in TMEM
+  // ---------------------------------------------------------------------------------------------
+  template <int NU>
+  FC_HD_CTX void bwd_units(int j0, const float* rp, int r0, bool top, bool last_step, const float* gxv, const float* dsq, int col) {
+    float rv[NU * 5 + 3];
+#pragma unroll
+    for (int r = 0; r < (NU * 5 + 3) / 4; ++r) {
+      F4 v = Ctx::ldg4_stream(rp + (size_t)(r0 + r) * 32 * 4);
+      rv[r * 4] = v.x; rv[r * 4 + 1] = v.y; rv[r * 4 + 2] = v.z; rv[r * 4 + 3] = v.w;
+    }
+    float dg[NU * 4];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const int j = j0 + i;
+      float gi = rv[i * 5 + 0], gf = rv[i * 5 + 1], gg = rv[i * 5 + 2], go = rv[i * 5 + 3], cp = rv[i * 5 + 4];
+      float cn = fmaf(gf, cp, gi * gg);
+      float tch = tanhf_(cn);
+      float dh = hrec[j];
+      if (top) {
+        if (last_step) {                                   // through fc (Functions.py:377)
+          const float* fw = sm + kSmSmallTC + u_first + j;
+          dh += fw[0] * gxv[0] + fw[kHid] * gxv[1] + fw[2 * kHid] * gxv[2] + fw[3 * kHid] * gxv[3];
+        }
+      } else {
+        dh += Ctx::ldcg(dsq + j * 32);
+      }
+      float dout = dh * tch;
+      float dct = fmaf(dh * go, 1.f - tch * tch, c[j]);
+      float di = dct * gg, dgg = dct * gi, df = dct * cp;
+      c[j] = dct * gf;
+      dg[i * 4 + 0] = di * gi * (1.f - gi);
+      dg[i * 4 + 1] = df * gf * (1.f - gf);
+      dg[i * 4 + 2] = dgg * (1.f - gg * gg);
+      dg[i * 4 + 3] = dout * go * (1.f - go);
+    }
+    st_split<NU * 4>(kColGhi + col, kColGlo + col, dg);
+  }
+
+  template <int HALF>
+  FC_HD_CTX void bwd_pointwise(int l, int t, const float* rec_in, const float* dseq_in) {
+    const float* rp = rec_in + ((size_t)warp * 33 * 32 + lane) * 4;
+    const float* dsq = dseq_in + (size_t)warp * kMaxOwn * 32 + lane;
+    const bool top = l == kLayers - 1, last = t == kLook - 1;
+    float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (top && last) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxTC + q * kTileTC + row];
+    }
+    constexpr int col0 = HALF == 0 ? 0 : kUnits0 * 4;
+#pragma unroll
+    for (int gi = 0; gi < 6; ++gi) bwd_units<4>(gi * 4, rp, gi * 5, top, last, gxv, dsq, col0 + gi * 16);
+    if (HALF == 1) bwd_units<2>(24, rp, 30, top, last, gxv, dsq, col0 + 96);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // before the reverse sweep of window m (half-0 thread per trajectory + 200 accumulation threads)
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void bwd_glue(int tile, int m) {
+    const int k = m + 1;
+    const float s = p.grad_scale;
+    const bool has_u = k <= p.N - 1;
+    const float* sw = sm + kSmSmallTC;
+    const float* iw = sw + (kINPW - kFCW);
+    const float* ib = sw + (kINPB - kFCW);
+    const float* ow = sw + (kOUTW - kFCW);
+    if (half == 0) {
+      const bool valid = tile * kTileTC + row < p.B;
+      const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;
+      float x0 = Ctx::ldcg(rx), x1 = Ctx::ldcg(rx + kTileTC), x2 = Ctx::ldcg(rx + 2 * kTileTC), x3 = Ctx::ldcg(rx + 3 * kTileTC);
+      const float ref = sm[kSmRefTC + row];
+      float g0 = 2.f * (x0 - ref) * s;
+      float g1 = s * ((x1 > kP1Max ? 1.f : 0.f) - (x1 < 0.f ? 1.f : 0.f));
+      float g2 = s * ((x2 > kP2Max ? 1.f : 0.f) - (x2 < 0.f ? 1.f : 0.f));
+      float g3 = 0.f;
+      float dv = 0.f;
+      if (has_u) {
+        const float* gr = grow + (size_t)k * kFeat * kTileTC + row;
+        float uk = Ctx::ldcg(rows + (size_t)((kLook - 1 + k) * kFeat + 4) * kTileTC + row);
+        float ukm1 = Ctx::ldcg(rows + (size_t)((kLook - 2 + k) * kFeat + 4) * kTileTC + row);
+        float gu = Ctx::ldcg(gr + 4 * kTileTC) - 2.f * p.alpha * (ukm1 - uk) * s;
+        if (k + 1 <= p.N - 1) {
+          float ukp1 = Ctx::ldcg(rows + (size_t)((kLook + k) * kFeat + 4) * kTileTC + row);
+          gu += 2.f * p.alpha * (uk - ukp1) * s;
+        }
+        float v = 0.f;
+        for (int u = 0; u < kFnnHid; ++u) {
+          float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x3, fmaf(iw[u * 3 + 0], x0, ib[u])));
+          v = fmaf(ow[u], fmaxf(pre, 0.f), v);
+        }
+        dv = (valid && v > -1.f && v < 1.f) ? gu : 0.f;           // hardtanh_backward
+        float d0 = 0.f, d1 = 0.f;
+        for (int u = 0; u < kFnnHid; ++u) {
+          float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x3, fmaf(iw[u * 3 + 0], x0, ib[u])));
+          float dp = pre > 0.f ? dv * ow[u] : 0.f;                  // threshold_backward
+          d0 = fmaf(dp, iw[u * 3 + 0], d0);
+          d1 = fmaf(dp, iw[u * 3 + 1], d1);
+        }
+        g0 += d0 + Ctx::ldcg(gr);
+        g1 += Ctx::ldcg(gr + kTileTC);
+        g2 += Ctx::ldcg(gr + 2 * kTileTC);
+        g3 += d1 + Ctx::ldcg(gr + 3 * kTileTC);
+        sm[kSmDvTC + row] = dv;
+        sm[kSmFinTC + row] = x0;
+        sm[kSmFinTC + kTileTC + row] = x3;
+      }
+      if (!valid) { g0 = g1 = g2 = g3 = 0.f; }
+      sm[kSmGxTC + row] = g0;
+      sm[kSmGxTC + kTileTC + row] = g1;
+      sm[kSmGxTC + 2 * kTileTC + row] = g2;
+      sm[kSmGxTC + 3 * kTileTC + row] = g3;
+    }
+    ctx.sync();
+    if (has_u && tid < 4 * kFnnHid) {                  // controller weight gradients, unit-parallel
+      const int u = tid % kFnnHid, part = tid / kFnnHid;
+      double a_ow = 0.0, a_b = 0.0, a_w0 = 0.0, a_w1 = 0.0, a_w2 = 0.0;   // batch sums cancel heavily: fp64
+      const float w0 = iw[u * 3 + 0], w1 = iw[u * 3 + 1], w2 = iw[u * 3 + 2], bb = ib[u], owu = ow[u];
+      for (int tr = part * 32; tr < part * 32 + 32; ++tr) {
+        float dv = sm[kSmDvTC + tr];
+        float x0 = sm[kSmFinTC + tr], x3 = sm[kSmFinTC + kTileTC + tr], ref = sm[kSmRefTC + tr];
+        float pre = fmaf(w2, ref, fmaf(w1, x3, fmaf(w0, x0, bb)));
+        a_ow += (double)dv * (double)fmaxf(pre, 0.f);
+        float dp = pre > 0.f ? dv * owu : 0.f;
+        a_b += dp;
+        a_w0 += (double)dp * (double)x0;
+        a_w1 += (double)dp * (double)x3;
+        a_w2 += (double)dp * (double)ref;
+      }
+      double* pg = reinterpret_cast<double*>(sm + kSmPgTC) + part * kNumFnnGrad;
+      pg[u * 3 + 0] += a_w0;
+      pg[u * 3 + 1] += a_w1;
+      pg[u * 3 + 2] += a_w2;
+      pg[150 + u] += a_b;
+      pg[200 + u] += a_ow;
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // reverse sweep of window m
+  // ---------------------------------------------------------------------------------------------
+  template <int HALF>
+  FC_HD_CTX void bwd_window(int tile, int m, bool more_after) {
+    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
+    const int tmin = t_min_of(m);
+    const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 8, p.acc_comp) : 0.0f;
+    bwd_glue(tile, m);
+    ctx.sync();
+    for (int l = kLayers - 1; l >= 0; --l) {
+      const int nb = nb_of(l);
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) { c[j] = 0.f; hrec[j] = 0.f; }
+      wait_bar(kBarWeights);
+      for (int t = kLook - 1; t >= tmin; --t) {
+        const float* rec_in = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
+        bwd_pointwise<HALF>(l, t, rec_in, dseq + (size_t)t * kSlot);
+        ctx.tmem_st_wait();
+        ctx.tc_sync();
+        if (tid == 0) {
+          const int imgf = bwd_img_floats(l);
+          if (l == 0) {
+            issue_chunk(kColD, kNB0, nb, 0, kColGhi, kColGlo, kKB / 8, imgf, kBarChunk0);
+          } else {
+            issue_chunk(kColD, 48, nb, 0, kColGhi, kColGlo, kKB / 8, imgf, kBarChunk0);
+            issue_chunk(kColD + 48, 64, nb, 48, kColGhi, kColGlo, kKB / 8, imgf, kBarChunk0 + 1);
+          }
+        }
+        wait_bar(kBarChunk0);
+        if (l > 0) wait_bar(kBarChunk0 + 1);
+        if (t == tmin && tid == 0) {                   // all MMAs that read this image are complete
+          if (l > 0) request_weights(true, l - 1);
+          else if (m > 0) request_weights(true, kLayers - 1);
+          else if (more_after) request_weights(false, 0);
+        }
+        if (l > 0) {
+          float d[2 * NOWN];
+          constexpr int c0 = HALF == 0 ? 0 : 48;
+          if (HALF == 0) {
+            ctx.template tmem_ld<32>(kColD + c0, d);
+            ctx.template tmem_ld<16>(kColD + c0 + 32, d + 32);
+          } else {
+            ctx.template tmem_ld<32>(kColD + c0, d);
+            ctx.template tmem_ld<16>(kColD + c0 + 32, d + 32);
+            ctx.template tmem_ld<4>(kColD + c0 + 48, d + 48);
+          }
+          float* dq = dseq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < NOWN; ++j) {
+            dq[j * 32] = fmaf(d[j], corr_b, d[j]);               // d(input unit) -> the layer below, same thread
+            hrec[j] = fmaf(d[NOWN + j], corr_b, d[NOWN + j]);
+          }
+        } else {
+          if (HALF == 0) {
+            float d[32];
+            ctx.template tmem_ld<32>(kColD, d);
+#pragma unroll
+            for (int j = 0; j < kUnits0; ++j) hrec[j] = fmaf(d[j], corr_b, d[j]);
+            const int kr = m + t - (kLook - 1);        // gradient of row rho_{9+kr}
+            if (kr >= 0) {
+              float* gp = grow + (size_t)kr * kFeat * kTileTC + row;
+#pragma unroll
+              for (int f = 0; f < kFeat; ++f) gp[f * kTileTC] = Ctx::ldcg(gp + f * kTileTC) + fmaf(d[24 + f], corr_b, d[24 + f]);
+            }
+          } else {
+            float d[32];
+            ctx.template tmem_ld<32>(kColD + 32, d);
+#pragma unroll
+            for (int j = 0; j < kUnits1; ++j) hrec[j] = fmaf(d[j], corr_b, d[j]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // per-tile epilogues
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void store_costs(int tile) {
+    if (half == 0) {
+      int b = tile * kTileTC + row;
+      if (b < p.B) {
+        const float inv = 1.f / (float)p.N;
+        float cst = sm[kSmCostTC + row] * inv;                                 // :1458-1460
+        p.cost[b] = cst;
+        p.command[b] = sm[kSmCostTC + kTileTC + row] * inv;
+        p.error[b] = sm[kSmCostTC + 2 * kTileTC + row] * inv;
+        sm[kSmCostTC + row] = cst;
+      } else {
+        sm[kSmCostTC + row] = 0.f;
+      }
+    }
+    ctx.sync();
+    if (tid == 0) {
+      double acc = 0.0;
+      for (int i = 0; i < kTileTC; ++i) acc += (double)sm[kSmCostTC + i];
+      *reinterpret_cast<double*>(sm + kSmRedTC) += acc;
+    }
+  }
+
+  FC_HD_CTX void store_du0(int tile) {
+    if (half == 0) {
+      int b = tile * kTileTC + row;
+      if (b < p.B) {
+        const float s = p.grad_scale;
+        float u0 = Ctx::ldcg(rows + (size_t)((kLook - 1) * kFeat + 4) * kTileTC + row);
+        float um1 = Ctx::ldcg(rows + (size_t)((kLook - 2) * kFeat + 4) * kTileTC + row);
+        float g = Ctx::ldcg(grow + 4 * kTileTC + row) - 2.f * p.alpha * (um1 - u0) * s;
+        if (p.N > 1) {
+          float u1 = Ctx::ldcg(rows + (size_t)(kLook * kFeat + 4) * kTileTC + row);
+          g += 2.f * p.alpha * (u0 - u1) * s;
+        }
+        p.du0[b] = g;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // persistent loop over tiles
+  // ---------------------------------------------------------------------------------------------
+  template <int HALF>
+  FC_HD_CTX void run_half() {
+    for (int tile = ctx.bid(); tile < p.num_tiles; tile += ctx.nblk()) {
+      const bool more = tile + ctx.nblk() < p.num_tiles;
+      load_tile(tile);
+      ctx.sync();
+      for (int m = 0; m < p.N; ++m) fwd_window<HALF>(tile, m, more);
+      store_costs(tile);
+      if (p.with_grad) {
+        if (HALF == 0) {
+          for (int k = 0; k < p.N; ++k)
+#pragma unroll
+            for (int f = 0; f < kFeat; ++f) grow[(size_t)(k * kFeat + f) * kTileTC + row] = 0.f;
+        }
+        ctx.sync();
+        for (int m = p.N - 1; m >= 0; --m) bwd_window<HALF>(tile, m, more);
+        ctx.sync();
+        store_du0(tile);
+      }
+      ctx.sync();
+    }
+  }
+
+  FC_HD_CTX void run() {
+    ctx.tc_setup(sm + kSmBarTC);
+    for (int i = tid; i < kSmallFloats; i += kThreads) sm[kSmSmallTC + i] = p.wpack[kSmallOff + i];
+    for (int i = tid; i < 4 * kNumFnnGrad; i += kThreads) reinterpret_cast<double*>(sm + kSmPgTC)[i] = 0.0;
+    if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedTC) = 0.0;
+    ctx.sync();
+    if (tid == 0 && ctx.bid() < p.num_tiles) request_weights(false, 0);
+    if (half == 0) run_half<0>(); else run_half<1>();
+    double* part = p.partial + (size_t)ctx.bid() * kPartialStride;
+    const double* pgd = reinterpret_cast<const double*>(sm + kSmPgTC);
+    for (int i = tid; i < kNumFnnGrad; i += kThreads)
+      part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
+    if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedTC);
+    ctx.sync();
+    ctx.tc_teardown();
+  }
+};
+
+}  // namespace tc
+}  // namespace fc

@@ -15,6 +15,9 @@
 
 #define FC_HD_CTX inline
 #include "../../forging_control_b200/csrc/fc_mpc_kernel.inl"
+#include "../../forging_control_b200/csrc/fc_mpc_tc_kernel.inl"
+#include <atomic>
+#include <cstdint>
 
 namespace {
 
@@ -47,6 +50,59 @@ struct EmuCtx {
   template <int N> static void cp_wait() {}
 };
 
+
+// ---- tcgen05 variant: TMEM = [128 lanes][512 columns] array, MMA executed synchronously by the issuing
+// thread with tf32-truncated operands, mbarriers = counters --------------------------------------------
+struct EmuBlockTC : EmuBlock {
+  std::vector<float> tmem;
+  std::atomic<unsigned> bars[8];
+  EmuBlockTC(int b, int n) : EmuBlock(b, n), tmem(128 * 512, 0.f) {
+    smem.assign(fc::tc::kSmFloatsTC, 0.f);
+    for (auto& x : bars) x.store(0);
+  }
+};
+
+static inline float tf32_trunc(float x) {
+  uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x;
+}
+
+struct EmuCtxTC : EmuCtx {
+  EmuBlockTC* tb;
+  EmuCtxTC(EmuBlockTC* b, int t_) : EmuCtx{b, t_}, tb(b) {}
+  int row() const { return 32 * ((t >> 5) & 3) + (t & 31); }
+  void tc_setup(float*) { sync(); }
+  void tc_teardown() { sync(); }
+  void tc_sync() const { sync(); }
+  template <int N> void tmem_ld(int col, float* v) const { for (int i = 0; i < N; ++i) v[i] = tb->tmem[row() * 512 + col + i]; }
+  template <int N> void tmem_st(int col, const float* v) const { for (int i = 0; i < N; ++i) tb->tmem[row() * 512 + col + i] = v[i]; }
+  void tmem_st_wait() const {}
+  static float tf32(float x) {   // cvt.rna.tf32.f32: round to nearest, ties away, keep 10 mantissa bits
+    uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x;
+  }
+  // the emulation accumulates exactly (round to nearest): it checks index arithmetic and dataflow, not the
+  // truncating accumulator of the hardware, so the kernel's accumulator compensation is switched off
+  static constexpr bool kAccTruncates = false;
+  void mma(int d_col, int n, int a_col, const float* b_img, int n_img, int row0, int ksteps, bool accumulate) const {
+    const int K = ksteps * 8;
+    for (int m = 0; m < 128; ++m) {
+      const float* a = &tb->tmem[m * 512 + a_col];
+      for (int j = 0; j < n; ++j) {
+        double s = accumulate ? (double)tb->tmem[m * 512 + d_col + j] : 0.0;
+        for (int k = 0; k < K; ++k) s += (double)tf32_trunc(a[k]) * (double)tf32_trunc(b_img[(k / 4) * (n_img * 4) + (row0 + j) * 4 + (k & 3)]);
+        tb->tmem[m * 512 + d_col + j] = (float)s;
+      }
+    }
+  }
+  void commit(int bar) const { tb->bars[bar].fetch_add(1); }
+  void bar_wait(int bar, unsigned phase) const {
+    while (tb->bars[bar].load() <= phase) std::this_thread::yield();
+  }
+  void bulk_load(float* dst, const float* src, int nfloats, int bar) const {
+    std::memcpy(dst, src, (size_t)nfloats * 4);
+    tb->bars[bar].fetch_add(1);
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -72,12 +128,13 @@ int fc_emu_mpc_loss(const float* X, const float* u0, const float* Z, const float
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
   p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.acc_comp = 1.0f;
   p.num_tiles = (B + fc::kTile - 1) / fc::kTile;
   if (grid > p.num_tiles) grid = p.num_tiles;
   fc::WorkLayout wl = fc::work_layout(N, with_grad);
   p.work_stride = wl.total;
   std::vector<float> work((size_t)grid * wl.total, 0.f);
-  std::vector<float> partial((size_t)grid * fc::kPartialStride, 0.f);
+  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
   p.work = work.data();
   p.partial = partial.data();
   for (int b = 0; b < grid; ++b) {
@@ -93,11 +150,69 @@ int fc_emu_mpc_loss(const float* X, const float* u0, const float* Z, const float
     for (auto& x : th) x.join();
   }
   for (int i = 0; i < 256; ++i) gl[i] = 0.f;
-  for (int b = 0; b < grid; ++b) {
-    for (int i = 0; i < fc::kNumFnnGrad; ++i) gl[i] += partial[(size_t)b * fc::kPartialStride + i];
-    gl[fc::kNumFnnGrad] += partial[(size_t)b * fc::kPartialStride + fc::kNumFnnGrad];
+  for (int i = 0; i <= fc::kNumFnnGrad; ++i) {
+    double a = 0.0;
+    for (int b = 0; b < grid; ++b) a += partial[(size_t)b * fc::kPartialStride + i];
+    gl[i] = (float)(i == fc::kNumFnnGrad ? a / (double)B_global : a);
   }
-  gl[fc::kNumFnnGrad] /= (float)B_global;
+  return 0;
+}
+
+
+int fc_emu_pack_floats_tc() { return fc::tc::kPackFloatsTC; }
+
+void fc_emu_pack_weights_tc(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
+                            const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
+                            const float* inp_w, const float* inp_b, const float* out_w, float* out) {
+  fc::RawWeights w;
+  w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
+  w.fc_w = fc_w; w.fc_b = fc_b; w.inp_w = inp_w; w.inp_b = inp_b; w.out_w = out_w;
+  for (int i = 0; i < fc::tc::kPackFloatsTC; ++i) {
+    float v = fc::tc::tc_packed_value(w, i);
+    if (i < fc::tc::kSmallOff) {
+      float hi = EmuCtxTC::tf32(v);
+      v = fc::tc::tc_is_lo(i) ? EmuCtxTC::tf32(v - hi) : hi;
+    }
+    out[i] = v;
+  }
+}
+
+int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                       long long B_global, int with_grad, int grid, float* cost, float* command, float* error,
+                       float* pred, float* du0, float* gl /*[256]*/) {
+  fc::MpcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.X = X; p.u0 = u0; p.Z = Z; p.wpack = wpack;
+  p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
+  p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
+  p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.acc_comp = 1.0f;
+  p.num_tiles = (B + fc::tc::kTileTC - 1) / fc::tc::kTileTC;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  fc::tc::WorkLayoutTC wl = fc::tc::work_layout_tc(N, with_grad);
+  p.work_stride = wl.total;
+  std::vector<float> work((size_t)grid * wl.total, 0.f);
+  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
+  p.work = work.data();
+  p.partial = partial.data();
+  for (int b = 0; b < grid; ++b) {
+    EmuBlockTC blk(b, grid);
+    std::vector<std::thread> th;
+    th.reserve(fc::kThreads);
+    for (int t = 0; t < fc::kThreads; ++t)
+      th.emplace_back([&blk, &p, t]() {
+        EmuCtxTC ctx(&blk, t);
+        fc::tc::MpcTileTC<EmuCtxTC> k(ctx, p);
+        k.run();
+      });
+    for (auto& x : th) x.join();
+  }
+  for (int i = 0; i < 256; ++i) gl[i] = 0.f;
+  for (int i = 0; i <= fc::kNumFnnGrad; ++i) {
+    double a = 0.0;
+    for (int b = 0; b < grid; ++b) a += partial[(size_t)b * fc::kPartialStride + i];
+    gl[i] = (float)(i == fc::kNumFnnGrad ? a / (double)B_global : a);
+  }
   return 0;
 }
 

@@ -35,6 +35,17 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["ffma", "tcgen05"], autouse=True)
+def kernel(request):
+    """Every parity test runs against both kernels behind fc_mpc_loss: the FP32 FFMA kernel and the
+    tcgen05 3xTF32 kernel (fc_mpc_select_kernel; the automatic choice is restored afterwards)."""
+    from forging_control_b200 import _native
+    L = _native.lib()
+    assert L.fc_mpc_select_kernel(1 if request.param == "ffma" else 2) == 0
+    yield request.param
+    assert L.fc_mpc_select_kernel(0) == 0
+
+
 @pytest.mark.parametrize("name", W1_CASES)
 def test_module_api_matches_reference_golden(dev, golden_cases, golden_weights, name):
     """The call sequence of NeuralNetwork.train_model (Functions.py:640-655) through the drop-in API."""
