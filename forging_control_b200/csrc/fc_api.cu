@@ -65,6 +65,14 @@ __global__ void __launch_bounds__(kThreads, 1) mpc_loss_kernel(const MpcParams p
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int N> struct TmemIO;
+template <> struct TmemIO<1> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(a) : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(r[0]) : "memory");
+  }
+};
 template <> struct TmemIO<2> {
   static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
@@ -152,6 +160,12 @@ struct DevCtxTC : DevCtx {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
   }
+  // split-phase load: the destination registers must not be read before tmem_ld_wait()
+  template <int N>
+  __device__ __forceinline__ void tmem_ld_nowait(int col, float* v) const {
+    TmemIO<N>::ld(lane_addr + col, reinterpret_cast<uint32_t*>(v));
+  }
+  __device__ __forceinline__ void tmem_ld_wait() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
   template <int N>
   __device__ __forceinline__ void tmem_st(int col, const float* v) const {
     uint32_t r[N];
@@ -210,7 +224,7 @@ struct DevCtxTC : DevCtx {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) mpc_loss_tc_kernel(const MpcParams p) {
+__global__ void __launch_bounds__(tc::kThreadsTC, 1) mpc_loss_tc_kernel(const MpcParams p) {
   DevCtxTC ctx;
   tc::MpcTileTC<DevCtxTC> k(ctx, p);
   k.run();
@@ -430,7 +444,7 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
   p.acc_comp = 1.3f;
   if (const char* e = getenv("FC_TC_ACC_COMP")) p.acc_comp = (float)atof(e);   // calibration experiments only
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl.use_tc) mpc_loss_tc_kernel<<<pl.grid, kThreads, tc::kSmBytesTC, st>>>(p);
+  if (pl.use_tc) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, tc::kSmBytesTC, st>>>(p);
   else mpc_loss_kernel<<<pl.grid, kThreads, kSmBytes, st>>>(p);
   FC_CUDA(cudaGetLastError(), "mpc_loss kernel launch");
   mpc_finalize_kernel<<<1, 1024, 0, st>>>(p.partial, pl.grid, 1.0 / (double)B_global, gl);

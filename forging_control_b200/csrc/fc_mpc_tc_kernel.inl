@@ -20,7 +20,8 @@ struct MpcTileTC {
   Ctx& ctx;
   const MpcParams& p;
   float* sm;
-  int tid, warp, lane, row, half, u_first;
+  int tid, warp, lane, row, quarter, nown, u_first;
+  bool full;             // this quarter owns 13 units (else 12: unit slot 12 is a masked dummy)
   float *rows, *seq, *dseq, *grow, *rec;
   float c[kMaxOwn];      // forward: cell state, backward: d(cell state)
   float hrec[kMaxOwn];   // backward: d(h) from step t+1
@@ -32,8 +33,10 @@ struct MpcTileTC {
     warp = tid >> 5;
     lane = tid & 31;
     row = 32 * (warp & 3) + lane;
-    half = warp >> 2;
-    u_first = half == 0 ? 0 : kUnits0;
+    quarter = warp >> 2;
+    nown = units_of(quarter);
+    u_first = first_unit(quarter);
+    full = nown == kMaxOwn;
     WorkLayoutTC wl = work_layout_tc(p.N, p.with_grad);
     float* base = p.work + (size_t)ctx.bid() * p.work_stride;
     rows = base + wl.rows;
@@ -48,7 +51,7 @@ struct MpcTileTC {
   FC_HD_CTX static float sigmoidf_(float x) { return Ctx::rcp(1.f + Ctx::ex2(-1.4426950408889634f * x)); }
   // tanh: 1 - 2/(1+e^{2x}) has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is a large
   // relative error for the small gate / cell values that dominate here; below |x| = 0.3 use the odd
-  // Taylor polynomial (relative error < 2e-8) instead.  Branch-free select.
+  // Taylor polynomial (relative error < 6e-8) instead.  Branch-free select.
   FC_HD_CTX static float tanhf_(float x) {
     const float big = 1.f - 2.f * Ctx::rcp(1.f + Ctx::ex2(2.8853900817779268f * x));
     const float x2 = x * x;
@@ -73,11 +76,11 @@ struct MpcTileTC {
     ctx.template tmem_st<N>(col_hi, hi);
     ctx.template tmem_st<N>(col_lo, lo);
   }
-  template <int NOWN>
-  FC_HD_CTX void st_own(int col_hi, int col_lo, const float* v) {   // NOWN = 24 or 26 columns
-    st_split<16>(col_hi, col_lo, v);
-    st_split<8>(col_hi + 16, col_lo + 16, v + 16);
-    if constexpr (NOWN == 26) st_split<2>(col_hi + 24, col_lo + 24, v + 24);
+  // the 12 or 13 owned unit columns starting at col
+  FC_HD_CTX void st_own(int col_hi, int col_lo, const float* v) {
+    st_split<8>(col_hi, col_lo, v);
+    st_split<4>(col_hi + 8, col_lo + 8, v + 8);
+    if (full) st_split<1>(col_hi + 12, col_lo + 12, v + 12);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -88,23 +91,23 @@ struct MpcTileTC {
     ctx.bulk_load(sm + kSmWTC, p.wpack + (bwd ? wb_off(l) : wf_off(l)), n, kBarWeights);
   }
 
-  // one accumulator chunk: 3 error-compensated terms, small ones first (tid 0 only)
-  FC_HD_CTX void issue_chunk(int d_col, int n, int n_img, int row0, int a_hi, int a_lo, int ksteps, int img_floats, int bar) {
+  // one accumulator: 3 error-compensated terms, small ones first (tid 0 only)
+  FC_HD_CTX void issue_mma(int d_col, int n, int a_hi, int a_lo, int ksteps, int img_floats, int bar) {
     const float* b_hi = sm + kSmWTC;
     const float* b_lo = b_hi + img_floats;
-    ctx.mma(d_col, n, a_lo, b_hi, n_img, row0, ksteps, false);
-    ctx.mma(d_col, n, a_hi, b_lo, n_img, row0, ksteps, true);
-    ctx.mma(d_col, n, a_hi, b_hi, n_img, row0, ksteps, true);
+    ctx.mma(d_col, n, a_lo, b_hi, n, 0, ksteps, false);
+    ctx.mma(d_col, n, a_hi, b_lo, n, 0, ksteps, true);
+    ctx.mma(d_col, n, a_hi, b_hi, n, 0, ksteps, true);
     ctx.commit(bar);
   }
 
   // ---------------------------------------------------------------------------------------------
-  // tile set-up
+  // tile set-up (quarter-0 thread of each trajectory)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void load_tile(int tile) {
     const int b = tile * kTileTC + row;
     const bool ok = b < p.B;
-    if (half == 0) {
+    if (quarter == 0) {
       for (int r = 0; r < kLook; ++r)
 #pragma unroll
         for (int f = 0; f < kFeat; ++f) {
@@ -123,7 +126,7 @@ struct MpcTileTC {
   }
 
   // ---------------------------------------------------------------------------------------------
-  // forward: cell update of `nu` units starting at owned index j0 from 4*nu accumulator columns
+  // forward: cell update of NU unit slots starting at slot j0 from 4*NU accumulator columns
   // ---------------------------------------------------------------------------------------------
   template <int NU>
   FC_HD_CTX void fwd_units(int j0, const float* g, bool first, float* h, float* rp, int r0) {
@@ -151,59 +154,75 @@ struct MpcTileTC {
     }
   }
 
-  // all owned units of one step; waits for the accumulator chunks it needs
-  template <int HALF>
+  // all unit slots of one step (the accumulator barrier has been waited for by the caller)
   FC_HD_CTX void fwd_pointwise(bool first, float corr, float* h, float* rec_out) {
-    float* rp = rec_out ? rec_out + ((size_t)warp * 33 * 32 + lane) * 4 : nullptr;
-    constexpr int col0 = HALF == 0 ? 0 : kUnits0 * 4;
-    constexpr int NG = 6;                                  // groups of 4 units
+    float* rp = rec_out ? rec_out + ((size_t)warp * kRecF4 * 32 + lane) * 4 : nullptr;
+    const int col0 = kColD + 4 * u_first;
+    float g[2][16];
+    ctx.template tmem_ld_nowait<16>(col0, g[0]);
 #pragma unroll
-    for (int gi = 0; gi < NG; ++gi) {
-      if (HALF == 0) {
-        if (gi == 0) wait_bar(kBarChunk0 + 0);             // A0: units 0..11
-        if (gi == 3) wait_bar(kBarChunk0 + 2);             // A1: units 12..23
-      } else {
-        if (gi == 0) wait_bar(kBarChunk0 + 1);             // B0: units 24..39
-        if (gi == 4) wait_bar(kBarChunk0 + 3);             // B1: units 40..49
-      }
-      float g[16];
-      ctx.template tmem_ld<16>(kColD + col0 + gi * 16, g);
+    for (int gi = 0; gi < 3; ++gi) {
+      ctx.tmem_ld_wait();
+      // software pipeline: request the next accumulator columns before working on these
+      if (gi + 1 < 3) ctx.template tmem_ld_nowait<16>(col0 + (gi + 1) * 16, g[(gi + 1) & 1]);
+      else ctx.template tmem_ld_nowait<4>(col0 + 48, g[(gi + 1) & 1]);
+      float* gg = g[gi & 1];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) g[i] = fmaf(g[i], corr, g[i]);
-      fwd_units<4>(gi * 4, g, first, h, rp, gi * 5);
+      for (int i = 0; i < 16; ++i) gg[i] = fmaf(gg[i], corr, gg[i]);
+      fwd_units<4>(gi * 4, gg, first, h, rp, gi * 5);
     }
-    if (HALF == 1) {
-      float g[8];
-      ctx.template tmem_ld<8>(kColD + col0 + NG * 16, g);
+    ctx.tmem_ld_wait();
+    float* gg = g[1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], corr, g[i]);
-      fwd_units<2>(NG * 4, g, first, h, rp, NG * 5);
+    for (int i = 0; i < 4; ++i) gg[i] = fmaf(gg[i], corr, gg[i]);
+    fwd_units<1>(12, gg, first, h, rp, 15);                // slot 12: a masked dummy for quarters 2,3
+  }
+
+  // input of (layer l, step t) for the owned columns: layer 0 -> 5 row features (quarter 0 only)
+  FC_HD_CTX void load_input(int l, int m, int t, float* xin) {
+    if (l == 0) {
+      if (quarter == 0) {
+        const float* rp = rows + (size_t)(m + t) * kFeat * kTileTC + row;
+#pragma unroll
+        for (int f = 0; f < kFeat; ++f) xin[f] = Ctx::ldcg(rp + f * kTileTC);
+      }
+    } else {
+      const float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) xin[j] = Ctx::ldcg(sq + j * 32);
+    }
+  }
+  FC_HD_CTX void store_input(int l, const float* xin) {
+    if (l == 0) {
+      if (quarter == 0) {
+        float v[8] = {xin[0], xin[1], xin[2], xin[3], xin[4], 0.f, 0.f, 0.f};
+        st_split<8>(kColAhi, kColAlo, v);
+      }
+    } else {
+      st_own(kColAhi + u_first, kColAlo + u_first, xin);
     }
   }
 
   // ---------------------------------------------------------------------------------------------
   // forward window
   // ---------------------------------------------------------------------------------------------
-  template <int HALF>
   FC_HD_CTX void fwd_window(int tile, int m, bool more_after) {
-    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
     const int tmin = t_min_of(m);
     for (int l = 0; l < kLayers; ++l) {
       const int kf = kf_of(l), rec0 = l == 0 ? kRec0 : kRec;
       float h[kMaxOwn], xin[kMaxOwn];
       // A(0): zero recurrent columns and padding, input of step 0
       {
-        float z[kMaxOwn];
-#pragma unroll
-        for (int i = 0; i < kMaxOwn; ++i) z[i] = 0.f;
-        ctx.template tmem_st<16>(kColAhi + rec0 + u_first, z);
-        ctx.template tmem_st<8>(kColAhi + rec0 + u_first + 16, z);
-        ctx.template tmem_st<16>(kColAlo + rec0 + u_first, z);
-        ctx.template tmem_st<8>(kColAlo + rec0 + u_first + 16, z);
-        if (HALF == 1) {
-          ctx.template tmem_st<2>(kColAhi + rec0 + u_first + 24, z);
-          ctx.template tmem_st<2>(kColAlo + rec0 + u_first + 24, z);
-          // padding columns behind the recurrent block: layer 0 -> [58,64), layers 1,2 -> [100,104)
+        float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ctx.template tmem_st<8>(kColAhi + rec0 + u_first, z);
+        ctx.template tmem_st<4>(kColAhi + rec0 + u_first + 8, z);
+        ctx.template tmem_st<8>(kColAlo + rec0 + u_first, z);
+        ctx.template tmem_st<4>(kColAlo + rec0 + u_first + 8, z);
+        if (full) {
+          ctx.template tmem_st<1>(kColAhi + rec0 + u_first + 12, z);
+          ctx.template tmem_st<1>(kColAlo + rec0 + u_first + 12, z);
+        }
+        if (quarter == 3) {    // padding columns behind the recurrent block: layer 0 [58,64), layers 1,2 [100,104)
           if (l == 0) {
             ctx.template tmem_st<4>(kColAhi + 58, z); ctx.template tmem_st<2>(kColAhi + 62, z);
             ctx.template tmem_st<4>(kColAlo + 58, z); ctx.template tmem_st<2>(kColAlo + 62, z);
@@ -213,53 +232,49 @@ struct MpcTileTC {
           }
         }
       }
-      load_input<HALF>(l, m, 0, xin);
-      store_input<HALF>(l, xin);
+      load_input(l, m, 0, xin);
+      store_input(l, xin);
       ctx.tmem_st_wait();
       wait_bar(kBarWeights);                               // operand image of this layer landed
       ctx.tc_sync();
       for (int t = 0; t < kLook; ++t) {
-        if (tid == 0) {
-          const int imgf = fwd_img_floats(l);
-#pragma unroll 1
-          for (int ck = 0; ck < kNumChunks; ++ck)
-            issue_chunk(kColD + chunk_col(ck), chunk_n(ck), kNF, chunk_col(ck), kColAhi, kColAlo, kf / 8, imgf, kBarChunk0 + ck);
-        }
-        if (t + 1 < kLook) load_input<HALF>(l, m, t + 1, xin);
+        // at t = 0 the recurrent columns are zero: only the k-steps that cover the input columns
+        const int ksteps = t == 0 ? (l == 0 ? 1 : 7) : kf / 8;
+        if (tid == 0) issue_mma(kColD, kNF, kColAhi, kColAlo, ksteps, fwd_img_floats(l), kBarChunk0);
+        if (t + 1 < kLook) load_input(l, m, t + 1, xin);
         float* rec_out = nullptr;
         if (p.with_grad && t >= tmin) rec_out = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
-        // accumulation steps that add non-zero blocks: at t = 0 the recurrent columns are zero
-        const float corr = Ctx::kAccTruncates ? acc_correction(t == 0 ? (l == 0 ? 1 : 7) : kf / 8, p.acc_comp) : 0.0f;
-        fwd_pointwise<HALF>(t == 0, corr, h, rec_out);
-        // every MMA of this step must have completed before A is overwritten / the image is replaced
-        if (HALF == 0) { wait_bar(kBarChunk0 + 1); wait_bar(kBarChunk0 + 3); }
-        else           { wait_bar(kBarChunk0 + 0); wait_bar(kBarChunk0 + 2); }
-        if (t == kLook - 1 && tid == 0) {
+        const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
+        wait_bar(kBarChunk0);                              // accumulator complete; A and the image are free again
+        if (t == kLook - 1 && tid == 0) {                  // stream the next operand image under the cell update
           if (l + 1 < kLayers) request_weights(false, l + 1);
           else if (m + 1 < p.N) request_weights(false, 0);
           else if (p.with_grad) request_weights(true, kLayers - 1);
           else if (more_after) request_weights(false, 0);
         }
+        fwd_pointwise(t == 0, corr, h, rec_out);
         if (l + 1 < kLayers) {
           float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
 #pragma unroll
-          for (int j = 0; j < NOWN; ++j) sq[j * 32] = h[j];
+          for (int j = 0; j < kMaxOwn; ++j) sq[j * 32] = h[j];
         }
         if (t + 1 < kLook) {
-          store_input<HALF>(l, xin);
-          st_own<NOWN>(kColAhi + rec0 + u_first, kColAlo + rec0 + u_first, h);
+          store_input(l, xin);
+          st_own(kColAhi + rec0 + u_first, kColAlo + rec0 + u_first, h);
           ctx.tmem_st_wait();
         } else if (l == kLayers - 1) {
           // read-out partial sums over the owned units (Functions.py:377)
           const float* fw = sm + kSmSmallTC;
           float xq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < NOWN; ++j)
+          for (int j = 0; j < kMaxOwn; ++j)
+            if (j < nown) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) xq[q] = fmaf(fw[q * kHid + u_first + j], h[j], xq[q]);
-          if (HALF == 1) {
+              for (int q = 0; q < 4; ++q) xq[q] = fmaf(fw[q * kHid + u_first + j], h[j], xq[q]);
+            }
+          if (quarter > 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) sm[kSmFcpTC + q * kTileTC + row] = xq[q];
+            for (int q = 0; q < 4; ++q) sm[kSmFcpTC + ((quarter - 1) * 4 + q) * kTileTC + row] = xq[q];
           } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) hrec[q] = xq[q];   // parked until the barrier below
@@ -268,47 +283,20 @@ struct MpcTileTC {
         ctx.tc_sync();
       }
     }
-    if (HALF == 0) fwd_glue(tile, m);
+    if (quarter == 0) fwd_glue(tile, m);
     ctx.sync();
   }
 
-  // input of (layer l, step t) for the owned columns: layer 0 -> 5 row features (half 0 only)
-  template <int HALF>
-  FC_HD_CTX void load_input(int l, int m, int t, float* xin) {
-    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
-    if (l == 0) {
-      if (HALF == 0) {
-        const float* rp = rows + (size_t)(m + t) * kFeat * kTileTC + row;
-#pragma unroll
-        for (int f = 0; f < kFeat; ++f) xin[f] = Ctx::ldcg(rp + f * kTileTC);
-      }
-    } else {
-      const float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
-#pragma unroll
-      for (int j = 0; j < NOWN; ++j) xin[j] = Ctx::ldcg(sq + j * 32);
-    }
-  }
-  template <int HALF>
-  FC_HD_CTX void store_input(int l, const float* xin) {
-    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
-    if (l == 0) {
-      if (HALF == 0) {
-        float v[8] = {xin[0], xin[1], xin[2], xin[3], xin[4], 0.f, 0.f, 0.f};
-        st_split<8>(kColAhi, kColAlo, v);
-      }
-    } else {
-      st_own<NOWN>(kColAhi + u_first, kColAlo + u_first, xin);
-    }
-  }
-
   // ---------------------------------------------------------------------------------------------
-  // after window m (half-0 thread of each trajectory): read-out, cost terms, next command
+  // after window m (quarter-0 thread of each trajectory): read-out, cost terms, next command
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void fwd_glue(int tile, int m) {
     const float* sw = sm + kSmSmallTC;
     float x[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) x[q] = (hrec[q] + sm[kSmFcpTC + q * kTileTC + row]) + sw[(kFCB - kFCW) + q];
+    for (int q = 0; q < 4; ++q)
+      x[q] = ((hrec[q] + sm[kSmFcpTC + q * kTileTC + row]) + (sm[kSmFcpTC + (4 + q) * kTileTC + row] + sm[kSmFcpTC + (8 + q) * kTileTC + row])) +
+             sw[(kFCB - kFCW) + q];
     const float ref = sm[kSmRefTC + row];
     const float ucur = sm[kSmUcurTC + row], uprev = sm[kSmUprevTC + row];
     float du = uprev - ucur;
@@ -341,62 +329,96 @@ struct MpcTileTC {
   }
 
   // ---------------------------------------------------------------------------------------------
-  // backward: gate gradients of the owned units -> dG columns (A operand) in TMEM
+  // backward cell gradient, split in two parts so that everything that does not depend on the result of
+  // the running MMA happens in its shadow:
+  //   bwd_factors (during MMA(t+1)): record(t) -> A = o(1-tanh^2 c), Ko = tanh(c) o(1-o), Ki = g i(1-i),
+  //                                  Kf = c_prev f(1-f), Kg = i(1-g^2), Gf = f          (all MUFU work)
+  //   bwd_finish  (after MMA(t+1)):  dh -> dct = dc + dh A; dG = (dct Ki, dct Kf, dct Kg, dh Ko); dc = dct Gf
   // ---------------------------------------------------------------------------------------------
+  struct Factors { float A[kMaxOwn], Ko[kMaxOwn], Ki[kMaxOwn], Kf[kMaxOwn], Kg[kMaxOwn], Gf[kMaxOwn]; };
+
   template <int NU>
-  FC_HD_CTX void bwd_units(int j0, const float* rp, int r0, bool top, bool last_step, const float* gxv, const float* dsq, int col) {
+  FC_HD_CTX void factors_group(const float* rp, int r0, int j0, Factors& fa) {
     float rv[NU * 5 + 3];
 #pragma unroll
     for (int r = 0; r < (NU * 5 + 3) / 4; ++r) {
       F4 v = Ctx::ldg4_stream(rp + (size_t)(r0 + r) * 32 * 4);
       rv[r * 4] = v.x; rv[r * 4 + 1] = v.y; rv[r * 4 + 2] = v.z; rv[r * 4 + 3] = v.w;
     }
-    float dg[NU * 4];
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
       const int j = j0 + i;
       float gi = rv[i * 5 + 0], gf = rv[i * 5 + 1], gg = rv[i * 5 + 2], go = rv[i * 5 + 3], cp = rv[i * 5 + 4];
-      float cn = fmaf(gf, cp, gi * gg);
-      float tch = tanhf_(cn);
-      float dh = hrec[j];
-      if (top) {
-        if (last_step) {                                   // through fc (Functions.py:377)
-          const float* fw = sm + kSmSmallTC + u_first + j;
-          dh += fw[0] * gxv[0] + fw[kHid] * gxv[1] + fw[2 * kHid] * gxv[2] + fw[3 * kHid] * gxv[3];
-        }
-      } else {
-        dh += Ctx::ldcg(dsq + j * 32);
-      }
-      float dout = dh * tch;
-      float dct = fmaf(dh * go, 1.f - tch * tch, c[j]);
-      float di = dct * gg, dgg = dct * gi, df = dct * cp;
-      c[j] = dct * gf;
-      dg[i * 4 + 0] = di * gi * (1.f - gi);
-      dg[i * 4 + 1] = df * gf * (1.f - gf);
-      dg[i * 4 + 2] = dgg * (1.f - gg * gg);
-      dg[i * 4 + 3] = dout * go * (1.f - go);
+      float tch = tanhf_(fmaf(gf, cp, gi * gg));
+      fa.A[j] = go * (1.f - tch * tch);
+      fa.Ko[j] = tch * go * (1.f - go);
+      fa.Ki[j] = gg * gi * (1.f - gi);
+      fa.Kf[j] = cp * gf * (1.f - gf);
+      fa.Kg[j] = gi * (1.f - gg * gg);
+      fa.Gf[j] = gf;
     }
-    st_split<NU * 4>(kColGhi + col, kColGlo + col, dg);
+  }
+  FC_HD_CTX void bwd_factors(const float* rec_in, Factors& fa) {
+    const float* rp = rec_in + ((size_t)warp * kRecF4 * 32 + lane) * 4;
+#pragma unroll
+    for (int gi = 0; gi < 3; ++gi) factors_group<4>(rp, gi * 5, gi * 4, fa);
+    factors_group<1>(rp, 15, 12, fa);
   }
 
-  template <int HALF>
-  FC_HD_CTX void bwd_pointwise(int l, int t, const float* rec_in, const float* dseq_in) {
-    const float* rp = rec_in + ((size_t)warp * 33 * 32 + lane) * 4;
-    const float* dsq = dseq_in + (size_t)warp * kMaxOwn * 32 + lane;
-    const bool top = l == kLayers - 1, last = t == kLook - 1;
-    float gxv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (top && last) {
+  // d(h) contributions that do not come from the recurrent MMA: the layer above (thread-private scratch)
+  // or, for the top layer at the last step, the read-out (Functions.py:377)
+  FC_HD_CTX void bwd_extra(int l, int t, float* extra) {
+    if (l == kLayers - 1) {
+      if (t == kLook - 1) {
+        float gxv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxTC + q * kTileTC + row];
+        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxTC + q * kTileTC + row];
+#pragma unroll
+        for (int j = 0; j < kMaxOwn; ++j) {
+          const int u = u_first + j < kHid ? u_first + j : kHid - 1;
+          const float* fw = sm + kSmSmallTC + u;
+          extra[j] = fw[0] * gxv[0] + fw[kHid] * gxv[1] + fw[2 * kHid] * gxv[2] + fw[3 * kHid] * gxv[3];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kMaxOwn; ++j) extra[j] = 0.f;
+      }
+    } else {
+      const float* dsq = dseq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) extra[j] = Ctx::ldcg(dsq + j * 32);
     }
-    constexpr int col0 = HALF == 0 ? 0 : kUnits0 * 4;
+  }
+
+  template <int NU>
+  FC_HD_CTX void finish_group(int j0, const Factors& fa, const float* extra, float* dg) {
 #pragma unroll
-    for (int gi = 0; gi < 6; ++gi) bwd_units<4>(gi * 4, rp, gi * 5, top, last, gxv, dsq, col0 + gi * 16);
-    if (HALF == 1) bwd_units<2>(24, rp, 30, top, last, gxv, dsq, col0 + 96);
+    for (int i = 0; i < NU; ++i) {
+      const int j = j0 + i;
+      const float dh = hrec[j] + extra[j];
+      const float dct = fmaf(dh, fa.A[j], c[j]);
+      c[j] = dct * fa.Gf[j];
+      dg[i * 4 + 0] = dct * fa.Ki[j];
+      dg[i * 4 + 1] = dct * fa.Kf[j];
+      dg[i * 4 + 2] = dct * fa.Kg[j];
+      dg[i * 4 + 3] = dh * fa.Ko[j];
+    }
+  }
+  FC_HD_CTX void bwd_finish(const Factors& fa, const float* extra) {
+    const int col0 = 4 * u_first;
+#pragma unroll
+    for (int gi = 0; gi < 3; ++gi) {
+      float dg[16];
+      finish_group<4>(gi * 4, fa, extra, dg);
+      st_split<16>(kColGhi + col0 + gi * 16, kColGlo + col0 + gi * 16, dg);
+    }
+    float dg[4];
+    finish_group<1>(12, fa, extra, dg);                    // slot 12: computed by everybody, stored by the owners
+    if (full) st_split<4>(kColGhi + col0 + 48, kColGlo + col0 + 48, dg);
   }
 
   // ---------------------------------------------------------------------------------------------
-  // before the reverse sweep of window m (half-0 thread per trajectory + 200 accumulation threads)
+  // before the reverse sweep of window m (quarter-0 thread per trajectory + 200 accumulation threads)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void bwd_glue(int tile, int m) {
     const int k = m + 1;
@@ -406,7 +428,7 @@ struct MpcTileTC {
     const float* iw = sw + (kINPW - kFCW);
     const float* ib = sw + (kINPB - kFCW);
     const float* ow = sw + (kOUTW - kFCW);
-    if (half == 0) {
+    if (quarter == 0) {
       const bool valid = tile * kTileTC + row < p.B;
       const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;
       float x0 = Ctx::ldcg(rx), x1 = Ctx::ldcg(rx + kTileTC), x2 = Ctx::ldcg(rx + 2 * kTileTC), x3 = Ctx::ldcg(rx + 3 * kTileTC);
@@ -480,9 +502,7 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   // reverse sweep of window m
   // ---------------------------------------------------------------------------------------------
-  template <int HALF>
   FC_HD_CTX void bwd_window(int tile, int m, bool more_after) {
-    constexpr int NOWN = HALF == 0 ? kUnits0 : kUnits1;
     const int tmin = t_min_of(m);
     const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 8, p.acc_comp) : 0.0f;
     bwd_glue(tile, m);
@@ -491,62 +511,54 @@ struct MpcTileTC {
       const int nb = nb_of(l);
 #pragma unroll
       for (int j = 0; j < kMaxOwn; ++j) { c[j] = 0.f; hrec[j] = 0.f; }
+      Factors fa;
+      float extra[kMaxOwn];
+      const float* rec_l = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m)) * kRecFloatsTC;
+      bwd_factors(rec_l + (size_t)(kLook - 1 - tmin) * kRecFloatsTC, fa);
+      bwd_extra(l, kLook - 1, extra);
       wait_bar(kBarWeights);
       for (int t = kLook - 1; t >= tmin; --t) {
-        const float* rec_in = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
-        bwd_pointwise<HALF>(l, t, rec_in, dseq + (size_t)t * kSlot);
+        bwd_finish(fa, extra);
         ctx.tmem_st_wait();
         ctx.tc_sync();
-        if (tid == 0) {
-          const int imgf = bwd_img_floats(l);
-          if (l == 0) {
-            issue_chunk(kColD, kNB0, nb, 0, kColGhi, kColGlo, kKB / 8, imgf, kBarChunk0);
-          } else {
-            issue_chunk(kColD, 48, nb, 0, kColGhi, kColGlo, kKB / 8, imgf, kBarChunk0);
-            issue_chunk(kColD + 48, 64, nb, 48, kColGhi, kColGlo, kKB / 8, imgf, kBarChunk0 + 1);
-          }
+        if (tid == 0) issue_mma(kColD, nb, kColGhi, kColGlo, kKB / 8, bwd_img_floats(l), kBarChunk0);
+        // in the shadow of the MMA: record and upstream gradient of the next step
+        if (t > tmin) {
+          bwd_factors(rec_l + (size_t)(t - 1 - tmin) * kRecFloatsTC, fa);
+          bwd_extra(l, t - 1, extra);
         }
         wait_bar(kBarChunk0);
-        if (l > 0) wait_bar(kBarChunk0 + 1);
         if (t == tmin && tid == 0) {                   // all MMAs that read this image are complete
           if (l > 0) request_weights(true, l - 1);
           else if (m > 0) request_weights(true, kLayers - 1);
           else if (more_after) request_weights(false, 0);
         }
         if (l > 0) {
-          float d[2 * NOWN];
-          constexpr int c0 = HALF == 0 ? 0 : 48;
-          if (HALF == 0) {
-            ctx.template tmem_ld<32>(kColD + c0, d);
-            ctx.template tmem_ld<16>(kColD + c0 + 32, d + 32);
-          } else {
-            ctx.template tmem_ld<32>(kColD + c0, d);
-            ctx.template tmem_ld<16>(kColD + c0 + 32, d + 32);
-            ctx.template tmem_ld<4>(kColD + c0 + 48, d + 48);
-          }
+          float d[32];
+          ctx.template tmem_ld_nowait<16>(kColD + 26 * quarter, d);
+          ctx.template tmem_ld_nowait<8>(kColD + 26 * quarter + 16, d + 16);
+          ctx.template tmem_ld_nowait<2>(kColD + 26 * quarter + 24, d + 24);
+          ctx.tmem_ld_wait();
           float* dq = dseq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
 #pragma unroll
-          for (int j = 0; j < NOWN; ++j) {
-            dq[j * 32] = fmaf(d[j], corr_b, d[j]);               // d(input unit) -> the layer below, same thread
-            hrec[j] = fmaf(d[NOWN + j], corr_b, d[NOWN + j]);
+          for (int j = 0; j < kMaxOwn; ++j) {
+            dq[j * 32] = fmaf(d[j], corr_b, d[j]);                     // d(input unit) -> the layer below, same thread
+            hrec[j] = fmaf(d[kMaxOwn + j], corr_b, d[kMaxOwn + j]);
           }
         } else {
-          if (HALF == 0) {
-            float d[32];
-            ctx.template tmem_ld<32>(kColD, d);
+          float d[16], df[8];
+          ctx.template tmem_ld_nowait<8>(kColD + 13 * quarter, d);
+          ctx.template tmem_ld_nowait<4>(kColD + 13 * quarter + 8, d + 8);
+          ctx.template tmem_ld_nowait<1>(kColD + 13 * quarter + 12, d + 12);
+          if (quarter == 0) ctx.template tmem_ld_nowait<8>(kColD + 52, df);
+          ctx.tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < kUnits0; ++j) hrec[j] = fmaf(d[j], corr_b, d[j]);
-            const int kr = m + t - (kLook - 1);        // gradient of row rho_{9+kr}
-            if (kr >= 0) {
-              float* gp = grow + (size_t)kr * kFeat * kTileTC + row;
+          for (int j = 0; j < kMaxOwn; ++j) hrec[j] = fmaf(d[j], corr_b, d[j]);
+          const int kr = m + t - (kLook - 1);          // gradient of row rho_{9+kr}
+          if (quarter == 0 && kr >= 0) {
+            float* gp = grow + (size_t)kr * kFeat * kTileTC + row;
 #pragma unroll
-              for (int f = 0; f < kFeat; ++f) gp[f * kTileTC] = Ctx::ldcg(gp + f * kTileTC) + fmaf(d[24 + f], corr_b, d[24 + f]);
-            }
-          } else {
-            float d[32];
-            ctx.template tmem_ld<32>(kColD + 32, d);
-#pragma unroll
-            for (int j = 0; j < kUnits1; ++j) hrec[j] = fmaf(d[j], corr_b, d[j]);
+            for (int f = 0; f < kFeat; ++f) gp[f * kTileTC] = Ctx::ldcg(gp + f * kTileTC) + fmaf(df[f], corr_b, df[f]);
           }
         }
       }
@@ -557,7 +569,7 @@ struct MpcTileTC {
   // per-tile epilogues
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void store_costs(int tile) {
-    if (half == 0) {
+    if (quarter == 0) {
       int b = tile * kTileTC + row;
       if (b < p.B) {
         const float inv = 1.f / (float)p.N;
@@ -579,7 +591,7 @@ struct MpcTileTC {
   }
 
   FC_HD_CTX void store_du0(int tile) {
-    if (half == 0) {
+    if (quarter == 0) {
       int b = tile * kTileTC + row;
       if (b < p.B) {
         const float s = p.grad_scale;
@@ -598,40 +610,35 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   // persistent loop over tiles
   // ---------------------------------------------------------------------------------------------
-  template <int HALF>
-  FC_HD_CTX void run_half() {
+  FC_HD_CTX void run() {
+    ctx.tc_setup(sm + kSmBarTC);
+    for (int i = tid; i < kSmallFloats; i += kThreadsTC) sm[kSmSmallTC + i] = p.wpack[kSmallOff + i];
+    for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsTC) reinterpret_cast<double*>(sm + kSmPgTC)[i] = 0.0;
+    if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedTC) = 0.0;
+    ctx.sync();
+    if (tid == 0 && ctx.bid() < p.num_tiles) request_weights(false, 0);
     for (int tile = ctx.bid(); tile < p.num_tiles; tile += ctx.nblk()) {
       const bool more = tile + ctx.nblk() < p.num_tiles;
       load_tile(tile);
       ctx.sync();
-      for (int m = 0; m < p.N; ++m) fwd_window<HALF>(tile, m, more);
+      for (int m = 0; m < p.N; ++m) fwd_window(tile, m, more);
       store_costs(tile);
       if (p.with_grad) {
-        if (HALF == 0) {
+        if (quarter == 0) {
           for (int k = 0; k < p.N; ++k)
 #pragma unroll
             for (int f = 0; f < kFeat; ++f) grow[(size_t)(k * kFeat + f) * kTileTC + row] = 0.f;
         }
         ctx.sync();
-        for (int m = p.N - 1; m >= 0; --m) bwd_window<HALF>(tile, m, more);
+        for (int m = p.N - 1; m >= 0; --m) bwd_window(tile, m, more);
         ctx.sync();
         store_du0(tile);
       }
       ctx.sync();
     }
-  }
-
-  FC_HD_CTX void run() {
-    ctx.tc_setup(sm + kSmBarTC);
-    for (int i = tid; i < kSmallFloats; i += kThreads) sm[kSmSmallTC + i] = p.wpack[kSmallOff + i];
-    for (int i = tid; i < 4 * kNumFnnGrad; i += kThreads) reinterpret_cast<double*>(sm + kSmPgTC)[i] = 0.0;
-    if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedTC) = 0.0;
-    ctx.sync();
-    if (tid == 0 && ctx.bid() < p.num_tiles) request_weights(false, 0);
-    if (half == 0) run_half<0>(); else run_half<1>();
     double* part = p.partial + (size_t)ctx.bid() * kPartialStride;
     const double* pgd = reinterpret_cast<const double*>(sm + kSmPgTC);
-    for (int i = tid; i < kNumFnnGrad; i += kThreads)
+    for (int i = tid; i < kNumFnnGrad; i += kThreadsTC)
       part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
     if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedTC);
     ctx.sync();

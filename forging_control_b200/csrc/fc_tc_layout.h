@@ -1,19 +1,20 @@
 // Layouts of the tcgen05 (3xTF32) variant of the fused MPC-loss kernel.  Shared by the device code,
 // the weight packer and the CPU thread-emulation harness.  See DESIGN.md section 2.3.
 //
-// CTA tile = 128 trajectories = the 128 TMEM lanes.  256 threads: thread (warp w, lane i) owns TMEM
+// CTA tile = 128 trajectories = the 128 TMEM lanes.  512 threads: thread (warp w, lane i) owns TMEM
 // lane / trajectory row r = 32*(w%4)+i (the only lanes warp w may touch with tcgen05.ld/st) and the
-// hidden units of half h = w/4:  half 0 -> units 0..23, half 1 -> units 24..49.
+// hidden units of quarter q = w/4:  q=0 -> units 0..12, q=1 -> 13..25, q=2 -> 26..37, q=3 -> 38..49
+// (13,13,12,12 units; every thread runs 13 unit slots, the 13th is masked for q >= 2).
 //
 // forward  phase: D[128 x 208] (TMEM fp32) = A[128 x K] (TMEM, tf32 hi/lo) * WF^T (smem [208 x K], tf32 hi/lo)
 //                 gate column n = unit*4 + gate (i,f,g,o); columns 200..207 are zero padding
 //                 A column k: layers 1,2: [0,50) input units | [50,100) recurrent units | 4 zero
 //                             layer 0   : [0,5) row features | 3 zero | [8,58) recurrent units | 6 zero
 // backward phase: D[128 x Nb] = dG[128 x 200] (TMEM hi/lo, column g = unit*4+gate) * WB^T (smem [Nb x 200])
-//                 layers 1,2 (Nb=112): [0,24) d input units 0..23 | [24,48) d h_prev units 0..23 |
-//                                      [48,74) d input units 24..49 | [74,100) d h_prev units 24..49 | 12 zero
-//                 layer 0    (Nb=64) : [0,24) d h_prev 0..23 | [24,29) d row features | 3 zero |
-//                                      [32,58) d h_prev 24..49 | 6 zero
+//                 layers 1,2 (Nb=112): quarter q owns columns [26q, 26q+26): 13 slots d(input unit) then 13 slots
+//                                      d(h_prev unit) of its units (unused slots have zero weights); 8 zero
+//                 layer 0    (Nb=64) : quarter q owns [13q, 13q+13) d(h_prev unit); [52,57) d(row feature)
+//                                      (read by quarter 0); 7 zero
 // smem operand images are the canonical K-major / no-swizzle UMMA layout: [k/4][row][4 floats]
 // (core matrix = 8 rows x 16 bytes contiguous; LBO = rows*16 B between K chunks, SBO = 128 B).
 #pragma once
@@ -28,8 +29,11 @@ constexpr int kKF0 = 64, kKF = 104;      // forward K per layer (multiple of 8)
 constexpr int kRec0 = 8, kRec = 50;      // first recurrent A column (layer 0 / layers 1,2)
 constexpr int kKB = 200;                 // backward K
 constexpr int kNB0 = 64, kNB = 112;      // backward output columns per layer
-constexpr int kUnits0 = 24, kUnits1 = 26;   // units owned by half 0 / half 1
-constexpr int kMaxOwn = 26;
+constexpr int kThreadsTC = 512, kWarpsTC = 16;
+constexpr int kMaxOwn = 13;              // unit slots per thread
+FC_HD int units_of(int q) { return q < 2 ? 13 : 12; }
+FC_HD int first_unit(int q) { return q < 2 ? 13 * q : 26 + 12 * (q - 2); }
+FC_HD int unit_quarter(int u) { return u < 13 ? 0 : (u < 26 ? 1 : (u < 38 ? 2 : 3)); }
 
 FC_HD int kf_of(int l) { return l == 0 ? kKF0 : kKF; }
 FC_HD int nb_of(int l) { return l == 0 ? kNB0 : kNB; }
@@ -74,15 +78,19 @@ FC_HD float tc_packed_value(const RawWeights& w, int idx) {
   int n = rem / 4, g = kc * 4 + (rem & 3);
   int row = gate_row(g);
   if (l == 0) {
-    if (n < 24) return w.w_hh[0][row * kHid + n];
-    if (n < 29) return w.w_ih[0][row * kFeat + (n - 24)];
-    if (n >= 32 && n < 58) return w.w_hh[0][row * kHid + 24 + (n - 32)];
+    if (n < 52) {
+      int q = n / 13, sl = n - q * 13;
+      return sl < units_of(q) ? w.w_hh[0][row * kHid + first_unit(q) + sl] : 0.f;
+    }
+    if (n < 57) return w.w_ih[0][row * kFeat + (n - 52)];
     return 0.f;
   }
-  if (n < 24) return w.w_ih[l][row * kHid + n];
-  if (n < 48) return w.w_hh[l][row * kHid + (n - 24)];
-  if (n < 74) return w.w_ih[l][row * kHid + 24 + (n - 48)];
-  if (n < 100) return w.w_hh[l][row * kHid + 24 + (n - 74)];
+  if (n < 104) {
+    int q = n / 26, r2 = n - q * 26, sl = r2 % 13;
+    if (sl >= units_of(q)) return 0.f;
+    int u = first_unit(q) + sl;
+    return r2 < 13 ? w.w_ih[l][row * kHid + u] : w.w_hh[l][row * kHid + u];
+  }
   return 0.f;
 }
 FC_HD bool tc_is_lo(int idx) {
@@ -100,18 +108,16 @@ constexpr int kColD = 0;
 constexpr int kColAhi = 256, kColAlo = 384;          // forward A operand
 constexpr int kColGhi = 112, kColGlo = 312;          // backward A operand (dG), 200 columns each
 
-// forward accumulator chunks (column ranges, multiples of 16): issue order A0, B0, A1, B1
-//   half 0: A0 = [0,48) units 0..11, A1 = [48,96) units 12..23
-//   half 1: B0 = [96,160) units 24..39, B1 = [160,208) units 40..49 (+2 padding units)
-constexpr int kNumChunks = 4;
-FC_HD int chunk_col(int c) { return c == 0 ? 0 : (c == 1 ? 96 : (c == 2 ? 48 : 160)); }
-FC_HD int chunk_n(int c) { return c == 1 ? 64 : 48; }
+// One accumulator group per step: every tcgen05.mma costs ~100 cycles whatever its N (the A operand is
+// fetched from TMEM per instruction), so column chunking to overlap cell update and MMA does not pay
+// (measured: 39 MMAs N=208 4340 cycles, 78 MMAs N=96/112 7490, 156 MMAs N=48/64 15400).
 
 // per-CTA global workspace (floats); every slot is private to one thread
-//   rows [(N+10)][5][128], seq [10][8][26][32], dseq [10][8][26][32], grow [N][5][128],
-//   rec [nrec][8][33][32] float4
-constexpr int kSlot = kWarps * kMaxOwn * 32;                 // 6656
-constexpr int kRecFloatsTC = kWarps * 33 * 32 * 4;          // 33792
+//   rows [(N+10)][5][128], seq [10][16][13][32], dseq [10][16][13][32], grow [N][5][128],
+//   rec [nrec][16][17][32] float4   (13 units x (i,f,g,o,c_prev) = 65 floats -> 17 float4)
+constexpr int kSlot = kWarpsTC * kMaxOwn * 32;               // 6656
+constexpr int kRecF4 = 17;
+constexpr int kRecFloatsTC = kWarpsTC * kRecF4 * 32 * 4;    // 34816
 struct WorkLayoutTC {
   size_t rows, seq, dseq, grow, rec, total;
 };
@@ -137,8 +143,8 @@ constexpr int kSmCostTC = kSmUprevTC + kTileTC;             // [3][128]
 constexpr int kSmGxTC = kSmCostTC + 3 * kTileTC;            // [4][128]
 constexpr int kSmDvTC = kSmGxTC + 4 * kTileTC;              // [128]
 constexpr int kSmFinTC = kSmDvTC + kTileTC;                 // [2][128]
-constexpr int kSmFcpTC = kSmFinTC + 2 * kTileTC;            // [4][128] read-out partial sums of half 1
-constexpr int kSmPgTC = kSmFcpTC + 4 * kTileTC;             // double [4][250]
+constexpr int kSmFcpTC = kSmFinTC + 2 * kTileTC;            // [3][4][128] read-out partial sums of quarters 1..3
+constexpr int kSmPgTC = kSmFcpTC + 12 * kTileTC;            // double [4][250]
 constexpr int kSmRedTC = kSmPgTC + 8 * kNumFnnGrad;         // double [4]
 static_assert(kSmPgTC % 2 == 0, "double alignment");
 constexpr int kSmBarTC = ((kSmRedTC + 8 + 3) / 4) * 4;      // 8 mbarriers (64-bit) + tmem base

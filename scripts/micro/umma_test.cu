@@ -132,6 +132,25 @@ __global__ void __launch_bounds__(256, 1) umma_test_kernel(const float* __restri
       if (mode == 3) { ta[0] = 1; tb[0] = 0; ta[1] = 0; tb[1] = 1; ta[2] = 0; tb[2] = 0; nterm = 3; }
       if (mode == 4) { ta[0] = 1; tb[0] = 1; ta[1] = 1; tb[1] = 0; ta[2] = 0; tb[2] = 1; ta[3] = 0; tb[3] = 0; nterm = 4; }
       if (mode == 5) { ta[0] = 0; tb[0] = 0; ta[1] = 1; tb[1] = 0; ta[2] = 0; tb[2] = 1; nterm = 3; }
+      if (mode == 12 || mode == 13) {
+        const int nch = mode == 13 ? 4 : 2;
+        const int c0[4] = {0, mode == 13 ? 48 : 96, 96, 160};
+        const int cn[4] = {mode == 13 ? 48 : 96, mode == 13 ? 48 : 112, 64, 48};
+        for (int ch = 0; ch < nch; ++ch) {
+          const uint32_t idc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cn[ch] >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+          acc = 0;
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a_col = term == 0 ? COL_ALO : COL_AHI;
+            const uint32_t b_addr = smem_u32(term == 1 ? b_lo : b_hi) + (c0[ch] / 8) * 128;
+#pragma unroll 1
+            for (int ks = 0; ks < K / 8; ++ks) {
+              uint64_t bd = make_desc(b_addr + ks * 2 * lbo, lbo, sbo);
+              mma_tf32_ts(tbase + COL_D + c0[ch], tbase + a_col + ks * 8, bd, idc, acc);
+              acc = 1;
+            }
+          }
+        }
+      } else
       for (int term = 0; term < nterm; ++term) {
         const uint32_t a_col = ta[term] ? COL_ALO : COL_AHI;
         const uint32_t b_addr = smem_u32(tb[term] ? b_lo : b_hi);
@@ -195,8 +214,8 @@ int main() {
   for (auto& v : A) { float r = (rand() / (float)RAND_MAX) * 2 - 1; v = dist ? r : r * r * r; }
   for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { double s2 = 0; for (int k = 0; k < K; ++k) s2 += (double)A[m * K + k] * (double)B[n * K + k]; ref[m * N + n] = s2; }
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
-  for (int mode : {3}) {
-    for (int reps : {1}) {
+  for (int mode : {3, 12, 13}) {
+    for (int reps : {1, 100}) {
       cudaMemset(dO, 0, out.size() * 4);
       umma_test_kernel<<<1, 256, smem_bytes>>>(dA, dB, dO, mode, reps, dC);
       cudaError_t e = cudaDeviceSynchronize();

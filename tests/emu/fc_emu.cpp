@@ -25,7 +25,7 @@ struct EmuBlock {
   std::barrier<> bar;
   std::vector<float> smem;
   int bid, nblk;
-  EmuBlock(int b, int n) : bar(fc::kThreads), smem(fc::kSmFloats, 0.f), bid(b), nblk(n) {}
+  EmuBlock(int b, int n, int nthreads = fc::kThreads) : bar(nthreads), smem(fc::kSmFloats, 0.f), bid(b), nblk(n) {}
 };
 
 struct EmuCtx {
@@ -56,7 +56,7 @@ struct EmuCtx {
 struct EmuBlockTC : EmuBlock {
   std::vector<float> tmem;
   std::atomic<unsigned> bars[8];
-  EmuBlockTC(int b, int n) : EmuBlock(b, n), tmem(128 * 512, 0.f) {
+  EmuBlockTC(int b, int n) : EmuBlock(b, n, fc::tc::kThreadsTC), tmem(128 * 512, 0.f) {
     smem.assign(fc::tc::kSmFloatsTC, 0.f);
     for (auto& x : bars) x.store(0);
   }
@@ -74,6 +74,8 @@ struct EmuCtxTC : EmuCtx {
   void tc_teardown() { sync(); }
   void tc_sync() const { sync(); }
   template <int N> void tmem_ld(int col, float* v) const { for (int i = 0; i < N; ++i) v[i] = tb->tmem[row() * 512 + col + i]; }
+  template <int N> void tmem_ld_nowait(int col, float* v) const { tmem_ld<N>(col, v); }
+  void tmem_ld_wait() const {}
   template <int N> void tmem_st(int col, const float* v) const { for (int i = 0; i < N; ++i) tb->tmem[row() * 512 + col + i] = v[i]; }
   void tmem_st_wait() const {}
   static float tf32(float x) {   // cvt.rna.tf32.f32: round to nearest, ties away, keep 10 mantissa bits
@@ -198,8 +200,8 @@ int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const fl
   for (int b = 0; b < grid; ++b) {
     EmuBlockTC blk(b, grid);
     std::vector<std::thread> th;
-    th.reserve(fc::kThreads);
-    for (int t = 0; t < fc::kThreads; ++t)
+    th.reserve(fc::tc::kThreadsTC);
+    for (int t = 0; t < fc::tc::kThreadsTC; ++t)
       th.emplace_back([&blk, &p, t]() {
         EmuCtxTC ctx(&blk, t);
         fc::tc::MpcTileTC<EmuCtxTC> k(ctx, p);
