@@ -198,6 +198,7 @@ struct MpcParams {
   float alpha;
   float grad_scale;      // 1 / (N * B_global)
   float acc_comp;        // scale of the tensor-core accumulator compensation (1 = calibrated value)
+  int debug_timing;      // CTA 0 prints a cycle breakdown (development aid)
 };
 
 }  // namespace fc

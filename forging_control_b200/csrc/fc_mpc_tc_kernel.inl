@@ -26,6 +26,9 @@ struct MpcTileTC {
   float c[kMaxOwn];      // forward: cell state, backward: d(cell state)
   float hrec[kMaxOwn];   // backward: d(h) from step t+1
   unsigned ph[8];        // completed phases per mbarrier
+#ifdef FC_TC_TIMING
+  long long tm[8], tlast;  // cycle breakdown of thread 0 (development aid, -DFC_TC_TIMING)
+#endif
 
   FC_HD_CTX MpcTileTC(Ctx& c_, const MpcParams& p_) : ctx(c_), p(p_) {
     sm = ctx.smem();
@@ -46,7 +49,16 @@ struct MpcTileTC {
     rec = base + wl.rec;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ph[i] = 0;
+#ifdef FC_TC_TIMING
+    for (int i = 0; i < 8; ++i) tm[i] = 0;
+    tlast = 0;
+#endif
   }
+#ifdef FC_TC_TIMING
+  FC_HD_CTX void lap(int k) { long long t = Ctx::clock(); tm[k] += t - tlast; tlast = t; }
+#else
+  FC_HD_CTX void lap(int) {}
+#endif
 
   FC_HD_CTX static float sigmoidf_(float x) { return Ctx::rcp(1.f + Ctx::ex2(-1.4426950408889634f * x)); }
   // tanh: 1 - 2/(1+e^{2x}) has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is a large
@@ -245,21 +257,24 @@ struct MpcTileTC {
         float* rec_out = nullptr;
         if (p.with_grad && t >= tmin) rec_out = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
         const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
+        lap(0);
         wait_bar(kBarChunk0);                              // accumulator complete; A and the image are free again
+        lap(1);
         if (t == kLook - 1 && tid == 0) {                  // stream the next operand image under the cell update
           if (l + 1 < kLayers) request_weights(false, l + 1);
           else if (m + 1 < p.N) request_weights(false, 0);
           else if (p.with_grad) request_weights(true, kLayers - 1);
           else if (more_after) request_weights(false, 0);
         }
+        if (t + 1 < kLook) store_input(l, xin);            // input columns of step t+1: overlap with the cell update
         fwd_pointwise(t == 0, corr, h, rec_out);
+        lap(2);
         if (l + 1 < kLayers) {
           float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
 #pragma unroll
           for (int j = 0; j < kMaxOwn; ++j) sq[j * 32] = h[j];
         }
         if (t + 1 < kLook) {
-          store_input(l, xin);
           st_own(kColAhi + rec0 + u_first, kColAlo + rec0 + u_first, h);
           ctx.tmem_st_wait();
         } else if (l == kLayers - 1) {
@@ -281,6 +296,7 @@ struct MpcTileTC {
           }
         }
         ctx.tc_sync();
+        lap(3);
       }
     }
     if (quarter == 0) fwd_glue(tile, m);
@@ -357,6 +373,11 @@ struct MpcTileTC {
       fa.Kg[j] = gi * (1.f - gg * gg);
       fa.Gf[j] = gf;
     }
+  }
+  FC_HD_CTX void prefetch_record(const float* rec_in) {
+    const float* rp = rec_in + ((size_t)warp * kRecF4 * 32 + lane) * 4;
+#pragma unroll
+    for (int r = 0; r < kRecF4; ++r) Ctx::prefetch_l2(rp + (size_t)r * 32 * 4);
   }
   FC_HD_CTX void bwd_factors(const float* rec_in, Factors& fa) {
     const float* rp = rec_in + ((size_t)warp * kRecF4 * 32 + lane) * 4;
@@ -518,16 +539,25 @@ struct MpcTileTC {
       bwd_extra(l, kLook - 1, extra);
       wait_bar(kBarWeights);
       for (int t = kLook - 1; t >= tmin; --t) {
+        lap(0);
         bwd_finish(fa, extra);
         ctx.tmem_st_wait();
+        lap(4);
         ctx.tc_sync();
+        lap(5);
         if (tid == 0) issue_mma(kColD, nb, kColGhi, kColGlo, kKB / 8, bwd_img_floats(l), kBarChunk0);
         // in the shadow of the MMA: record and upstream gradient of the next step
         if (t > tmin) {
+          // HBM -> L2 for the step after next (or the first step of the next layer / window)
+          if (t - 2 >= tmin) prefetch_record(rec_l + (size_t)(t - 2 - tmin) * kRecFloatsTC);
+          else if (l > 0) prefetch_record(rec + (size_t)(rec_base(m) + (long)(l - 1) * steps_kept(m) + (kLook - 1 - tmin)) * kRecFloatsTC);
+          else if (m > 0) prefetch_record(rec + (size_t)(rec_base(m - 1) + (long)(kLayers - 1) * steps_kept(m - 1) + (kLook - 1 - t_min_of(m - 1))) * kRecFloatsTC);
           bwd_factors(rec_l + (size_t)(t - 1 - tmin) * kRecFloatsTC, fa);
           bwd_extra(l, t - 1, extra);
         }
+        lap(6);
         wait_bar(kBarChunk0);
+        lap(7);
         if (t == tmin && tid == 0) {                   // all MMAs that read this image are complete
           if (l > 0) request_weights(true, l - 1);
           else if (m > 0) request_weights(true, kLayers - 1);
@@ -642,6 +672,9 @@ struct MpcTileTC {
       part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
     if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedTC);
     ctx.sync();
+#ifdef FC_TC_TIMING
+    if (p.debug_timing && tid == 0 && ctx.bid() == 0) Ctx::report(tm);
+#endif
     ctx.tc_teardown();
   }
 };

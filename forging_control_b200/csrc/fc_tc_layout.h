@@ -29,7 +29,8 @@ constexpr int kKF0 = 64, kKF = 104;      // forward K per layer (multiple of 8)
 constexpr int kRec0 = 8, kRec = 50;      // first recurrent A column (layer 0 / layers 1,2)
 constexpr int kKB = 200;                 // backward K
 constexpr int kNB0 = 64, kNB = 112;      // backward output columns per layer
-constexpr int kThreadsTC = 512, kWarpsTC = 16;
+constexpr int kWarpsTC = 16;
+constexpr int kThreadsTC = kWarpsTC * 32;
 constexpr int kMaxOwn = 13;              // unit slots per thread
 FC_HD int units_of(int q) { return q < 2 ? 13 : 12; }
 FC_HD int first_unit(int q) { return q < 2 ? 13 * q : 26 + 12 * (q - 2); }

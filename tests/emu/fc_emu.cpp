@@ -84,6 +84,9 @@ struct EmuCtxTC : EmuCtx {
   // the emulation accumulates exactly (round to nearest): it checks index arithmetic and dataflow, not the
   // truncating accumulator of the hardware, so the kernel's accumulator compensation is switched off
   static constexpr bool kAccTruncates = false;
+  static long long clock() { return 0; }
+  static void prefetch_l2(const float*) {}
+  static void report(const long long*) {}
   void mma(int d_col, int n, int a_col, const float* b_img, int n_img, int row0, int ksteps, bool accumulate) const {
     const int K = ksteps * 8;
     for (int m = 0; m < 128; ++m) {
