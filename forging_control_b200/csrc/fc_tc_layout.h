@@ -1,5 +1,5 @@
 // Layouts of the tcgen05 (3xTF32) variant of the fused MPC-loss kernel.  Shared by the device code,
-// the weight packer and the CPU thread-emulation harness.  See DESIGN.md section 2.3.
+// the weight packer and the CPU thread-emulation harness.  See DESIGN.md section 2.2.
 //
 // CTA tile = 128 trajectories = the 128 TMEM lanes.  512 threads: thread (warp w, lane i) owns TMEM
 // lane / trajectory row r = 32*(w%4)+i (the only lanes warp w may touch with tcgen05.ld/st) and the
