@@ -344,14 +344,15 @@ struct MpcPlan {
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
-// The gate contraction goes to the tensor cores when the batch fills at least half of one M=128 tile
-// (a real dense GEMM); tiny batches (the reference's own B=15) stay on the FFMA kernel.
+// Automatic choice = tcgen05 kernel for every batch size: measured on B200 (profiles/r01_bench_configs_both_kernels.jsonl)
+// it is 2.5x faster than the FFMA kernel from the reference's own B=15 (2.9 ms vs 7.5 ms per step; one M=128 tile is
+// the smallest MMA either way) up to B=524288 (57 M vs 23 M trajectory-steps/s).  The FFMA kernel stays selectable.
 static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
-  pl->use_tc = mode == 2 || (mode == 0 && B >= 64);
+  pl->use_tc = mode == 2 || mode == 0;
   const int tile = pl->use_tc ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
   pl->grid = pl->tiles < sms ? pl->tiles : sms;

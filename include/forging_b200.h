@@ -58,7 +58,7 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
  *   du0 [B] = d loss / d output_controller), gl[250] = sum_b cost[b] / B_global (the loss).
  *   with_grad = 0 computes the forward only (du0 may be NULL, gl[0..249] are zero).              */
 size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad);
-/* Kernel behind fc_mpc_loss: 0 = automatic (tcgen05 3xTF32 kernel when B >= 64, FP32 FFMA kernel below),
+/* Kernel behind fc_mpc_loss: 0 = automatic (the tcgen05 3xTF32 kernel; measured faster at every batch size),
  * 1 = always the FP32 FFMA kernel, 2 = always the tcgen05 kernel.  Also settable with the environment
  * variable FC_MPC_KERNEL=ffma|tc before the first call.  Both kernels meet the same parity bar.      */
 int fc_mpc_select_kernel(int mode);
