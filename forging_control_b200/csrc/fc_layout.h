@@ -199,6 +199,8 @@ struct MpcParams {
   float grad_scale;      // 1 / (N * B_global)
   float acc_comp;        // scale of the tensor-core accumulator compensation (1 = calibrated value)
   int debug_timing;      // CTA 0 prints a cycle breakdown (development aid)
+  float g_scale;         // tcgen05 kernel: power-of-two scale of the gate gradients before the fp16 split
+  float g_unscale;       // 1 / g_scale
 };
 
 }  // namespace fc

@@ -1,11 +1,13 @@
-// tcgen05 (3xTF32) variant of the fused MPC-loss forward + reverse sweep.  Same mathematics and the
+// tcgen05 variant of the fused MPC-loss forward + reverse sweep (fp16 hi/lo split operands).  Same mathematics and the
 // same reference citations as fc_mpc_kernel.inl (MPCLoss.forward Functions.py:1353-1472,
 // LSTMModel.forward :353-379, FNNModel.forward :261-289, loss.backward() :655); what changes is where the
 // 99.9 % of the FLOPs run: the per-step gate contraction [128 trajectories x K] x [K x 200 gates] is a
 // real dense GEMM, so it goes to the 5th-generation tensor cores:
-//   * weights: tf32 hi/lo images resident in shared memory (B operand, K-major, no swizzle)
-//   * activations (A operand, hi/lo) and the fp32 accumulator live in TMEM, one trajectory per lane
-//   * error-compensated split  a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (same error as an fp32 FMA chain)
+//   * weights: fp16 hi/lo images (x 2^11) resident in shared memory (B operand, K-major, no swizzle)
+//   * activations (A operand, fp16 hi/lo of x 2^10, two K-elements per 32-bit column) and the fp32
+//     accumulator live in TMEM, one trajectory per lane
+//   * error-compensated split  a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (2 x 11 bits per operand: same error
+//     as an fp32 FMA chain; kind::f16 takes K=16 per instruction, half the instructions of 3xTF32)
 //   * the thread that owns TMEM lane r does the cell update of trajectory r: no cross-thread exchange
 // Written against the same execution-context interface as the FFMA kernel (+ TMEM / MMA / mbarrier
 // operations) so that g++ can compile it into the CPU thread emulation of tests/emu.
@@ -76,37 +78,42 @@ struct MpcTileTC {
 
   FC_HD_CTX void wait_bar(int b) { ctx.bar_wait(b, ph[b]); ph[b] += 1; }
 
-  // hi/lo split and store of N consecutive A-operand columns of the own lane
-  template <int N>
-  FC_HD_CTX void st_split(int col_hi, int col_lo, const float* v) {
-    float hi[N], lo[N];
+  // hi/lo fp16 split of 2*NP pre-scaled values and store into NP consecutive A-operand columns of the own lane
+  // (column c holds K-elements 2c (low half) and 2c+1 (high half))
+  template <int NP>
+  FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v, float scale) {
+    float hi[NP], lo[NP];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      hi[i] = Ctx::tf32(v[i]);
-      lo[i] = Ctx::tf32(v[i] - hi[i]);      // rounded (the MMA would truncate): unbiased, half the error
+    for (int i = 0; i < NP; ++i) {
+      const float x0 = fminf(fmaxf(v[2 * i] * scale, -kHalfMax), kHalfMax);
+      const float x1 = fminf(fmaxf(v[2 * i + 1] * scale, -kHalfMax), kHalfMax);
+      Ctx::split_h2(x0, x1, hi[i], lo[i]);
     }
-    ctx.template tmem_st<N>(col_hi, hi);
-    ctx.template tmem_st<N>(col_lo, lo);
+    ctx.template tmem_st<NP>(col_hi, hi);
+    ctx.template tmem_st<NP>(col_lo, lo);
   }
-  // the 12 or 13 owned unit columns starting at col
+  // the 13 (12) owned unit values -> the 7 (6) columns of this quarter's block starting at block column col
   FC_HD_CTX void st_own(int col_hi, int col_lo, const float* v) {
-    st_split<8>(col_hi, col_lo, v);
-    st_split<4>(col_hi + 8, col_lo + 8, v + 8);
-    if (full) st_split<1>(col_hi + 12, col_lo + 12, v + 12);
+    st_pairs<4>(col_hi, col_lo, v, kScaleA);
+    st_pairs<2>(col_hi + 4, col_lo + 4, v + 8, kScaleA);
+    if (full) {
+      const float last[2] = {v[12], 0.f};
+      st_pairs<1>(col_hi + 6, col_lo + 6, last, kScaleA);
+    }
   }
 
   // ---------------------------------------------------------------------------------------------
   // operand images
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void request_weights(bool bwd, int l) {          // tid 0 only
-    const int n = 2 * (bwd ? bwd_img_floats(l) : fwd_img_floats(l));
+    const int n = bwd ? bwd_img_halves(l) : fwd_img_halves(l);   // hi + lo images of halves = that many floats
     ctx.bulk_load(sm + kSmWTC, p.wpack + (bwd ? wb_off(l) : wf_off(l)), n, kBarWeights);
   }
 
-  // one accumulator: 3 error-compensated terms, small ones first (tid 0 only)
-  FC_HD_CTX void issue_mma(int d_col, int n, int a_hi, int a_lo, int ksteps, int img_floats, int bar) {
+  // one accumulator: 3 error-compensated terms, small ones first (tid 0 only); K = 16 * ksteps
+  FC_HD_CTX void issue_mma(int d_col, int n, int a_hi, int a_lo, int ksteps, int img_halves, int bar) {
     const float* b_hi = sm + kSmWTC;
-    const float* b_lo = b_hi + img_floats;
+    const float* b_lo = b_hi + img_halves / 2;
     ctx.mma(d_col, n, a_lo, b_hi, n, 0, ksteps, false);
     ctx.mma(d_col, n, a_hi, b_lo, n, 0, ksteps, true);
     ctx.mma(d_col, n, a_hi, b_hi, n, 0, ksteps, true);
@@ -168,6 +175,7 @@ struct MpcTileTC {
 
   // all unit slots of one step (the accumulator barrier has been waited for by the caller)
   FC_HD_CTX void fwd_pointwise(bool first, float corr, float* h, float* rec_out) {
+    const float unscale = 1.0f / (kScaleA * kScaleW);      // exact power of two
     float* rp = rec_out ? rec_out + ((size_t)warp * kRecF4 * 32 + lane) * 4 : nullptr;
     const int col0 = kColD + 4 * u_first;
     float g[2][16];
@@ -180,13 +188,13 @@ struct MpcTileTC {
       else ctx.template tmem_ld_nowait<4>(col0 + 48, g[(gi + 1) & 1]);
       float* gg = g[gi & 1];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) gg[i] = fmaf(gg[i], corr, gg[i]);
+      for (int i = 0; i < 16; ++i) { gg[i] *= unscale; gg[i] = fmaf(gg[i], corr, gg[i]); }
       fwd_units<4>(gi * 4, gg, first, h, rp, gi * 5);
     }
     ctx.tmem_ld_wait();
     float* gg = g[1];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) gg[i] = fmaf(gg[i], corr, gg[i]);
+    for (int i = 0; i < 4; ++i) { gg[i] *= unscale; gg[i] = fmaf(gg[i], corr, gg[i]); }
     fwd_units<1>(12, gg, first, h, rp, 15);                // slot 12: a masked dummy for quarters 2,3
   }
 
@@ -207,11 +215,11 @@ struct MpcTileTC {
   FC_HD_CTX void store_input(int l, const float* xin) {
     if (l == 0) {
       if (quarter == 0) {
-        float v[8] = {xin[0], xin[1], xin[2], xin[3], xin[4], 0.f, 0.f, 0.f};
-        st_split<8>(kColAhi, kColAlo, v);
+        const float v[8] = {xin[0], xin[1], xin[2], xin[3], xin[4], 0.f, 0.f, 0.f};
+        st_pairs<4>(kColAhi, kColAlo, v, kScaleA);         // k = 0..7
       }
     } else {
-      st_own(kColAhi + u_first, kColAlo + u_first, xin);
+      st_own(kColAhi + block_start(quarter) / 2, kColAlo + block_start(quarter) / 2, xin);
     }
   }
 
@@ -221,27 +229,18 @@ struct MpcTileTC {
   FC_HD_CTX void fwd_window(int tile, int m, bool more_after) {
     const int tmin = t_min_of(m);
     for (int l = 0; l < kLayers; ++l) {
-      const int kf = kf_of(l), rec0 = l == 0 ? kRec0 : kRec;
+      const int kf = kf_of(l);
+      const int rec_col = (l == 0 ? kRec0 : kRec) / 2 + block_start(quarter) / 2;   // first recurrent column of this quarter
       float h[kMaxOwn], xin[kMaxOwn];
       // A(0): zero recurrent columns and padding, input of step 0
       {
-        float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        ctx.template tmem_st<8>(kColAhi + rec0 + u_first, z);
-        ctx.template tmem_st<4>(kColAhi + rec0 + u_first + 8, z);
-        ctx.template tmem_st<8>(kColAlo + rec0 + u_first, z);
-        ctx.template tmem_st<4>(kColAlo + rec0 + u_first + 8, z);
-        if (full) {
-          ctx.template tmem_st<1>(kColAhi + rec0 + u_first + 12, z);
-          ctx.template tmem_st<1>(kColAlo + rec0 + u_first + 12, z);
-        }
-        if (quarter == 3) {    // padding columns behind the recurrent block: layer 0 [58,64), layers 1,2 [100,104)
-          if (l == 0) {
-            ctx.template tmem_st<4>(kColAhi + 58, z); ctx.template tmem_st<2>(kColAhi + 62, z);
-            ctx.template tmem_st<4>(kColAlo + 58, z); ctx.template tmem_st<2>(kColAlo + 62, z);
-          } else {
-            ctx.template tmem_st<4>(kColAhi + 100, z);
-            ctx.template tmem_st<4>(kColAlo + 100, z);
-          }
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        ctx.template tmem_st<4>(kColAhi + rec_col, z); ctx.template tmem_st<2>(kColAhi + rec_col + 4, z);
+        ctx.template tmem_st<4>(kColAlo + rec_col, z); ctx.template tmem_st<2>(kColAlo + rec_col + 4, z);
+        if (full) { ctx.template tmem_st<1>(kColAhi + rec_col + 6, z); ctx.template tmem_st<1>(kColAlo + rec_col + 6, z); }
+        if (quarter == 3) {    // padding columns behind the recurrent block: layer 0 k [60,64), layers 1,2 k [104,112)
+          if (l == 0) { ctx.template tmem_st<2>(kColAhi + 30, z); ctx.template tmem_st<2>(kColAlo + 30, z); }
+          else        { ctx.template tmem_st<4>(kColAhi + 52, z); ctx.template tmem_st<4>(kColAlo + 52, z); }
         }
       }
       load_input(l, m, 0, xin);
@@ -251,15 +250,16 @@ struct MpcTileTC {
       ctx.tc_sync();
       for (int t = 0; t < kLook; ++t) {
         // at t = 0 the recurrent columns are zero: only the k-steps that cover the input columns
-        const int ksteps = t == 0 ? (l == 0 ? 1 : 7) : kf / 8;
-        if (tid == 0) issue_mma(kColD, kNF, kColAhi, kColAlo, ksteps, fwd_img_floats(l), kBarChunk0);
+        lap(0);
+        const int ksteps = t == 0 ? (l == 0 ? 1 : 4) : kf / 16;
+        if (tid == 0) issue_mma(kColD, kNF, kColAhi, kColAlo, ksteps, fwd_img_halves(l), kBarChunk0);
         if (t + 1 < kLook) load_input(l, m, t + 1, xin);
         float* rec_out = nullptr;
         if (p.with_grad && t >= tmin) rec_out = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
         const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
-        lap(0);
-        wait_bar(kBarChunk0);                              // accumulator complete; A and the image are free again
         lap(1);
+        wait_bar(kBarChunk0);                              // accumulator complete; A and the image are free again
+        lap(2);
         if (t == kLook - 1 && tid == 0) {                  // stream the next operand image under the cell update
           if (l + 1 < kLayers) request_weights(false, l + 1);
           else if (m + 1 < p.N) request_weights(false, 0);
@@ -268,14 +268,14 @@ struct MpcTileTC {
         }
         if (t + 1 < kLook) store_input(l, xin);            // input columns of step t+1: overlap with the cell update
         fwd_pointwise(t == 0, corr, h, rec_out);
-        lap(2);
+        lap(3);
         if (l + 1 < kLayers) {
           float* sq = seq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
 #pragma unroll
           for (int j = 0; j < kMaxOwn; ++j) sq[j * 32] = h[j];
         }
         if (t + 1 < kLook) {
-          st_own(kColAhi + rec0 + u_first, kColAlo + rec0 + u_first, h);
+          st_own(kColAhi + rec_col, kColAlo + rec_col, h);
           ctx.tmem_st_wait();
         } else if (l == kLayers - 1) {
           // read-out partial sums over the owned units (Functions.py:377)
@@ -296,7 +296,7 @@ struct MpcTileTC {
           }
         }
         ctx.tc_sync();
-        lap(3);
+        lap(4);
       }
     }
     if (quarter == 0) fwd_glue(tile, m);
@@ -426,16 +426,16 @@ struct MpcTileTC {
     }
   }
   FC_HD_CTX void bwd_finish(const Factors& fa, const float* extra) {
-    const int col0 = 4 * u_first;
+    const int col0 = 2 * u_first;                          // dG k-index = unit*4+gate, two per column
 #pragma unroll
     for (int gi = 0; gi < 3; ++gi) {
       float dg[16];
       finish_group<4>(gi * 4, fa, extra, dg);
-      st_split<16>(kColGhi + col0 + gi * 16, kColGlo + col0 + gi * 16, dg);
+      st_pairs<8>(kColGhi + col0 + gi * 8, kColGlo + col0 + gi * 8, dg, p.g_scale);
     }
     float dg[4];
     finish_group<1>(12, fa, extra, dg);                    // slot 12: computed by everybody, stored by the owners
-    if (full) st_split<4>(kColGhi + col0 + 48, kColGlo + col0 + 48, dg);
+    if (full) st_pairs<2>(kColGhi + col0 + 24, kColGlo + col0 + 24, dg, p.g_scale);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -525,13 +525,19 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void bwd_window(int tile, int m, bool more_after) {
     const int tmin = t_min_of(m);
-    const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 8, p.acc_comp) : 0.0f;
+    const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
+    const float unscale_b = p.g_unscale / kScaleW;         // exact power of two
     bwd_glue(tile, m);
     ctx.sync();
     for (int l = kLayers - 1; l >= 0; --l) {
       const int nb = nb_of(l);
 #pragma unroll
       for (int j = 0; j < kMaxOwn; ++j) { c[j] = 0.f; hrec[j] = 0.f; }
+      if (quarter == 3) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        ctx.template tmem_st<4>(kColGhi + 100, z);
+        ctx.template tmem_st<4>(kColGlo + 100, z);
+      }
       Factors fa;
       float extra[kMaxOwn];
       const float* rec_l = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m)) * kRecFloatsTC;
@@ -542,10 +548,9 @@ struct MpcTileTC {
         lap(0);
         bwd_finish(fa, extra);
         ctx.tmem_st_wait();
-        lap(4);
         ctx.tc_sync();
         lap(5);
-        if (tid == 0) issue_mma(kColD, nb, kColGhi, kColGlo, kKB / 8, bwd_img_floats(l), kBarChunk0);
+        if (tid == 0) issue_mma(kColD, nb, kColGhi, kColGlo, kKB / 16, bwd_img_halves(l), kBarChunk0);
         // in the shadow of the MMA: record and upstream gradient of the next step
         if (t > tmin) {
           // HBM -> L2 for the step after next (or the first step of the next layer / window)
@@ -569,6 +574,8 @@ struct MpcTileTC {
           ctx.template tmem_ld_nowait<8>(kColD + 26 * quarter + 16, d + 16);
           ctx.template tmem_ld_nowait<2>(kColD + 26 * quarter + 24, d + 24);
           ctx.tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 2 * kMaxOwn; ++j) d[j] *= unscale_b;
           float* dq = dseq + (size_t)t * kSlot + (size_t)warp * kMaxOwn * 32 + lane;
 #pragma unroll
           for (int j = 0; j < kMaxOwn; ++j) {
@@ -582,6 +589,10 @@ struct MpcTileTC {
           ctx.template tmem_ld_nowait<1>(kColD + 13 * quarter + 12, d + 12);
           if (quarter == 0) ctx.template tmem_ld_nowait<8>(kColD + 52, df);
           ctx.tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kMaxOwn; ++j) d[j] *= unscale_b;
+#pragma unroll
+          for (int f = 0; f < kFeat; ++f) df[f] *= unscale_b;
 #pragma unroll
           for (int j = 0; j < kMaxOwn; ++j) hrec[j] = fmaf(d[j], corr_b, d[j]);
           const int kr = m + t - (kLook - 1);          // gradient of row rho_{9+kr}
@@ -642,6 +653,9 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void run() {
     ctx.tc_setup(sm + kSmBarTC);
+#ifdef FC_TC_TIMING
+    tlast = Ctx::clock();
+#endif
     for (int i = tid; i < kSmallFloats; i += kThreadsTC) sm[kSmSmallTC + i] = p.wpack[kSmallOff + i];
     for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsTC) reinterpret_cast<double*>(sm + kSmPgTC)[i] = 0.0;
     if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedTC) = 0.0;

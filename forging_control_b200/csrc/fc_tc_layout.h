@@ -1,21 +1,28 @@
-// Layouts of the tcgen05 (3xTF32) variant of the fused MPC-loss kernel.  Shared by the device code,
-// the weight packer and the CPU thread-emulation harness.  See DESIGN.md section 2.2.
+// Layouts of the tcgen05 variant of the fused MPC-loss kernel (fp16 hi/lo split operands, fp32 accumulate).
+// Shared by the device code, the weight packer and the CPU thread-emulation harness.  See DESIGN.md section 2.2.
 //
 // CTA tile = 128 trajectories = the 128 TMEM lanes.  512 threads: thread (warp w, lane i) owns TMEM
 // lane / trajectory row r = 32*(w%4)+i (the only lanes warp w may touch with tcgen05.ld/st) and the
 // hidden units of quarter q = w/4:  q=0 -> units 0..12, q=1 -> 13..25, q=2 -> 26..37, q=3 -> 38..49
 // (13,13,12,12 units; every thread runs 13 unit slots, the 13th is masked for q >= 2).
 //
-// forward  phase: D[128 x 208] (TMEM fp32) = A[128 x K] (TMEM, tf32 hi/lo) * WF^T (smem [208 x K], tf32 hi/lo)
+// Operands are fp16 hi/lo pairs of power-of-two pre-scaled values (x*S = hi + lo, 2 x 11 bits): kind::f16 MMAs
+// take K=16 per instruction, half the instruction count of 3xTF32 for the same accuracy (measured,
+// profiles/r01_umma_fp16x2_feasibility.txt).  Two fp16 K-elements share one 32-bit TMEM column.
+//
+// K ordering: hidden units are laid out in per-quarter blocks of even size so that every thread owns whole
+// TMEM columns: block slot kb(u) = BS[q] + (u - first_unit(q)), BS = {0,14,28,40}, 52 slots (slot 13 of
+// quarters 0,1 is zero padding).
+// forward  phase: D[128 x 208] (TMEM fp32) = A[128 x K] (TMEM fp16 hi/lo) * WF^T (smem [208 x K] fp16 hi/lo)
 //                 gate column n = unit*4 + gate (i,f,g,o); columns 200..207 are zero padding
-//                 A column k: layers 1,2: [0,50) input units | [50,100) recurrent units | 4 zero
-//                             layer 0   : [0,5) row features | 3 zero | [8,58) recurrent units | 6 zero
-// backward phase: D[128 x Nb] = dG[128 x 200] (TMEM hi/lo, column g = unit*4+gate) * WB^T (smem [Nb x 200])
+//                 A k-index: layers 1,2 (K=112): [0,52) input slots | [52,104) recurrent slots | 8 zero
+//                            layer 0   (K=64) : [0,5) row features | 3 zero | [8,60) recurrent slots | 4 zero
+// backward phase: D[128 x Nb] = dG[128 x 208] (TMEM fp16 hi/lo, k = unit*4+gate, 8 zero) * WB^T (smem [Nb x 208])
 //                 layers 1,2 (Nb=112): quarter q owns columns [26q, 26q+26): 13 slots d(input unit) then 13 slots
 //                                      d(h_prev unit) of its units (unused slots have zero weights); 8 zero
 //                 layer 0    (Nb=64) : quarter q owns [13q, 13q+13) d(h_prev unit); [52,57) d(row feature)
 //                                      (read by quarter 0); 7 zero
-// smem operand images are the canonical K-major / no-swizzle UMMA layout: [k/4][row][4 floats]
+// smem operand images are the canonical K-major / no-swizzle UMMA layout for 16-bit types: [k/8][row][8 halves]
 // (core matrix = 8 rows x 16 bytes contiguous; LBO = rows*16 B between K chunks, SBO = 128 B).
 #pragma once
 #include "fc_layout.h"
@@ -25,58 +32,77 @@ namespace tc {
 
 constexpr int kTileTC = 128;
 constexpr int kNF = 208;                 // forward gate columns incl. padding
-constexpr int kKF0 = 64, kKF = 104;      // forward K per layer (multiple of 8)
-constexpr int kRec0 = 8, kRec = 50;      // first recurrent A column (layer 0 / layers 1,2)
-constexpr int kKB = 200;                 // backward K
+constexpr int kKF0 = 64, kKF = 112;      // forward K per layer (multiple of 16)
+constexpr int kSlots = 52;               // unit slots (per-quarter blocks 14,14,12,12)
+constexpr int kRec0 = 8, kRec = 52;      // first recurrent k-index (layer 0 / layers 1,2)
+constexpr int kKB = 208;                 // backward K (200 gate gradients + 8 zero)
 constexpr int kNB0 = 64, kNB = 112;      // backward output columns per layer
 constexpr int kWarpsTC = 16;
 constexpr int kThreadsTC = kWarpsTC * 32;
 constexpr int kMaxOwn = 13;              // unit slots per thread
+// power-of-two operand scales (exact): activations / row features x 2^10 (|x| < 58), weights x 2^11 (|w| < 29);
+// gate gradients x 2^g_exp chosen per launch from N * B_global
+constexpr float kScaleA = 1024.0f, kScaleW = 2048.0f;
+constexpr float kHalfMax = 60000.0f;     // saturation bound applied before the fp16 conversion
+
 FC_HD int units_of(int q) { return q < 2 ? 13 : 12; }
 FC_HD int first_unit(int q) { return q < 2 ? 13 * q : 26 + 12 * (q - 2); }
-FC_HD int unit_quarter(int u) { return u < 13 ? 0 : (u < 26 ? 1 : (u < 38 ? 2 : 3)); }
+FC_HD int block_start(int q) { return q == 0 ? 0 : (q == 1 ? 14 : (q == 2 ? 28 : 40)); }
+// unit of block slot kb (or -1 for padding slots)
+FC_HD int slot_unit(int kb) {
+  int q = kb < 14 ? 0 : (kb < 28 ? 1 : (kb < 40 ? 2 : 3));
+  int j = kb - block_start(q);
+  return j < units_of(q) ? first_unit(q) + j : -1;
+}
 
 FC_HD int kf_of(int l) { return l == 0 ? kKF0 : kKF; }
 FC_HD int nb_of(int l) { return l == 0 ? kNB0 : kNB; }
-FC_HD int fwd_img_floats(int l) { return kNF * kf_of(l); }          // one of hi / lo
-FC_HD int bwd_img_floats(int l) { return nb_of(l) * kKB; }
+// operand images are fp16: sizes in HALVES for one of hi / lo (multiples of 8); hi + lo = that many floats
+FC_HD int fwd_img_halves(int l) { return kNF * kf_of(l); }
+FC_HD int bwd_img_halves(int l) { return nb_of(l) * kKB; }
 
-// packed weight buffer (floats): per layer [hi image | lo image] forward, then backward, then the
-// small fc/fnn block of the FFMA layout (kSmallFloats)
-FC_HD int wf_off(int l) { return l == 0 ? 0 : 2 * fwd_img_floats(0) + (l - 1) * 2 * fwd_img_floats(1); }
-constexpr int kFwdTotal = 2 * kNF * kKF0 + 4 * kNF * kKF;              // 113152
-FC_HD int wb_off(int l) { return kFwdTotal + (l == 0 ? 0 : 2 * bwd_img_floats(0) + (l - 1) * 2 * bwd_img_floats(1)); }
-constexpr int kBwdTotal = 2 * kNB0 * kKB + 4 * kNB * kKB;              // 115200
-constexpr int kSmallOff = kFwdTotal + kBwdTotal;                       // 228352
-constexpr int kPackFloatsTC = kSmallOff + kSmallFloats;                // 228808
+// packed weight buffer (offsets in floats = 2 halves): per layer [hi image | lo image] forward, then backward,
+// then the small fc/fnn block of the FFMA layout (kSmallFloats, fp32)
+FC_HD int wf_off(int l) { return l == 0 ? 0 : fwd_img_halves(0) + (l - 1) * fwd_img_halves(1); }
+constexpr int kFwdTotal = kNF * kKF0 + 2 * kNF * kKF;                  // 59904
+FC_HD int wb_off(int l) { return kFwdTotal + (l == 0 ? 0 : bwd_img_halves(0) + (l - 1) * bwd_img_halves(1)); }
+constexpr int kBwdTotal = kNB0 * kKB + 2 * kNB * kKB;                  // 59904
+constexpr int kSmallOff = kFwdTotal + kBwdTotal;                       // 119808
+constexpr int kPackFloatsTC = kSmallOff + kSmallFloats;                // 120264
 
-// PyTorch gate row of gate column / dG column c = unit*4+gate
+// PyTorch gate row of gate column / dG index c = unit*4+gate
 FC_HD int gate_row(int c) { return (c & 3) * kHid + (c >> 2); }
 
-// value of element `idx` of the packed buffer BEFORE the hi/lo split (lo images repeat the hi index)
-FC_HD float tc_packed_value(const RawWeights& w, int idx) {
-  if (idx >= kSmallOff) return packed_value(w, kFCW + (idx - kSmallOff));
-  if (idx < kFwdTotal) {
-    int l = idx < wf_off(1) ? 0 : (idx < wf_off(2) ? 1 : 2);
-    int r = (idx - wf_off(l)) % fwd_img_floats(l);
-    int kc = r / (kNF * 4), rem = r - kc * (kNF * 4);
-    int n = rem / 4, k = kc * 4 + (rem & 3);
-    if (n >= kGates) return 0.f;
-    int row = gate_row(n);
-    if (l == 0) {
-      if (k < kFeat) return w.w_ih[0][row * kFeat + k];
-      if (k >= kRec0 && k < kRec0 + kHid) return w.w_hh[0][row * kHid + (k - kRec0)];
-      return 0.f;
+// UNSCALED weight behind half-element h of the forward image of layer l: h = (k/8)*(208*8) + n*8 + k%8
+FC_HD float fwd_weight(const RawWeights& w, int l, int h) {
+  int kc = h / (kNF * 8), rem = h - kc * (kNF * 8);
+  int n = rem / 8, k = kc * 8 + (rem & 7);
+  if (n >= kGates) return 0.f;
+  int row = gate_row(n);
+  if (l == 0) {
+    if (k < kFeat) return w.w_ih[0][row * kFeat + k];
+    if (k >= kRec0 && k < kRec0 + kSlots) {
+      int u = slot_unit(k - kRec0);
+      return u < 0 ? 0.f : w.w_hh[0][row * kHid + u];
     }
-    if (k < kHid) return w.w_ih[l][row * kHid + k];
-    if (k < 2 * kHid) return w.w_hh[l][row * kHid + (k - kHid)];
     return 0.f;
   }
-  int l = idx < wb_off(1) ? 0 : (idx < wb_off(2) ? 1 : 2);
-  int nb = nb_of(l);
-  int r = (idx - wb_off(l)) % bwd_img_floats(l);
-  int kc = r / (nb * 4), rem = r - kc * (nb * 4);
-  int n = rem / 4, g = kc * 4 + (rem & 3);
+  if (k < kSlots) {
+    int u = slot_unit(k);
+    return u < 0 ? 0.f : w.w_ih[l][row * kHid + u];
+  }
+  if (k < 2 * kSlots) {
+    int u = slot_unit(k - kSlots);
+    return u < 0 ? 0.f : w.w_hh[l][row * kHid + u];
+  }
+  return 0.f;
+}
+// backward image of layer l: h = (g/8)*(Nb*8) + n*8 + g%8, g = gate-gradient index unit*4+gate (>= 200: zero)
+FC_HD float bwd_weight(const RawWeights& w, int l, int h) {
+  const int nb = nb_of(l);
+  int kc = h / (nb * 8), rem = h - kc * (nb * 8);
+  int n = rem / 8, g = kc * 8 + (rem & 7);
+  if (g >= kGates) return 0.f;
   int row = gate_row(g);
   if (l == 0) {
     if (n < 52) {
@@ -94,24 +120,35 @@ FC_HD float tc_packed_value(const RawWeights& w, int idx) {
   }
   return 0.f;
 }
-FC_HD bool tc_is_lo(int idx) {
-  if (idx >= kSmallOff) return false;
-  if (idx < kFwdTotal) {
-    int l = idx < wf_off(1) ? 0 : (idx < wf_off(2) ? 1 : 2);
-    return (idx - wf_off(l)) >= fwd_img_floats(l);
+// decode a half index of the packed buffer: which image, layer, hi/lo and element
+struct TcSlot { int kind; int l; int lo; int h; };   // kind 0 = forward, 1 = backward
+FC_HD TcSlot tc_decode_half(long hidx) {             // hidx counts halves from the start of the TC pack buffer
+  TcSlot s;
+  const long f2 = 2L * kFwdTotal;
+  if (hidx < f2) {
+    s.kind = 0;
+    s.l = hidx < 2L * wf_off(1) ? 0 : (hidx < 2L * wf_off(2) ? 1 : 2);
+    long r = hidx - 2L * wf_off(s.l);
+    s.lo = r >= fwd_img_halves(s.l) ? 1 : 0;
+    s.h = (int)(r - (s.lo ? fwd_img_halves(s.l) : 0));
+  } else {
+    s.kind = 1;
+    s.l = hidx < 2L * wb_off(1) ? 0 : (hidx < 2L * wb_off(2) ? 1 : 2);
+    long r = hidx - 2L * wb_off(s.l);
+    s.lo = r >= bwd_img_halves(s.l) ? 1 : 0;
+    s.h = (int)(r - (s.lo ? bwd_img_halves(s.l) : 0));
   }
-  int l = idx < wb_off(1) ? 0 : (idx < wb_off(2) ? 1 : 2);
-  return (idx - wb_off(l)) >= bwd_img_floats(l);
+  return s;
 }
 
 // TMEM columns
 constexpr int kColD = 0;
-constexpr int kColAhi = 256, kColAlo = 384;          // forward A operand
-constexpr int kColGhi = 112, kColGlo = 312;          // backward A operand (dG), 200 columns each
+constexpr int kColAhi = 256, kColAlo = 320;          // forward A operand: K/2 = 56 columns each (2 fp16 per column)
+constexpr int kColGhi = 112, kColGlo = 216;          // backward A operand (dG): 104 columns each
 
 // One accumulator group per step: every tcgen05.mma costs ~100 cycles whatever its N (the A operand is
 // fetched from TMEM per instruction), so column chunking to overlap cell update and MMA does not pay
-// (measured: 39 MMAs N=208 4340 cycles, 78 MMAs N=96/112 7490, 156 MMAs N=48/64 15400).
+// (measured with tf32: 39 MMAs N=208 4340 cycles, 78 MMAs N=96/112 7490, 156 MMAs N=48/64 15400).
 
 // per-CTA global workspace (floats); every slot is private to one thread
 //   rows [(N+10)][5][128], seq [10][16][13][32], dseq [10][16][13][32], grow [N][5][128],
@@ -150,25 +187,25 @@ constexpr int kSmRedTC = kSmPgTC + 8 * kNumFnnGrad;         // double [4]
 static_assert(kSmPgTC % 2 == 0, "double alignment");
 constexpr int kSmBarTC = ((kSmRedTC + 8 + 3) / 4) * 4;      // 8 mbarriers (64-bit) + tmem base
 constexpr int kSmWTC = ((kSmBarTC + 24 + 255) / 256) * 256; // operand images, 1 KiB aligned
-constexpr int kSmWFloats = 2 * kNB * kKB;                   // 44800 >= 2*208*104 = 43264
+constexpr int kSmWFloats = kNB * kKB;                       // hi + lo fp16 images: 2*112*208 halves = 23296 floats
 constexpr int kSmFloatsTC = kSmWTC + kSmWFloats;
 constexpr size_t kSmBytesTC = (size_t)kSmFloatsTC * sizeof(float);
 static_assert(kSmBytesTC <= 227 * 1024, "shared memory budget exceeded (tcgen05 variant)");
-static_assert(2 * kNF * kKF <= kSmWFloats, "forward image does not fit");
+static_assert(kNF * kKF <= kSmWFloats, "forward image does not fit");
 
-// Expected-value compensation of the tensor-core accumulator.  tcgen05.mma adds every K=8 block into the
-// fp32 accumulator with TRUNCATION toward zero, so a chain of S accumulation steps of the hi*hi term
-// shrinks |D| by (0.17 + 0.135*S) * 2^-23 * |D| on average, independent of the data distribution
-// (measured on B200 with scripts/micro/umma_test.cu: S=8 -> 1.25 ulp, S=13 -> 1.95, S=25 -> 3.55; a
-// software model of a truncating accumulator gives the same law).  Left alone this systematic shrink does
-// not average out over the batch and costs a factor ~4 in gradient accuracy; multiplying the accumulator
-// by (1 + beta) -- as fmaf(x, beta, x), beta is a fraction of an ulp -- removes the mean and halves the rms
-// error (to that of an fp32 FMA chain).
+// Expected-value compensation of the tensor-core accumulator.  tcgen05.mma adds every K-block into the fp32
+// accumulator with TRUNCATION toward zero, so a chain of S accumulation steps of the hi*hi term shrinks |D| by
+// (0.17 + 0.135*S) * 2^-23 * |D| on average, independent of the data distribution (measured on B200 with
+// scripts/micro/umma_test.cu, kind::tf32: S=8 -> 1.25 ulp, S=13 -> 1.95, S=25 -> 3.55; kind::f16
+// (umma_f16_test.cu): S=7 -> 1.17, S=13 -> 2.0; a software model of a truncating accumulator gives the same law).
+// Left alone this systematic shrink does not average out over the batch and costs a factor ~4 in gradient
+// accuracy; multiplying the accumulator by (1 + beta) -- as fmaf(x, beta, x), beta is a fraction of an ulp --
+// removes the mean and halves the rms error (to that of an fp32 FMA chain).
 // returns beta; apply as fmaf(x, beta, x) so that fractions of an ulp are honoured in expectation
 FC_HD float acc_correction(int steps, float scale) { return scale * (0.17f + 0.135f * (float)steps) * 1.1920929e-7f; }
 
 // mbarrier ids
-constexpr int kBarChunk0 = 0;      // 0..3: forward chunk accumulators ready / backward: 0,1
+constexpr int kBarChunk0 = 0;      // accumulator of the current step complete
 constexpr int kBarWeights = 4;     // bulk copy of an operand image landed
 
 }  // namespace tc

@@ -62,9 +62,6 @@ struct EmuBlockTC : EmuBlock {
   }
 };
 
-static inline float tf32_trunc(float x) {
-  uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x;
-}
 
 struct EmuCtxTC : EmuCtx {
   EmuBlockTC* tb;
@@ -78,8 +75,13 @@ struct EmuCtxTC : EmuCtx {
   void tmem_ld_wait() const {}
   template <int N> void tmem_st(int col, const float* v) const { for (int i = 0; i < N; ++i) tb->tmem[row() * 512 + col + i] = v[i]; }
   void tmem_st_wait() const {}
-  static float tf32(float x) {   // cvt.rna.tf32.f32: round to nearest, ties away, keep 10 mantissa bits
-    uint32_t u; std::memcpy(&u, &x, 4); u += 0x1000u; u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x;
+  static uint16_t h_bits(float x) { _Float16 h = (_Float16)x; uint16_t u; std::memcpy(&u, &h, 2); return u; }
+  static float h_val(uint16_t u) { _Float16 h; std::memcpy(&h, &u, 2); return (float)h; }
+  static void split_h2(float x0, float x1, float& hi, float& lo) {
+    uint16_t h0 = h_bits(x0), h1 = h_bits(x1);
+    uint16_t l0 = h_bits(x0 - h_val(h0)), l1 = h_bits(x1 - h_val(h1));
+    uint32_t ph = (uint32_t)h0 | ((uint32_t)h1 << 16), pl = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    std::memcpy(&hi, &ph, 4); std::memcpy(&lo, &pl, 4);
   }
   // the emulation accumulates exactly (round to nearest): it checks index arithmetic and dataflow, not the
   // truncating accumulator of the hardware, so the kernel's accumulator compensation is switched off
@@ -88,12 +90,16 @@ struct EmuCtxTC : EmuCtx {
   static void prefetch_l2(const float*) {}
   static void report(const long long*) {}
   void mma(int d_col, int n, int a_col, const float* b_img, int n_img, int row0, int ksteps, bool accumulate) const {
-    const int K = ksteps * 8;
+    const int K = ksteps * 16;
+    const uint16_t* bh = reinterpret_cast<const uint16_t*>(b_img);
     for (int m = 0; m < 128; ++m) {
-      const float* a = &tb->tmem[m * 512 + a_col];
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(&tb->tmem[m * 512 + a_col]);
       for (int j = 0; j < n; ++j) {
         double s = accumulate ? (double)tb->tmem[m * 512 + d_col + j] : 0.0;
-        for (int k = 0; k < K; ++k) s += (double)tf32_trunc(a[k]) * (double)tf32_trunc(b_img[(k / 4) * (n_img * 4) + (row0 + j) * 4 + (k & 3)]);
+        for (int k = 0; k < K; ++k) {
+          const uint16_t ab = (uint16_t)((a[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+          s += (double)h_val(ab) * (double)h_val(bh[(k / 8) * (n_img * 8) + (row0 + j) * 8 + (k & 7)]);
+        }
         tb->tmem[m * 512 + d_col + j] = (float)s;
       }
     }
@@ -134,6 +140,7 @@ int fc_emu_mpc_loss(const float* X, const float* u0, const float* Z, const float
   p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
   p.grad_scale = 1.0f / ((float)N * (float)B_global);
   p.acc_comp = 1.0f;
+  { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
   p.num_tiles = (B + fc::kTile - 1) / fc::kTile;
   if (grid > p.num_tiles) grid = p.num_tiles;
   fc::WorkLayout wl = fc::work_layout(N, with_grad);
@@ -172,14 +179,15 @@ void fc_emu_pack_weights_tc(const float* w_ih0, const float* w_hh0, const float*
   fc::RawWeights w;
   w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
   w.fc_w = fc_w; w.fc_b = fc_b; w.inp_w = inp_w; w.inp_b = inp_b; w.out_w = out_w;
-  for (int i = 0; i < fc::tc::kPackFloatsTC; ++i) {
-    float v = fc::tc::tc_packed_value(w, i);
-    if (i < fc::tc::kSmallOff) {
-      float hi = EmuCtxTC::tf32(v);
-      v = fc::tc::tc_is_lo(i) ? EmuCtxTC::tf32(v - hi) : hi;
-    }
-    out[i] = v;
+  uint16_t* oh = reinterpret_cast<uint16_t*>(out);
+  const long n_halves = 2L * fc::tc::kSmallOff;
+  for (long i = 0; i < n_halves; ++i) {
+    const fc::tc::TcSlot s = fc::tc::tc_decode_half(i);
+    const float v = (s.kind == 0 ? fc::tc::fwd_weight(w, s.l, s.h) : fc::tc::bwd_weight(w, s.l, s.h)) * fc::tc::kScaleW;
+    const uint16_t hi = EmuCtxTC::h_bits(v);
+    oh[i] = s.lo ? EmuCtxTC::h_bits(v - EmuCtxTC::h_val(hi)) : hi;
   }
+  for (int j = 0; j < fc::kSmallFloats; ++j) out[fc::tc::kSmallOff + j] = fc::packed_value(w, fc::kFCW + j);
 }
 
 int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
@@ -192,6 +200,7 @@ int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const fl
   p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
   p.grad_scale = 1.0f / ((float)N * (float)B_global);
   p.acc_comp = 1.0f;
+  { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
   p.num_tiles = (B + fc::tc::kTileTC - 1) / fc::tc::kTileTC;
   if (grid > p.num_tiles) grid = p.num_tiles;
   fc::tc::WorkLayoutTC wl = fc::tc::work_layout_tc(N, with_grad);
