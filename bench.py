@@ -13,8 +13,8 @@
 `e2e`      : the same metric through the public drop-in API (pinned host tensors -> H2D -> controller
              -> MPCLoss -> backward -> loss.item()), copies inside the timed region.
 `roofline` : achieved = F_alg * trajectory-steps / kernel time with F_alg = 2 041 600 FLOP per
-             trajectory-step.  Default kernel (tcgen05 3xTF32): bound "tensor", peak =
-             measured bf16 GEMM peak / 2 (tf32 rate); the FP32-FFMA-equivalent fraction (peak measured in
+             trajectory-step.  Default kernel (tcgen05, fp16 hi/lo operands): bound "tensor", peak =
+             measured dense bf16 GEMM peak (kind::f16 rate); the FP32-FFMA-equivalent fraction (peak measured in
              the same run by a register-resident FFMA loop, fc_fp32_peak) and HBM figures beside it.
              FC_MPC_KERNEL=ffma selects the FP32 FFMA kernel (bound "fp32").
 `cpu_baseline` / `--impl reference`: the oracle's torch restatement of the reference path
@@ -277,25 +277,25 @@ def run_ours(args):
         achieved = F_ALG * B * N / (kern_ms * 1e-3) / 1e12
         kernel = os.environ.get("FC_MPC_KERNEL", "auto")
         use_tc = kernel in ("tc", "auto")
-        # tf32 runs at half the bf16 rate; MEASURED_PEAKS.json holds the bf16 figure of this pool (sustained: the
-        # kernel runs for 100+ ms under the power cap), fallback 1.4 PFLOP/s (B200_PROFILING.md)
-        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        tf32_peak = bf16_peak / 2.0
+        # kind::f16 runs at the bf16 rate; MEASURED_PEAKS.json holds the dense bf16 figure of this pool (sustained:
+        # the kernel runs for 70+ ms under the power cap), fallback 1.4 PFLOP/s (B200_PROFILING.md)
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         fp32 = {"achieved": achieved, "peak": fp32_peak / 1e12, "frac": achieved / (fp32_peak / 1e12), "unit": "TFLOP/s",
                 "peak_source": "fc_fp32_peak register-resident FFMA loop measured in this run (nominal 74.45)"}
         if use_tc:
-            roof = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate)"
-                                    if peaks else "fallback 1.4 PFLOP/s bf16 / 2"),
-                    "note": "gate contraction on tcgen05 as 3xTF32 (three tf32 MMAs per fp32-accurate product): the tensor pipe executes "
-                            "~3.2x the algorithmic FLOPs (split terms + padding), the cell update (MUFU) is serialised with it by the TMEM budget; "
-                            "ncu tensor-pipe-active and the FP32-FFMA-equivalent fraction are in profiles/",
+            roof = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kind::f16 runs at the bf16 rate)"
+                                    if peaks else "fallback 1.4 PFLOP/s dense bf16"),
+                    "note": "gate contraction on tcgen05 with fp16 hi/lo split operands (three kind::f16 MMAs per fp32-accurate "
+                            "product): the tensor pipe executes ~3.3x the algorithmic FLOPs (split terms + padding) and the "
+                            "cell update (MUFU-bound) alternates with it; ncu tensor-pipe-active and the FP32-FFMA-equivalent "
+                            "fraction are in profiles/",
                     "fp32_equivalent": fp32}
         else:
             roof = dict(fp32, bound="fp32")
         # DRAM traffic per launch: ncu --set full capture of the same kernel at B=71040, N=10 (profiles/), scaled
         # linearly in B (the traffic is the per-trajectory activation records, written once and read once)
-        traffic_per_traj = (24.54e9 if use_tc else 25.67e9) / 71040.0
+        traffic_per_traj = (27.86e9 if use_tc else 25.67e9) / 71040.0
         roof.update({"flop_per_trajectory_step": F_ALG, "kernel_ms": kern_ms,
                      "traffic": traffic_per_traj * B if N == 10 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu capture at B=71040 scaled by B (profiles/r01_*)",
@@ -308,7 +308,7 @@ def run_ours(args):
             "config": {"workload": f"fused MPC-loss fwd+bwd, N={N}, {B} synthetic trajectories per GPU "
                                    f"(BASELINE config 5: 4194304 / 8), U(-1,1) inputs, shipped surrogate + controller weights",
                        "horizon": N, "alpha": ALPHA, "batch_per_gpu": B, "global_batch": B_global,
-                       "kernel": "tcgen05 3xTF32 (fc::mpc_loss_tc_kernel)" if use_tc else "FP32 FFMA (fc::mpc_loss_kernel)",
+                       "kernel": "tcgen05 fp16 hi/lo split (fc::mpc_loss_tc_kernel)" if use_tc else "FP32 FFMA (fc::mpc_loss_kernel)",
                        "parallelism": f"dp{world}", "l2": "inputs (105 MB Z + GBs of activation records) exceed the 126 MB L2"},
             "loss": loss_val,
             "e2e": {"value": B_global * N / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",

@@ -125,8 +125,8 @@ struct DevCtxTC : DevCtx {
   static __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
   static __device__ __forceinline__ long long clock() { return clock64(); }
   static __device__ void report(const long long* tm) {
-    printf("[fc timing, CTA 0 thread 0, cycles] glue+bwd-post+other %lld | fwd: issue+input %lld mma-wait %lld pointwise %lld store+sync %lld | bwd: finish+sync %lld issue+shadow %lld mma-wait %lld\n",
-           tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7]);
+    printf("[fc timing, CTA 0 thread 0, cycles] other %lld | fwd: prologue %lld issue+input %lld mma-wait %lld pointwise %lld store+sync %lld glue %lld | bwd: glue %lld prologue %lld finish+sync %lld issue+shadow %lld mma-wait %lld post %lld\n",
+           tm[0], tm[9], tm[1], tm[2], tm[3], tm[4], tm[10], tm[11], tm[12], tm[5], tm[6], tm[7], tm[8]);
   }
   static constexpr bool kAccTruncates = true;   // tcgen05 accumulates with truncation, see tc::acc_correction
   uint32_t tbase;        // TMEM base address of this CTA's 512-column allocation

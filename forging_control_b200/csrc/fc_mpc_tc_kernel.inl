@@ -29,7 +29,7 @@ struct MpcTileTC {
   float hrec[kMaxOwn];   // backward: d(h) from step t+1
   unsigned ph[8];        // completed phases per mbarrier
 #ifdef FC_TC_TIMING
-  long long tm[8], tlast;  // cycle breakdown of thread 0 (development aid, -DFC_TC_TIMING)
+  long long tm[16], tlast;  // cycle breakdown of thread 0 (development aid, -DFC_TC_TIMING)
 #endif
 
   FC_HD_CTX MpcTileTC(Ctx& c_, const MpcParams& p_) : ctx(c_), p(p_) {
@@ -52,7 +52,7 @@ struct MpcTileTC {
 #pragma unroll
     for (int i = 0; i < 8; ++i) ph[i] = 0;
 #ifdef FC_TC_TIMING
-    for (int i = 0; i < 8; ++i) tm[i] = 0;
+    for (int i = 0; i < 16; ++i) tm[i] = 0;
     tlast = 0;
 #endif
   }
@@ -62,18 +62,43 @@ struct MpcTileTC {
   FC_HD_CTX void lap(int) {}
 #endif
 
-  FC_HD_CTX static float sigmoidf_(float x) { return Ctx::rcp(1.f + Ctx::ex2(-1.4426950408889634f * x)); }
-  // tanh: 1 - 2/(1+e^{2x}) has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is a large
-  // relative error for the small gate / cell values that dominate here; below |x| = 0.3 use the odd
+  // Activations.  MUFU (ex2 / rcp, 16 lanes per clock and SM) bounds the cell update, so reciprocals are shared:
+  // 1/a, 1/b, 1/c, 1/d come from ONE rcp of the product (9 extra multiplies on the FMA pipe instead of 3 MUFU
+  // operations).  Every denominator is 1 + 2^e with e clamped to kExpMax, so the product stays below 2^121.
+  static constexpr float kExpMax = 30.0f;
+  static constexpr float kLog2e = 1.4426950216293335f;            // fp32(log2 e)
+  static constexpr float kLog2eLo = 1.92596e-8f;                  // log2 e - fp32(log2 e)
+  FC_HD_CTX static float denom_(float e2arg) { return 1.f + Ctx::ex2(fminf(e2arg, kExpMax)); }
+  FC_HD_CTX static void quad_rcp(float a, float b, float c, float d, float& ra, float& rb, float& rc, float& rd) {
+    const float ab = a * b, cd = c * d;
+    const float r = Ctx::rcp(ab * cd);
+    const float rab = r * cd, rcd = r * ab;
+    ra = rab * b; rb = rab * a; rc = rcd * d; rd = rcd * c;
+  }
+  // tanh(x) from rd = 1/(1 + e^{2x}): 1 - 2 rd has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is
+  // a large relative error for the small gate / cell values that dominate here; below |x| = 0.3 use the odd
   // Taylor polynomial (relative error < 6e-8) instead.  Branch-free select.
-  FC_HD_CTX static float tanhf_(float x) {
-    const float big = 1.f - 2.f * Ctx::rcp(1.f + Ctx::ex2(2.8853900817779268f * x));
+  FC_HD_CTX static float tanh_from_(float x, float rd) {
+    const float big = fmaf(-2.f, rd, 1.f);
     const float x2 = x * x;
     float pl = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);
     pl = fmaf(x2, pl, 0.13333333333333333f);
     pl = fmaf(x2, pl, -0.33333333333333331f);
     pl = fmaf(x2 * x, pl, x);
     return fabsf(x) < 0.3f ? pl : big;
+  }
+  // tanh of NU values with one reciprocal per four
+  template <int NU>
+  FC_HD_CTX static void tanh_batch(const float* x, float* y) {
+    float d[NU], r[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) d[i] = denom_(2.f * kLog2e * x[i]);
+#pragma unroll
+    for (int i = 0; i + 3 < NU; i += 4) quad_rcp(d[i], d[i + 1], d[i + 2], d[i + 3], r[i], r[i + 1], r[i + 2], r[i + 3]);
+#pragma unroll
+    for (int i = NU & ~3; i < NU; ++i) r[i] = Ctx::rcp(d[i]);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) y[i] = tanh_from_(x[i], r[i]);
   }
 
   FC_HD_CTX void wait_bar(int b) { ctx.bar_wait(b, ph[b]); ph[b] += 1; }
@@ -147,21 +172,40 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   // forward: cell update of NU unit slots starting at slot j0 from 4*NU accumulator columns
   // ---------------------------------------------------------------------------------------------
+  // g holds RAW accumulator values (pre-activation * kScaleA * kScaleW, before the truncation compensation);
+  // ak folds unscale, compensation and -log2(e) into the exponent argument of the three sigmoid gates
+  struct ActK { float khi, klo, us, corr; };
+  FC_HD_CTX static ActK make_actk(float unscale, float corr) {
+    ActK k;
+    k.khi = -kLog2e * unscale;                              // exact: unscale is a power of two
+    k.klo = fmaf(k.khi, corr, -kLog2eLo * unscale);
+    k.us = unscale; k.corr = corr;
+    return k;
+  }
   template <int NU>
-  FC_HD_CTX void fwd_units(int j0, const float* g, bool first, float* h, float* rp, int r0) {
+  FC_HD_CTX void fwd_units(int j0, const float* g, const ActK& ak, bool first, float* h, float* rp, int r0) {
     float rv[NU * 5 + 3];
+    float cn[NU], th[NU];
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-      float gi = sigmoidf_(g[i * 4 + 0]);
-      float gf = sigmoidf_(g[i * 4 + 1]);
-      float gg = tanhf_(g[i * 4 + 2]);
-      float go = sigmoidf_(g[i * 4 + 3]);
-      float cp = first ? 0.f : c[j0 + i];
-      float cn = fmaf(gf, cp, gi * gg);
-      c[j0 + i] = cn;
-      h[j0 + i] = go * tanhf_(cn);
+      const float xi = g[i * 4 + 0], xf = g[i * 4 + 1], xo = g[i * 4 + 3];
+      float xg = g[i * 4 + 2] * ak.us;
+      xg = fmaf(xg, ak.corr, xg);
+      const float di = denom_(fmaf(xi, ak.khi, xi * ak.klo));
+      const float df = denom_(fmaf(xf, ak.khi, xf * ak.klo));
+      const float dq = denom_(fmaf(xo, ak.khi, xo * ak.klo));
+      const float dg = denom_(2.f * kLog2e * xg);
+      float gi, gf, go, rg;
+      quad_rcp(di, df, dq, dg, gi, gf, go, rg);
+      const float gg = tanh_from_(xg, rg);
+      const float cp = first ? 0.f : c[j0 + i];
+      cn[i] = fmaf(gf, cp, gi * gg);
+      c[j0 + i] = cn[i];
       rv[i * 5 + 0] = gi; rv[i * 5 + 1] = gf; rv[i * 5 + 2] = gg; rv[i * 5 + 3] = go; rv[i * 5 + 4] = cp;
     }
+    tanh_batch<NU>(cn, th);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) h[j0 + i] = rv[i * 5 + 3] * th[i];
     if (rp) {
 #pragma unroll
       for (int i = NU * 5; i < NU * 5 + 3; ++i) rv[i] = 0.f;
@@ -175,7 +219,7 @@ struct MpcTileTC {
 
   // all unit slots of one step (the accumulator barrier has been waited for by the caller)
   FC_HD_CTX void fwd_pointwise(bool first, float corr, float* h, float* rec_out) {
-    const float unscale = 1.0f / (kScaleA * kScaleW);      // exact power of two
+    const ActK ak = make_actk(1.0f / (kScaleA * kScaleW), corr);
     float* rp = rec_out ? rec_out + ((size_t)warp * kRecF4 * 32 + lane) * 4 : nullptr;
     const int col0 = kColD + 4 * u_first;
     float g[2][16];
@@ -186,16 +230,10 @@ struct MpcTileTC {
       // software pipeline: request the next accumulator columns before working on these
       if (gi + 1 < 3) ctx.template tmem_ld_nowait<16>(col0 + (gi + 1) * 16, g[(gi + 1) & 1]);
       else ctx.template tmem_ld_nowait<4>(col0 + 48, g[(gi + 1) & 1]);
-      float* gg = g[gi & 1];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { gg[i] *= unscale; gg[i] = fmaf(gg[i], corr, gg[i]); }
-      fwd_units<4>(gi * 4, gg, first, h, rp, gi * 5);
+      fwd_units<4>(gi * 4, g[gi & 1], ak, first, h, rp, gi * 5);
     }
     ctx.tmem_ld_wait();
-    float* gg = g[1];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { gg[i] *= unscale; gg[i] = fmaf(gg[i], corr, gg[i]); }
-    fwd_units<1>(12, gg, first, h, rp, 15);                // slot 12: a masked dummy for quarters 2,3
+    fwd_units<1>(12, g[1], ak, first, h, rp, 15);                // slot 12: a masked dummy for quarters 2,3
   }
 
   // input of (layer l, step t) for the owned columns: layer 0 -> 5 row features (quarter 0 only)
@@ -248,6 +286,7 @@ struct MpcTileTC {
       ctx.tmem_st_wait();
       wait_bar(kBarWeights);                               // operand image of this layer landed
       ctx.tc_sync();
+      lap(9);
       for (int t = 0; t < kLook; ++t) {
         // at t = 0 the recurrent columns are zero: only the k-steps that cover the input columns
         lap(0);
@@ -299,8 +338,10 @@ struct MpcTileTC {
         lap(4);
       }
     }
+    lap(0);
     if (quarter == 0) fwd_glue(tile, m);
     ctx.sync();
+    lap(10);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -361,11 +402,15 @@ struct MpcTileTC {
       F4 v = Ctx::ldg4_stream(rp + (size_t)(r0 + r) * 32 * 4);
       rv[r * 4] = v.x; rv[r * 4 + 1] = v.y; rv[r * 4 + 2] = v.z; rv[r * 4 + 3] = v.w;
     }
+    float cn[NU], th[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) cn[i] = fmaf(rv[i * 5 + 1], rv[i * 5 + 4], rv[i * 5 + 0] * rv[i * 5 + 2]);
+    tanh_batch<NU>(cn, th);
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
       const int j = j0 + i;
       float gi = rv[i * 5 + 0], gf = rv[i * 5 + 1], gg = rv[i * 5 + 2], go = rv[i * 5 + 3], cp = rv[i * 5 + 4];
-      float tch = tanhf_(fmaf(gf, cp, gi * gg));
+      float tch = th[i];
       fa.A[j] = go * (1.f - tch * tch);
       fa.Ko[j] = tch * go * (1.f - go);
       fa.Ki[j] = gg * gi * (1.f - gi);
@@ -527,8 +572,10 @@ struct MpcTileTC {
     const int tmin = t_min_of(m);
     const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
     const float unscale_b = p.g_unscale / kScaleW;         // exact power of two
+    lap(0);
     bwd_glue(tile, m);
     ctx.sync();
+    lap(11);
     for (int l = kLayers - 1; l >= 0; --l) {
       const int nb = nb_of(l);
 #pragma unroll
@@ -544,6 +591,7 @@ struct MpcTileTC {
       bwd_factors(rec_l + (size_t)(kLook - 1 - tmin) * kRecFloatsTC, fa);
       bwd_extra(l, kLook - 1, extra);
       wait_bar(kBarWeights);
+      lap(12);
       for (int t = kLook - 1; t >= tmin; --t) {
         lap(0);
         bwd_finish(fa, extra);
@@ -602,6 +650,7 @@ struct MpcTileTC {
             for (int f = 0; f < kFeat; ++f) gp[f * kTileTC] = Ctx::ldcg(gp + f * kTileTC) + fmaf(df[f], corr_b, df[f]);
           }
         }
+        lap(8);
       }
     }
   }
