@@ -12,6 +12,7 @@
 #define FC_HD_CTX __device__ __forceinline__
 #include "fc_mpc_kernel.inl"
 #include "fc_mpc_tc_kernel.inl"
+#include "fc_mpc_pair_kernel.inl"
 #include "fc_plant.cuh"
 
 namespace fc {
@@ -128,6 +129,12 @@ struct DevCtxTC : DevCtx {
     printf("[fc timing, CTA 0 thread 0, cycles] other %lld | fwd: prologue %lld issue+input %lld mma-wait %lld pointwise %lld store+sync %lld glue %lld | bwd: glue %lld prologue %lld finish+sync %lld issue+shadow %lld mma-wait %lld post %lld\n",
            tm[0], tm[9], tm[1], tm[2], tm[3], tm[4], tm[10], tm[11], tm[12], tm[5], tm[6], tm[7], tm[8]);
   }
+  static __device__ void report_pair(int tid, const long long* tm) {
+    printf("[fc pair timing, CTA 0 thread %d, cycles] other %lld | fwd: wait-full %lld update %lld arrive %lld wait-ready %lld issue %lld | bwd: wait-full %lld update %lld arrive %lld wait-ready %lld issue %lld | swap %lld loads %lld fwd-t9 %lld prologue/tail %lld glue %lld | before: fwd-item %lld fwd-wait %lld prologue %lld fwd-sync %lld bwd-item %lld bwd-window %lld bwd-tail %lld service-item %lld\n",
+           tid, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], tm[8], tm[9], tm[10], tm[11], tm[12], tm[13], tm[14], tm[15],
+           tm[16], tm[17], tm[18], tm[19], tm[20], tm[21], tm[22], tm[23]);
+  }
+  __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
   static constexpr bool kAccTruncates = true;   // tcgen05 accumulates with truncation, see tc::acc_correction
   uint32_t tbase;        // TMEM base address of this CTA's 512-column allocation
   uint32_t lane_addr;    // tbase + first lane of this warp's quadrant
@@ -221,10 +228,46 @@ struct DevCtxTC : DevCtx {
     const uint32_t addr = bar0 + bar * 8, parity = phase & 1u;
     uint32_t done = 0;
     while (!done) {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                   : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+      // the suspend-time hint lets the hardware park the warp until the phase completes instead of spinning
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // ---- pair kernel: per-tile hand-shakes and shared-memory A operands ----
+  __device__ __forceinline__ void bar_init(int bar, int count) const {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + bar * 8), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void bar_init_fence() const { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __device__ __forceinline__ void bar_arrive(int bar) const {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + bar * 8) : "memory");
+  }
+  // generic-proxy shared-memory writes -> visible to the tensor core (async proxy); TMEM accesses ordered before the arrive
+  __device__ __forceinline__ void operand_fence() const {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  static __device__ __forceinline__ void sts2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+  // D[128 x n] (+)= A[128 x 16*ksteps] * B[n x 16*ksteps]^T with BOTH operands in shared memory:
+  // A image = [k/8][128][8 halves], B image = [k/8][n_img][8 halves]
+  __device__ __forceinline__ void mma_ss(int d_col, int n, const float* a_img, const float* b_img, int n_img, int ksteps, bool accumulate) const {
+    const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t lbo_b = (uint32_t)n_img * 16u, lbo_a = 128u * 16u, sbo = 128u;
+    uint64_t bdesc = (uint64_t)((smem_u32(b_img) >> 4) & 0x3FFF) | ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+    uint64_t adesc = (uint64_t)((smem_u32(a_img) >> 4) & 0x3FFF) | ((uint64_t)((lbo_a >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+    const uint64_t bstep = (uint64_t)((2u * lbo_b) >> 4), astep = (uint64_t)((2u * lbo_a) >> 4);
+    const uint32_t d_addr = tbase + d_col;
+    if (!accumulate) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_addr),
+                   "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+      adesc += astep; bdesc += bstep; --ksteps;
+    }
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_addr),
+                   "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+      adesc += astep; bdesc += bstep;
+    }
   }
   // one thread: bulk (TMA) copy global -> shared, completion on an mbarrier
   __device__ __forceinline__ void bulk_load(float* dst, const float* src, int nfloats, int bar) const {
@@ -247,7 +290,31 @@ __global__ void __launch_bounds__(tc::kThreadsTC, 1) mpc_loss_tc_kernel(const Mp
   k.run();
 }
 
-// packed buffer = [FFMA layouts (kPackFloats) | tcgen05 operand images, fp16 hi/lo (tc::kPackFloatsTC floats)]
+__global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_pair_kernel(const MpcParams p) {
+  DevCtxTC ctx;
+  pr::MpcPair<DevCtxTC> k(ctx, p);
+  k.run();
+}
+
+// pair-kernel operand images behind the two others in the packed buffer
+__global__ void pack_weights_pair_kernel(RawWeights w, float* out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // half index
+  const long n_halves = 2L * pr::kSmallOff;
+  float* base = out + kPackFloats + tc::kPackFloatsTC;
+  __half* oh = reinterpret_cast<__half*>(base);
+  if (i < n_halves) {
+    const pr::PrSlot s = pr::decode_half(i);
+    const float v = (s.kind == 0 ? pr::fwd_weight(w, s.l, s.h) : pr::bwd_weight(w, s.l, s.h)) * pr::kScaleW;
+    const __half hi = __float2half_rn(v);
+    oh[i] = s.lo ? __float2half_rn(v - __half2float(hi)) : hi;
+  } else if (i < n_halves + kSmallFloats) {
+    const int j = (int)(i - n_halves);
+    base[pr::kSmallOff + j] = packed_value(w, kFCW + j);
+  }
+}
+
+// packed buffer = [FFMA layouts (kPackFloats) | tcgen05 operand images, fp16 hi/lo (tc::kPackFloatsTC floats) |
+//                  pair-kernel operand images (pr::kPackFloatsP floats)]
 __global__ void pack_weights_tc_kernel(RawWeights w, float* out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // half index
   const long n_halves = 2L * tc::kSmallOff;
@@ -335,7 +402,7 @@ static int sm_count(int* out) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 3xTF32 kernel
+// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel
 static int g_mpc_mode = -1;
 static int mpc_mode() {
   if (g_mpc_mode < 0) {
@@ -343,12 +410,13 @@ static int mpc_mode() {
     g_mpc_mode = 0;
     if (e && !strcmp(e, "ffma")) g_mpc_mode = 1;
     if (e && !strcmp(e, "tc")) g_mpc_mode = 2;
+    if (e && !strcmp(e, "pair")) g_mpc_mode = 3;
   }
   return g_mpc_mode;
 }
 
 struct MpcPlan {
-  bool use_tc;
+  int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair
   int grid, tiles;
   size_t work_stride;   // floats per CTA
   size_t bytes;
@@ -361,11 +429,13 @@ static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl) {
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
-  pl->use_tc = mode == 2 || mode == 0;
-  const int tile = pl->use_tc ? tc::kTileTC : kTile;
+  pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
+  const int tile = pl->kind ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
-  pl->grid = pl->tiles < sms ? pl->tiles : sms;
-  pl->work_stride = pl->use_tc ? tc::work_layout_tc(N, with_grad).total : work_layout(N, with_grad).total;
+  const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
+  pl->grid = units < sms ? units : sms;
+  pl->work_stride = pl->kind == 2 ? pr::kTiles * pr::work_layout_p(N, with_grad).total
+                                  : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad).total : work_layout(N, with_grad).total);
   pl->bytes = (size_t)pl->grid * kPartialStride * sizeof(double) + (size_t)pl->grid * pl->work_stride * sizeof(float);
   return FC_OK;
 }
@@ -393,7 +463,7 @@ extern "C" {
 
 const char* fc_last_error(void) { return g_err; }
 int fc_version(void) { return 100; }
-size_t fc_pack_floats(void) { return (size_t)kPackFloats + (size_t)tc::kPackFloatsTC; }
+size_t fc_pack_floats(void) { return (size_t)kPackFloats + (size_t)tc::kPackFloatsTC + (size_t)pr::kPackFloatsP; }
 
 int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
                     const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
@@ -410,11 +480,14 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
   FC_CUDA(cudaGetLastError(), "pack_weights_kernel launch");
   pack_weights_tc_kernel<<<(2 * tc::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, wpack);
   FC_CUDA(cudaGetLastError(), "pack_weights_tc_kernel launch");
+  pack_weights_pair_kernel<<<(2 * pr::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, wpack);
+  FC_CUDA(cudaGetLastError(), "pack_weights_pair_kernel launch");
   return FC_OK;
 }
 
 int fc_mpc_select_kernel(int mode) {
-  if (mode < 0 || mode > 2) return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma) or 2 (tcgen05)");
+  if (mode < 0 || mode > 3)
+    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05) or 3 (tcgen05 pair)");
   g_mpc_mode = mode;
   return FC_OK;
 }
@@ -447,12 +520,14 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
             "cudaFuncSetAttribute(smem)");
     FC_CUDA(cudaFuncSetAttribute(mpc_loss_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmBytesTC),
             "cudaFuncSetAttribute(smem, tc)");
+    FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
+            "cudaFuncSetAttribute(smem, pair)");
     attr_set = true;
   }
   MpcParams p;
   memset(&p, 0, sizeof(p));
   p.X = X; p.u0 = u0; p.Z = Z;
-  p.wpack = pl.use_tc ? wpack + kPackFloats : wpack;
+  p.wpack = pl.kind == 2 ? wpack + kPackFloats + tc::kPackFloatsTC : (pl.kind == 1 ? wpack + kPackFloats : wpack);
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.partial = reinterpret_cast<double*>(workspace);
   p.work = reinterpret_cast<float*>(p.partial + (size_t)pl.grid * kPartialStride);
@@ -471,7 +546,8 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
   if (const char* e = getenv("FC_TC_ACC_COMP")) p.acc_comp = (float)atof(e);   // calibration experiments only
   p.debug_timing = getenv("FC_TC_TIMING") ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl.use_tc) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, tc::kSmBytesTC, st>>>(p);
+  if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+  else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, tc::kSmBytesTC, st>>>(p);
   else mpc_loss_kernel<<<pl.grid, kThreads, kSmBytes, st>>>(p);
   FC_CUDA(cudaGetLastError(), "mpc_loss kernel launch");
   mpc_finalize_kernel<<<1, 1024, 0, st>>>(p.partial, pl.grid, 1.0 / (double)B_global, gl);

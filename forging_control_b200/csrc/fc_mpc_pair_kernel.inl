@@ -1,0 +1,964 @@
+// Two-tile ("pair") tcgen05 variant of the fused MPC-loss forward + reverse sweep.  Same mathematics and reference
+// citations as fc_mpc_kernel.inl (MPCLoss.forward Functions.py:1353-1472, LSTMModel.forward :353-379,
+// FNNModel.forward :261-289, loss.backward() :655) and the same fp16 hi/lo split tensor-core contraction as
+// fc_mpc_tc_kernel.inl.  What changes is the schedule: a CTA owns TWO 128-trajectory tiles and alternates between
+// them, LSTM cell step by cell step.  The gate contraction of one tile (tcgen05.mma, asynchronous) runs while all
+// 16 warps do the cell update (MUFU / FMA pipes) of the other tile, instead of the two phases taking turns:
+//
+//   thread 0 :  ... issue MMA(tile 0, step t+1) | cell update tile 1, step t | issue MMA(tile 1, t+1) | ...
+//   tensor   :  ...        MMA(tile 0, t+1) running ............ | MMA(tile 1, t+1) running ...........
+//   16 warps :  ... cell update (tile 1, t) .................... | cell update (tile 0, t+1) ..........
+//
+// Hand-shakes are per tile and by mbarrier, never CTA-wide: full[tile] (tcgen05.commit: accumulator complete, operand
+// free) and ready[tile] (512 arrivals: accumulator consumed, next operand written).  See fc_pair_layout.h for where
+// the operands live (TMEM / shared memory budget) and DESIGN.md section 2.3.
+// Warps 0..3 are service warps (thread 0 = the MMA issuer; per-trajectory scalar work of both tiles), warps 4..15 do
+// the cell updates: third th = w/4 - 1 owns the hidden units [16 th, 16 th + 16) (18 for th = 2).
+#pragma once
+#include "fc_pair_layout.h"
+
+namespace fc {
+namespace pr {
+
+template <class Ctx>
+struct MpcPair {
+  Ctx& ctx;
+  const MpcParams& p;
+  float* sm;
+  int tid, warp, lane, row, th, nown, u_first, uw;
+  bool service;          // warps 0..3
+  bool last;             // third 2: 18 units (else 16)
+  float* wbase;          // workspace of tile 0 of this CTA; tile 1 follows at +tstride
+  size_t tstride;
+  int ntl;               // live tiles in this pass (1 or 2)
+  int tile0;             // global index of tile 0 of this pass
+  // forward: cell state, backward: d(cell state) of the tile of the CURRENT item; the state of the other tile is
+  // parked in spare TMEM columns of the own lane and exchanged at the start of every item (items alternate strictly)
+  float c[kMaxOwn];
+  unsigned phF0, phF1, phR0, phR1, phW;
+#ifdef FC_TC_TIMING
+  long long tm[24], tlast;  // cycle breakdown (development aid, -DFC_TC_TIMING): threads 0 and 160 of CTA 0 report
+  FC_HD_CTX void lap(int k) { long long t = Ctx::clock(); tm[k] += t - tlast; tlast = t; }
+#else
+  FC_HD_CTX void lap(int) {}
+#endif
+
+  FC_HD_CTX MpcPair(Ctx& c_, const MpcParams& p_) : ctx(c_), p(p_) {
+    sm = ctx.smem();
+    tid = ctx.tid();
+    warp = tid >> 5;
+    lane = tid & 31;
+    row = 32 * (warp & 3) + lane;
+    service = warp < 4;
+    th = service ? 0 : (warp >> 2) - 1;
+    nown = units_of(th);
+    u_first = first_unit(th);
+    last = th == 2;
+    uw = service ? 0 : warp - 4;                             // index among the cell-update warps
+    tstride = work_layout_p(p.N, p.with_grad).total;
+    wbase = p.work + (size_t)ctx.bid() * p.work_stride;
+    phF0 = phF1 = phR0 = phR1 = phW = 0;
+    ntl = 0; tile0 = 0;
+#ifdef FC_TC_TIMING
+    for (int i = 0; i < 24; ++i) tm[i] = 0;
+    tlast = 0;
+#endif
+  }
+
+  // workspace pointers of tile X
+  FC_HD_CTX float* w_rows(int X) const { return wbase + X * tstride; }
+  FC_HD_CTX float* w_cost(int X) const { return w_rows(X) + (size_t)(p.N + kLook) * kFeat * kTileP; }
+  FC_HD_CTX float* w_seq(int X) const { return w_cost(X) + 3 * kTileP; }
+  FC_HD_CTX float* w_dseq(int X) const { return w_seq(X) + (size_t)kLook * kSlot; }
+  FC_HD_CTX float* w_grow(int X) const { return w_dseq(X) + (size_t)kLook * kSlot; }
+  FC_HD_CTX float* w_rec(int X) const { return w_rows(X) + work_layout_p(p.N, p.with_grad).rec; }
+
+  // ---------------------------------------------------------------------------------------------
+  // activations (see fc_mpc_tc_kernel.inl): one reciprocal per four denominators, polynomial tanh near 0
+  // ---------------------------------------------------------------------------------------------
+  static constexpr float kExpMax = 30.0f;
+  static constexpr float kLog2e = 1.4426950216293335f;            // fp32(log2 e)
+  static constexpr float kLog2eLo = 1.92596e-8f;                  // log2 e - fp32(log2 e)
+  FC_HD_CTX static float denom_(float e2arg) { return 1.f + Ctx::ex2(fminf(e2arg, kExpMax)); }
+  FC_HD_CTX static void quad_rcp(float a, float b, float c, float d, float& ra, float& rb, float& rc, float& rd) {
+    const float ab = a * b, cd = c * d;
+    const float r = Ctx::rcp(ab * cd);
+    const float rab = r * cd, rcd = r * ab;
+    ra = rab * b; rb = rab * a; rc = rcd * d; rd = rcd * c;
+  }
+  FC_HD_CTX static float tanh_from_(float x, float rd) {
+    const float big = fmaf(-2.f, rd, 1.f);
+    const float x2 = x * x;
+    float pl = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);
+    pl = fmaf(x2, pl, 0.13333333333333333f);
+    pl = fmaf(x2, pl, -0.33333333333333331f);
+    pl = fmaf(x2 * x, pl, x);
+    return fabsf(x) < 0.3f ? pl : big;
+  }
+  template <int NU>
+  FC_HD_CTX static void tanh_batch(const float* x, float* y) {
+    float d[NU], r[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) d[i] = denom_(2.f * kLog2e * x[i]);
+#pragma unroll
+    for (int i = 0; i + 3 < NU; i += 4) quad_rcp(d[i], d[i + 1], d[i + 2], d[i + 3], r[i], r[i + 1], r[i + 2], r[i + 3]);
+    if ((NU & 3) == 2) {
+      const float r2 = Ctx::rcp(d[NU - 2] * d[NU - 1]);
+      r[NU - 2] = r2 * d[NU - 1]; r[NU - 1] = r2 * d[NU - 2];
+    } else {
+#pragma unroll
+      for (int i = NU & ~3; i < NU; ++i) r[i] = Ctx::rcp(d[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) y[i] = tanh_from_(x[i], r[i]);
+  }
+  struct ActK { float khi, klo, us, corr; };
+  FC_HD_CTX static ActK make_actk(float unscale, float corr) {
+    ActK k;
+    k.khi = -kLog2e * unscale;                              // exact: unscale is a power of two
+    k.klo = fmaf(k.khi, corr, -kLog2eLo * unscale);
+    k.us = unscale; k.corr = corr;
+    return k;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // hand-shakes
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void wait_full(int X) {
+    ctx.bar_wait(kBarFull + X, X ? phF1 : phF0);
+    if (X) phF1 += 1; else phF0 += 1;
+  }
+  FC_HD_CTX void swap_cells() {                            // cell-update warps only
+    if (ntl > 1) {
+      float o[kMaxOwn];
+      const int col = kColPark + kMaxOwn * th;
+      ctx.template tmem_ld_nowait<16>(col, o);
+      ctx.template tmem_ld_nowait<2>(col + 16, o + 16);
+      ctx.tmem_ld_wait();
+      ctx.template tmem_st<16>(col, c);
+      ctx.template tmem_st<2>(col + 16, c + 16);
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) c[j] = o[j];
+      ctx.tmem_st_wait();
+    }
+  }
+  // all operand writes / accumulator reads of this thread for tile X are done
+  FC_HD_CTX void arrive_ready(int X) {
+    ctx.operand_fence();
+    ctx.warp_sync();
+    if (lane == 0) ctx.bar_arrive(kBarReady + X);            // one arrival per warp
+  }
+  FC_HD_CTX void wait_ready(int X) {                                                             // tid 0 only
+    ctx.bar_wait(kBarReady + X, X ? phR1 : phR0);
+    if (X) phR1 += 1; else phR0 += 1;
+  }
+  FC_HD_CTX void wait_weights() { ctx.bar_wait(kBarWeightsP, phW); phW += 1; }                    // tid 0 only
+  FC_HD_CTX void request_weights(bool bwd, int l) {                                              // tid 0 only
+    const int n = bwd ? bwd_img_halves(l) : fwd_img_halves(l);   // hi + lo images of halves = that many floats
+    ctx.bulk_load(sm + kSmWP, p.wpack + (bwd ? wb_off(l) : wf_off(l)), n, kBarWeightsP);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // shared-memory operand images: K-major, no swizzle: half (row r, k) at (k/8)*1024 + r*8 + k%8
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX float* op_ptr(int halves_off, int k) const {       // k multiple of 2
+    return sm + kSmOpP + ((halves_off + (k >> 3) * (kTileP * 8) + row * 8 + (k & 7)) >> 1);
+  }
+  // the owned units' values v[0..nown) (scaled here) as fp16 hi/lo pieces of 8 halves (third 2: the third piece
+  // holds units 48,49 and the zero padding up to slot 56)
+  FC_HD_CTX void split_units(const float* v, float scale, F4* hi4, F4* lo4) const {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = ch * 8 + 2 * i;
+        const float x0 = j < kMaxOwn ? fminf(fmaxf(v[j < kMaxOwn ? j : 0] * scale, -kHalfMax), kHalfMax) : 0.f;
+        const float x1 = j + 1 < kMaxOwn ? fminf(fmaxf(v[j + 1 < kMaxOwn ? j + 1 : 0] * scale, -kHalfMax), kHalfMax) : 0.f;
+        Ctx::split_h2(x0, x1, hi[i], lo[i]);
+      }
+      hi4[ch] = F4{hi[0], hi[1], hi[2], hi[3]};
+      lo4[ch] = F4{lo[0], lo[1], lo[2], lo[3]};
+    }
+  }
+  // pieces -> halves [kbase + u_first, ...) of the hi and lo operand images (kbase multiple of 8)
+  FC_HD_CTX void st_pieces(int img_hi, int img_lo, int kbase, const F4* hi4, const F4* lo4) {
+    const int k0 = kbase + u_first;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      if (ch < 2 || last) { Ctx::sts4(op_ptr(img_hi, k0 + ch * 8), hi4[ch]); Ctx::sts4(op_ptr(img_lo, k0 + ch * 8), lo4[ch]); }
+  }
+  // pieces <-> the hidden-sequence scratch of the layer below: [t][warp][piece*2 + hi/lo][lane] float4, thread-private
+  FC_HD_CTX float* seq_ptr(int X, int t) const { return w_seq(X) + (size_t)t * kSlot + ((size_t)uw * 6 * 32 + lane) * 4; }
+  FC_HD_CTX void stg_pieces(int X, int t, const F4* hi4, const F4* lo4) {
+    float* sq = seq_ptr(X, t);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      if (ch < 2 || last) { Ctx::stg4(sq + (ch * 2) * 128, hi4[ch]); Ctx::stg4(sq + (ch * 2 + 1) * 128, lo4[ch]); }
+  }
+  // asynchronous copy scratch -> input block of the operand images (cp.async, no registers); cp_wait before the arrive
+  FC_HD_CTX void copy_input(int X, int t) {
+    const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
+    const float* sq = seq_ptr(X, t);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      if (ch < 2 || last) {
+        Ctx::cp_async16(op_ptr(img_hi, u_first + ch * 8), sq + (ch * 2) * 128);
+        Ctx::cp_async16(op_ptr(img_lo, u_first + ch * 8), sq + (ch * 2 + 1) * 128);
+      }
+    Ctx::cp_commit();
+  }
+  FC_HD_CTX void st_units_zero(int img_hi, int img_lo, int kbase) {
+    const int k0 = kbase + u_first;
+    const F4 z = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      if (ch < 2 || last) { Ctx::sts4(op_ptr(img_hi, k0 + ch * 8), z); Ctx::sts4(op_ptr(img_lo, k0 + ch * 8), z); }
+  }
+
+  // hi/lo fp16 split of 2*NP pre-scaled values into NP consecutive TMEM operand columns of the own lane
+  template <int NP>
+  FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v, float scale) {
+    float hi[NP], lo[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float x0 = fminf(fmaxf(v[2 * i] * scale, -kHalfMax), kHalfMax);
+      const float x1 = fminf(fmaxf(v[2 * i + 1] * scale, -kHalfMax), kHalfMax);
+      Ctx::split_h2(x0, x1, hi[i], lo[i]);
+    }
+    ctx.template tmem_st<NP>(col_hi, hi);
+    ctx.template tmem_st<NP>(col_lo, lo);
+  }
+  // the same into 2*NP halves of the shared-memory dG image (tile 1), k0 multiple of 8, NP multiple of 4
+  template <int NP>
+  FC_HD_CTX void st_pairs_smem(int k0, const float* v, float scale) {
+#pragma unroll
+    for (int ch = 0; ch < NP / 4; ++ch) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x0 = fminf(fmaxf(v[ch * 8 + 2 * i] * scale, -kHalfMax), kHalfMax);
+        const float x1 = fminf(fmaxf(v[ch * 8 + 2 * i + 1] * scale, -kHalfMax), kHalfMax);
+        Ctx::split_h2(x0, x1, hi[i], lo[i]);
+      }
+      Ctx::sts4(op_ptr(0, k0 + ch * 8), F4{hi[0], hi[1], hi[2], hi[3]});
+      Ctx::sts4(op_ptr(kOpGLoHalves, k0 + ch * 8), F4{lo[0], lo[1], lo[2], lo[3]});
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // MMA issue (tid 0 only): 3 error-compensated terms, small ones first
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void issue_fwd(int X, int l, int ksteps) {
+    const float* b_hi = sm + kSmWP;
+    const float* b_lo = b_hi + fwd_img_halves(l) / 2;
+    const float* a_hi = sm + kSmOpP + op_fwd_halves(X) / 2;
+    const float* a_lo = a_hi + kOpLoHalves / 2;
+    const int d = col_d_fwd(X);
+    ctx.mma_ss(d, kNF, a_lo, b_hi, kNF, ksteps, false);
+    ctx.mma_ss(d, kNF, a_hi, b_lo, kNF, ksteps, true);
+    ctx.mma_ss(d, kNF, a_hi, b_hi, kNF, ksteps, true);
+    ctx.commit(kBarFull + X);
+  }
+  FC_HD_CTX void issue_bwd(int X, int l) {
+    const int nb = nb_of(l);
+    const float* b_hi = sm + kSmWP;
+    const float* b_lo = b_hi + bwd_img_halves(l) / 2;
+    const int d = col_d_bwd(X);
+    if (X == 0) {
+      ctx.mma(d, nb, kColGlo, b_hi, nb, 0, kKB / 16, false);
+      ctx.mma(d, nb, kColGhi, b_lo, nb, 0, kKB / 16, true);
+      ctx.mma(d, nb, kColGhi, b_hi, nb, 0, kKB / 16, true);
+    } else {
+      const float* a_hi = sm + kSmOpP;
+      const float* a_lo = a_hi + kOpGLoHalves / 2;
+      ctx.mma_ss(d, nb, a_lo, b_hi, nb, kKB / 16, false);
+      ctx.mma_ss(d, nb, a_hi, b_lo, nb, kKB / 16, true);
+      ctx.mma_ss(d, nb, a_hi, b_hi, nb, kKB / 16, true);
+    }
+    ctx.commit(kBarFull + X);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // tile set-up (service thread of each trajectory)
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void load_tile(int X) {
+    const int b = (tile0 + X) * kTileP + row;
+    const bool ok = b < p.B;
+    float* rows = w_rows(X);
+    for (int r = 0; r < kLook; ++r)
+#pragma unroll
+      for (int f = 0; f < kFeat; ++f) {
+        float v = ok ? p.Z[(size_t)b * (kLook * kFeat) + r * kFeat + f] : 0.f;
+        if (r == kLook - 1 && f == kFeat - 1) v = ok ? p.u0[b] : 0.f;              // Functions.py:1396
+        rows[(size_t)(r * kFeat + f) * kTileP + row] = v;
+      }
+    sm[kSmRefP + X * kTileP + row] = ok ? p.X[(size_t)b * 3 + 2] : 0.f;            // :1392
+    float* cg = w_cost(X);
+    cg[row] = 0.f; cg[kTileP + row] = 0.f; cg[2 * kTileP + row] = 0.f;
+    if (ok) p.pred[(size_t)b * p.N] = p.u0[b];                                     // :1417-1418
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // forward: cell update of NU unit slots starting at slot j0 from 4*NU raw accumulator columns
+  // ---------------------------------------------------------------------------------------------
+  template <int NU>
+  FC_HD_CTX void fwd_units(int j0, const float* g, const ActK& ak, bool first, float* h, float* rp, int r0) {
+    constexpr int NR = (NU * 5 + 3) / 4 * 4;
+    float rv[NR];
+    float cn[NU], tch[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const float xi = g[i * 4 + 0], xf = g[i * 4 + 1], xo = g[i * 4 + 3];
+      float xg = g[i * 4 + 2] * ak.us;
+      xg = fmaf(xg, ak.corr, xg);
+      const float di = denom_(fmaf(xi, ak.khi, xi * ak.klo));
+      const float df = denom_(fmaf(xf, ak.khi, xf * ak.klo));
+      const float dq = denom_(fmaf(xo, ak.khi, xo * ak.klo));
+      const float dg = denom_(2.f * kLog2e * xg);
+      float gi, gf, go, rg;
+      quad_rcp(di, df, dq, dg, gi, gf, go, rg);
+      const float gg = tanh_from_(xg, rg);
+      const float cp = first ? 0.f : c[j0 + i];
+      cn[i] = fmaf(gf, cp, gi * gg);
+      c[j0 + i] = cn[i];
+      rv[i * 5 + 0] = gi; rv[i * 5 + 1] = gf; rv[i * 5 + 2] = gg; rv[i * 5 + 3] = go; rv[i * 5 + 4] = cp;
+    }
+    tanh_batch<NU>(cn, tch);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) h[j0 + i] = rv[i * 5 + 3] * tch[i];
+    if (rp) {
+#pragma unroll
+      for (int i = NU * 5; i < NR; ++i) rv[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR / 4; ++r) {
+        F4 v = {rv[r * 4], rv[r * 4 + 1], rv[r * 4 + 2], rv[r * 4 + 3]};
+        Ctx::stg4_stream(rp + (size_t)(r0 + r) * 32 * 4, v);
+      }
+    }
+  }
+
+  // all unit slots of one step (the accumulator barrier has been waited for by the caller)
+  FC_HD_CTX void fwd_pointwise(int X, bool first, float corr, float* h, float* rec_out) {
+    const ActK ak = make_actk(1.0f / (kScaleA * kScaleW), corr);
+    float* rp = rec_out ? rec_out + ((size_t)uw * kRecF4 * 32 + lane) * 4 : nullptr;
+    const int col0 = col_d_fwd(X) + 4 * u_first;
+    float g[2][16];
+    ctx.template tmem_ld_nowait<16>(col0, g[0]);
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      ctx.tmem_ld_wait();
+      // software pipeline: request the next accumulator columns before working on these
+      if (gi + 1 < 4) ctx.template tmem_ld_nowait<16>(col0 + (gi + 1) * 16, g[(gi + 1) & 1]);
+      else if (last) ctx.template tmem_ld_nowait<8>(col0 + 64, g[(gi + 1) & 1]);
+      fwd_units<4>(gi * 4, g[gi & 1], ak, first, h, rp, gi * 5);
+    }
+    if (last) {
+      ctx.tmem_ld_wait();
+      fwd_units<2>(16, g[0], ak, first, h, rp, 20);        // units 48, 49: record float4 20..22
+    }
+  }
+
+  // layer 0: the 5 row features of step t (service thread of the row): k = 0..7, 3 zero
+  FC_HD_CTX void load_features(int X, int m, int t, float* xin) {
+    const float* rp = w_rows(X) + (size_t)(m + t) * kFeat * kTileP + row;
+#pragma unroll
+    for (int f = 0; f < kFeat; ++f) xin[f] = Ctx::ldcg(rp + f * kTileP);
+  }
+  FC_HD_CTX void store_features(int X, const float* xin) {
+    const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
+    float hi[4], lo[4];
+    Ctx::split_h2(xin[0] * kScaleA, xin[1] * kScaleA, hi[0], lo[0]);
+    Ctx::split_h2(xin[2] * kScaleA, xin[3] * kScaleA, hi[1], lo[1]);
+    Ctx::split_h2(xin[4] * kScaleA, 0.f, hi[2], lo[2]);
+    Ctx::sts4(op_ptr(img_hi, 0), F4{hi[0], hi[1], hi[2], 0.f});
+    Ctx::sts4(op_ptr(img_lo, 0), F4{lo[0], lo[1], lo[2], 0.f});
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // forward window: both tiles, interleaved cell step by cell step
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void fwd_prologue(int X, int l, int m) {
+    // operand of step 0: zero recurrent block, input of step 0 (the previous MMA on this tile has been waited for)
+    const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
+    lap(18);
+    if (service) {
+      if (l == 0) {
+        float xin[kFeat];
+        load_features(X, m, 0, xin);
+        store_features(X, xin);
+      }
+    } else {
+      st_units_zero(img_hi, img_lo, l == 0 ? kRec0 : kRec);
+      if (l > 0) {
+        copy_input(X, 0);
+        Ctx::template cp_wait<0>();
+      }
+    }
+    arrive_ready(X);
+    if (tid == 0) {
+      wait_ready(X);
+      if (X == 0) wait_weights();                            // operand image of this layer landed
+      issue_fwd(X, l, l == 0 ? 1 : 4);                       // recurrent part is zero: only the k-steps over the input
+    }
+    lap(14);
+  }
+
+  FC_HD_CTX void fwd_item_service(int X, int l, int m, int t, bool more_after) {
+    float xin[kFeat];
+    if (l == 0 && t + 1 < kLook) load_features(X, m, t + 1, xin);
+    lap(23);
+    wait_full(X);                                            // accumulator complete; operand and (last tile) image free
+    lap(1);
+    if (t == kLook - 1 && X == ntl - 1 && tid == 0) {        // stream the next weight image under the cell updates
+      if (l + 1 < kLayers) request_weights(false, l + 1);
+      else if (m + 1 < p.N) request_weights(false, 0);
+      else if (p.with_grad) request_weights(true, kLayers - 1);
+      else if (more_after) request_weights(false, 0);
+    }
+    if (t + 1 < kLook) {
+      if (l == 0) store_features(X, xin);
+      lap(2);
+      arrive_ready(X);
+      lap(3);
+      if (tid == 0) {
+        wait_ready(X);
+        lap(4);
+        issue_fwd(X, l, kf_of(l) / 16);
+        lap(5);
+      }
+    }
+  }
+
+  FC_HD_CTX void fwd_item(int X, int l, int m, int t) {
+    const int tmin = t_min_of(m);
+    float h[kMaxOwn];
+    lap(16);
+    swap_cells();
+    lap(11);
+    float* rec_out = nullptr;
+    if (p.with_grad && t >= tmin)
+      rec_out = w_rec(X) + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsP;
+    const int ksteps = t == 0 ? (l == 0 ? 1 : 4) : kf_of(l) / 16;
+    const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
+    const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
+    lap(17);
+    wait_full(X);                                            // accumulator complete; operand free
+    lap(1);
+    if (l > 0 && t + 1 < kLook) copy_input(X, t + 1);        // input block of step t+1: lands during the cell update
+    fwd_pointwise(X, t == 0, corr, h, rec_out);
+    if (l + 1 < kLayers || t + 1 < kLook) {
+      F4 hi4[3], lo4[3];
+      split_units(h, kScaleA, hi4, lo4);
+      if (l + 1 < kLayers) stg_pieces(X, t, hi4, lo4);       // input of the layer above, already in operand format
+      if (t + 1 < kLook) st_pieces(img_hi, img_lo, l == 0 ? kRec0 : kRec, hi4, lo4);
+    }
+    if (t + 1 < kLook) {
+      if (l > 0) Ctx::template cp_wait<0>();
+      lap(2);
+      arrive_ready(X);
+      lap(3);
+    } else if (l == kLayers - 1) {
+      // read-out partial sums over the owned units (Functions.py:377), handed to the service thread of the row
+      // through spare TMEM columns of the own lane
+      const float* fw = sm + kSmSmallP;
+      float xq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j)
+        if (j < nown) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xq[q] = fmaf(fw[q * kHid + u_first + j], h[j], xq[q]);
+        }
+      ctx.template tmem_st<4>(kColFcp + 12 * X + 4 * th, xq);
+      ctx.tmem_st_wait();
+    }
+    if (t + 1 == kLook) lap(13);
+  }
+
+  FC_HD_CTX void fwd_window(int m, bool more_after) {
+    for (int l = 0; l < kLayers; ++l) {
+      for (int X = 0; X < ntl; ++X) fwd_prologue(X, l, m);
+      for (int t = 0; t < kLook; ++t)
+        for (int X = 0; X < ntl; ++X) {
+          if (service) fwd_item_service(X, l, m, t, more_after);
+          else fwd_item(X, l, m, t);
+        }
+    }
+    lap(19);
+    ctx.tc_sync();                                           // read-out partial sums visible
+    if (service)
+      for (int X = 0; X < ntl; ++X) fwd_glue(X, m);
+    lap(15);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // after window m (service thread of each trajectory): read-out, cost terms, next command
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void fwd_glue(int X, int m) {
+    const float* sw = sm + kSmSmallP;
+    float fp[12];
+    ctx.template tmem_ld_nowait<8>(kColFcp + 12 * X, fp);
+    ctx.template tmem_ld_nowait<4>(kColFcp + 12 * X + 8, fp + 8);
+    ctx.tmem_ld_wait();
+    float x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = ((fp[q] + fp[4 + q]) + fp[8 + q]) + sw[(kFCB - kFCW) + q];
+    float* rows = w_rows(X);
+    const float ref = sm[kSmRefP + X * kTileP + row];
+    const float ucur = Ctx::ldcg(rows + (size_t)((kLook - 1 + m) * kFeat + 4) * kTileP + row);
+    const float uprev = Ctx::ldcg(rows + (size_t)((kLook - 2 + m) * kFeat + 4) * kTileP + row);
+    float du = uprev - ucur;
+    float cmd = p.alpha * du * du;                                             // :1405 / :1446
+    float er = (x[0] - ref) * (x[0] - ref);                                    // :1408 / :1443
+    float con = fmaxf(-x[1], 0.f) + fmaxf(-x[2], 0.f) + fmaxf(x[1] - kP1Max, 0.f) + fmaxf(x[2] - kP2Max, 0.f);
+    float* cg = w_cost(X);
+    cg[row] = Ctx::ldcg(cg + row) + ((er + cmd) + con);                        // :1414 / :1452
+    cg[kTileP + row] = Ctx::ldcg(cg + kTileP + row) + cmd;
+    cg[2 * kTileP + row] = Ctx::ldcg(cg + 2 * kTileP + row) + er;
+    float* rnew = rows + (size_t)(kLook + m) * kFeat * kTileP + row;           // rho_{10+m} = [x_{m+1}, u_{m+1}]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rnew[q * kTileP] = x[q];
+    float unext = 0.f;
+    if (m + 1 < p.N) {                                                         // :1424-1430
+      const float* iw = sw + (kINPW - kFCW);
+      const float* ib = sw + (kINPB - kFCW);
+      const float* ow = sw + (kOUTW - kFCW);
+      float v = 0.f;
+      for (int u = 0; u < kFnnHid; ++u) {
+        float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x[3], fmaf(iw[u * 3 + 0], x[0], ib[u])));
+        v = fmaf(ow[u], fmaxf(pre, 0.f), v);
+      }
+      unext = fminf(fmaxf(v, -1.f), 1.f);                                      // nn.Hardtanh
+      int b = (tile0 + X) * kTileP + row;
+      if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;                    // :1455
+    }
+    rnew[4 * kTileP] = unext;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // before the reverse sweep of window m (service thread per trajectory, then 200 accumulation threads)
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void bwd_glue_tile(int X, int m) {
+    const int k = m + 1;
+    const float s = p.grad_scale;
+    const bool has_u = k <= p.N - 1;
+    const float* sw = sm + kSmSmallP;
+    const float* iw = sw + (kINPW - kFCW);
+    const float* ib = sw + (kINPB - kFCW);
+    const float* ow = sw + (kOUTW - kFCW);
+    const bool valid = (tile0 + X) * kTileP + row < p.B;
+    const float* rows = w_rows(X);
+    const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileP + row;
+    float x0 = Ctx::ldcg(rx), x1 = Ctx::ldcg(rx + kTileP), x2 = Ctx::ldcg(rx + 2 * kTileP), x3 = Ctx::ldcg(rx + 3 * kTileP);
+    const float ref = sm[kSmRefP + X * kTileP + row];
+    float g0 = 2.f * (x0 - ref) * s;
+    float g1 = s * ((x1 > kP1Max ? 1.f : 0.f) - (x1 < 0.f ? 1.f : 0.f));
+    float g2 = s * ((x2 > kP2Max ? 1.f : 0.f) - (x2 < 0.f ? 1.f : 0.f));
+    float g3 = 0.f;
+    float dv = 0.f;
+    if (has_u) {
+      const float* gr = w_grow(X) + (size_t)k * kFeat * kTileP + row;
+      float uk = Ctx::ldcg(rows + (size_t)((kLook - 1 + k) * kFeat + 4) * kTileP + row);
+      float ukm1 = Ctx::ldcg(rows + (size_t)((kLook - 2 + k) * kFeat + 4) * kTileP + row);
+      float gu = Ctx::ldcg(gr + 4 * kTileP) - 2.f * p.alpha * (ukm1 - uk) * s;
+      if (k + 1 <= p.N - 1) {
+        float ukp1 = Ctx::ldcg(rows + (size_t)((kLook + k) * kFeat + 4) * kTileP + row);
+        gu += 2.f * p.alpha * (uk - ukp1) * s;
+      }
+      float v = 0.f;
+      for (int u = 0; u < kFnnHid; ++u) {
+        float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x3, fmaf(iw[u * 3 + 0], x0, ib[u])));
+        v = fmaf(ow[u], fmaxf(pre, 0.f), v);
+      }
+      dv = (valid && v > -1.f && v < 1.f) ? gu : 0.f;           // hardtanh_backward
+      float d0 = 0.f, d1 = 0.f;
+      for (int u = 0; u < kFnnHid; ++u) {
+        float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x3, fmaf(iw[u * 3 + 0], x0, ib[u])));
+        float dp = pre > 0.f ? dv * ow[u] : 0.f;                  // threshold_backward
+        d0 = fmaf(dp, iw[u * 3 + 0], d0);
+        d1 = fmaf(dp, iw[u * 3 + 1], d1);
+      }
+      g0 += d0 + Ctx::ldcg(gr);
+      g1 += Ctx::ldcg(gr + kTileP);
+      g2 += Ctx::ldcg(gr + 2 * kTileP);
+      g3 += d1 + Ctx::ldcg(gr + 3 * kTileP);
+      sm[kSmDvP + X * kTileP + row] = dv;
+      sm[kSmFinP + (X * 2) * kTileP + row] = x0;
+      sm[kSmFinP + (X * 2 + 1) * kTileP + row] = x3;
+    }
+    if (!valid) { g0 = g1 = g2 = g3 = 0.f; }
+    sm[kSmGxP + (X * 4 + 0) * kTileP + row] = g0;
+    sm[kSmGxP + (X * 4 + 1) * kTileP + row] = g1;
+    sm[kSmGxP + (X * 4 + 2) * kTileP + row] = g2;
+    sm[kSmGxP + (X * 4 + 3) * kTileP + row] = g3;
+  }
+  FC_HD_CTX void bwd_glue(int m) {
+    const bool has_u = m + 1 <= p.N - 1;
+    const float* sw = sm + kSmSmallP;
+    const float* iw = sw + (kINPW - kFCW);
+    const float* ib = sw + (kINPB - kFCW);
+    const float* ow = sw + (kOUTW - kFCW);
+    if (service)
+      for (int X = 0; X < ntl; ++X) bwd_glue_tile(X, m);
+    ctx.sync();
+    // controller weight gradients, unit-parallel: the 200 threads behind the service warps
+    if (has_u && tid >= 128 && tid < 128 + 4 * kFnnHid) {
+      const int u = (tid - 128) % kFnnHid, part = (tid - 128) / kFnnHid;
+      double a_ow = 0.0, a_b = 0.0, a_w0 = 0.0, a_w1 = 0.0, a_w2 = 0.0;   // batch sums cancel heavily: fp64
+      const float w0 = iw[u * 3 + 0], w1 = iw[u * 3 + 1], w2 = iw[u * 3 + 2], bb = ib[u], owu = ow[u];
+      for (int X = 0; X < ntl; ++X)
+        for (int tr = part * 32; tr < part * 32 + 32; ++tr) {
+          float dv = sm[kSmDvP + X * kTileP + tr];
+          float x0 = sm[kSmFinP + (X * 2) * kTileP + tr], x3 = sm[kSmFinP + (X * 2 + 1) * kTileP + tr];
+          float ref = sm[kSmRefP + X * kTileP + tr];
+          float pre = fmaf(w2, ref, fmaf(w1, x3, fmaf(w0, x0, bb)));
+          a_ow += (double)dv * (double)fmaxf(pre, 0.f);
+          float dp = pre > 0.f ? dv * owu : 0.f;
+          a_b += dp;
+          a_w0 += (double)dp * (double)x0;
+          a_w1 += (double)dp * (double)x3;
+          a_w2 += (double)dp * (double)ref;
+        }
+      double* pg = reinterpret_cast<double*>(sm + kSmPgP) + part * kNumFnnGrad;
+      pg[u * 3 + 0] += a_w0;
+      pg[u * 3 + 1] += a_w1;
+      pg[u * 3 + 2] += a_w2;
+      pg[150 + u] += a_b;
+      pg[200 + u] += a_ow;
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // backward cell gradient of NU unit slots: record(t) -> factors, dh -> d(cell), d(gates)
+  //   A = o(1-tanh^2 c), Ko = tanh(c) o(1-o), Ki = g i(1-i), Kf = c_prev f(1-f), Kg = i(1-g^2)
+  //   dct = dc + dh A; dG = (dct Ki, dct Kf, dct Kg, dh Ko); dc = dct f
+  // ---------------------------------------------------------------------------------------------
+  template <int NU>
+  FC_HD_CTX static void rec_load(const float* rp, int r0, float* rv) {
+    constexpr int NR = (NU * 5 + 3) / 4 * 4;
+#pragma unroll
+    for (int r = 0; r < NR / 4; ++r) {
+      F4 v = Ctx::ldg4_stream(rp + (size_t)(r0 + r) * 32 * 4);
+      rv[r * 4] = v.x; rv[r * 4 + 1] = v.y; rv[r * 4 + 2] = v.z; rv[r * 4 + 3] = v.w;
+    }
+  }
+  template <int NU>
+  FC_HD_CTX void bwd_units(int j0, const float* rv, const float* dh, float* dg) {
+    float cn[NU], tch[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) cn[i] = fmaf(rv[i * 5 + 1], rv[i * 5 + 4], rv[i * 5 + 0] * rv[i * 5 + 2]);
+    tanh_batch<NU>(cn, tch);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const int j = j0 + i;
+      const float gi = rv[i * 5 + 0], gf = rv[i * 5 + 1], gg = rv[i * 5 + 2], go = rv[i * 5 + 3], cp = rv[i * 5 + 4];
+      const float A = go * (1.f - tch[i] * tch[i]);
+      const float dct = fmaf(dh[j], A, c[j]);
+      c[j] = dct * gf;
+      dg[i * 4 + 0] = dct * (gg * gi * (1.f - gi));
+      dg[i * 4 + 1] = dct * (cp * gf * (1.f - gf));
+      dg[i * 4 + 2] = dct * (gi * (1.f - gg * gg));
+      dg[i * 4 + 3] = dh[j] * (tch[i] * go * (1.f - go));
+    }
+  }
+
+  FC_HD_CTX void prefetch_record(const float* rec_in) {
+    const float* rp = rec_in + ((size_t)uw * kRecF4 * 32 + lane) * 4;
+    const int nf4 = last ? 23 : 20;
+    for (int r = 0; r < nf4; ++r) Ctx::prefetch_l2(rp + (size_t)r * 32 * 4);
+  }
+
+  // d(h) of step t that does not come from the recurrent MMA: the layer above (thread-private scratch) or,
+  // for the top layer at the last step, the read-out (Functions.py:377)
+  FC_HD_CTX void bwd_extra(int X, int l, int t, float* extra) {
+    if (l == kLayers - 1) {
+      if (t == kLook - 1) {
+        float gxv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + row];
+#pragma unroll
+        for (int j = 0; j < kMaxOwn; ++j) {
+          const int u = u_first + j < kHid ? u_first + j : kHid - 1;
+          const float* fw = sm + kSmSmallP + u;
+          extra[j] = fw[0] * gxv[0] + fw[kHid] * gxv[1] + fw[2 * kHid] * gxv[2] + fw[3 * kHid] * gxv[3];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kMaxOwn; ++j) extra[j] = 0.f;
+      }
+    } else {
+      const float* dsq = w_dseq(X) + (size_t)t * kSlot + (size_t)uw * kMaxOwn * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) extra[j] = j < nown ? Ctx::ldcg(dsq + j * 32) : 0.f;
+    }
+  }
+
+  // result of MMA(X, l, t): d(input) of step t -> the layer below, d(h_prev) -> dh   (cell-update warps)
+  FC_HD_CTX void bwd_collect(int X, int l, int t, float* dh) {
+    const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
+    const float unscale_b = p.g_unscale / kScaleW;         // exact power of two
+    const int dcol = col_d_bwd(X);
+    if (l > 0) {
+      float d[36];
+      ctx.template tmem_ld_nowait<32>(dcol + 36 * th, d);
+      ctx.template tmem_ld_nowait<4>(dcol + 36 * th + 32, d + 32);
+      ctx.tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 2 * kMaxOwn; ++j) { d[j] *= unscale_b; d[j] = fmaf(d[j], corr_b, d[j]); }
+      float* dq = w_dseq(X) + (size_t)t * kSlot + (size_t)uw * kMaxOwn * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) {
+        if (j < nown) dq[j * 32] = d[j];                   // d(input unit) -> the layer below, same thread
+        dh[j] = d[kMaxOwn + j];
+      }
+    } else {
+      float d[18];
+      ctx.template tmem_ld_nowait<16>(dcol + 18 * th, d);
+      ctx.template tmem_ld_nowait<2>(dcol + 18 * th + 16, d + 16);
+      ctx.tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) { d[j] *= unscale_b; dh[j] = fmaf(d[j], corr_b, d[j]); }
+    }
+  }
+  // layer 0: gradient of the row features of step t (service thread of the row)
+  FC_HD_CTX void bwd_collect_features(int X, int m, int t) {
+    const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
+    const float unscale_b = p.g_unscale / kScaleW;
+    const int kr = m + t - (kLook - 1);                    // gradient of row rho_{9+kr}
+    if (kr >= 0) {
+      float df[8];
+      ctx.template tmem_ld<8>(col_d_bwd(X) + 56, df);
+      float* gp = w_grow(X) + (size_t)kr * kFeat * kTileP + row;
+#pragma unroll
+      for (int f = 0; f < kFeat; ++f) {
+        const float v = df[f] * unscale_b;
+        gp[f * kTileP] = Ctx::ldcg(gp + f * kTileP) + fmaf(v, corr_b, v);
+      }
+    }
+  }
+
+  FC_HD_CTX void bwd_item_service(int X, int l, int m, int t) {
+    if (t < kLook - 1) {
+      lap(23);
+      wait_full(X);                                        // MMA(X, l, t+1) complete
+      lap(6);
+      if (l == 0) bwd_collect_features(X, m, t + 1);
+    }
+    lap(7);
+    arrive_ready(X);
+    lap(8);
+    if (tid == 0) {
+      wait_ready(X);
+      if (X == 0 && t == kLook - 1) wait_weights();        // backward image of this layer landed
+      lap(9);
+      issue_bwd(X, l);
+      lap(10);
+    }
+  }
+
+  FC_HD_CTX void bwd_item(int X, int l, int m, int t) {
+    const int tmin = t_min_of(m);
+    float dh[kMaxOwn];
+    lap(20);
+    swap_cells();
+    lap(11);
+    const float* rec_l = w_rec(X) + (size_t)(rec_base(m) + (long)l * steps_kept(m)) * kRecFloatsP;
+    // HBM -> L2 for the next step of this tile (or the first step of the next layer / window)
+    if (t - 1 >= tmin) prefetch_record(rec_l + (size_t)(t - 1 - tmin) * kRecFloatsP);
+    else if (l > 0) prefetch_record(w_rec(X) + (size_t)(rec_base(m) + (long)(l - 1) * steps_kept(m) + (kLook - 1 - tmin)) * kRecFloatsP);
+    else if (m > 0) prefetch_record(w_rec(X) + (size_t)(rec_base(m - 1) + (long)(kLayers - 1) * steps_kept(m - 1) + (kLook - 1 - t_min_of(m - 1))) * kRecFloatsP);
+    const float* rp = rec_l + (size_t)(t - tmin) * kRecFloatsP + ((size_t)uw * kRecF4 * 32 + lane) * 4;
+    float rv[2][20];
+    rec_load<4>(rp, 0, rv[0]);                             // first record group: in flight during the wait
+    {
+      float extra[kMaxOwn];
+      bwd_extra(X, l, t, extra);
+      if (t == kLook - 1) {
+#pragma unroll
+        for (int j = 0; j < kMaxOwn; ++j) { dh[j] = extra[j]; c[j] = 0.f; }
+      } else {
+        lap(12);
+        wait_full(X);                                      // MMA(X, l, t+1) complete
+        lap(6);
+        bwd_collect(X, l, t + 1, dh);
+#pragma unroll
+        for (int j = 0; j < kMaxOwn; ++j) dh[j] += extra[j];
+      }
+    }
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      // software pipeline: request the next record group before working on this one
+      if (gi + 1 < 4) rec_load<4>(rp, (gi + 1) * 5, rv[(gi + 1) & 1]);
+      else if (last) rec_load<2>(rp, 20, rv[(gi + 1) & 1]);
+      float dg[16];
+      bwd_units<4>(gi * 4, rv[gi & 1], dh, dg);
+      if (X == 0) st_pairs<8>(kColGhi + 2 * u_first + gi * 8, kColGlo + 2 * u_first + gi * 8, dg, p.g_scale);
+      else st_pairs_smem<8>(4 * u_first + gi * 16, dg, p.g_scale);
+    }
+    if (last) {
+      float dg[8];
+      bwd_units<2>(16, rv[0], dh, dg);
+      if (X == 0) st_pairs<4>(kColGhi + 2 * u_first + 32, kColGlo + 2 * u_first + 32, dg, p.g_scale);
+      else st_pairs_smem<4>(4 * u_first + 64, dg, p.g_scale);
+    }
+    if (X == 0) ctx.tmem_st_wait();
+    lap(7);
+    arrive_ready(X);
+    lap(8);
+  }
+
+  // after the last step of a layer: collect the result of MMA(X, l, tmin)
+  FC_HD_CTX void bwd_tail(int X, int l, int m, bool more_after) {
+    const int tmin = t_min_of(m);
+    lap(22);
+    wait_full(X);
+    lap(6);
+    if (X == ntl - 1 && tid == 0) {                        // all MMAs that read this image are complete
+      if (l > 0) request_weights(true, l - 1);
+      else if (m > 0) request_weights(true, kLayers - 1);
+      else if (more_after) request_weights(false, 0);
+    }
+    if (service) {
+      if (l == 0) bwd_collect_features(X, m, tmin);
+    } else if (l > 0) {
+      float dh[kMaxOwn];
+      bwd_collect(X, l, tmin, dh);                         // d(h) before the first kept step is not needed
+    }
+    lap(14);
+  }
+
+  FC_HD_CTX void bwd_window(int m, bool more_after) {
+    const int tmin = t_min_of(m);
+    lap(21);
+    bwd_glue(m);
+    ctx.sync();
+    lap(15);
+    for (int l = kLayers - 1; l >= 0; --l) {
+      for (int t = kLook - 1; t >= tmin; --t)
+        for (int X = 0; X < ntl; ++X) {
+          if (service) bwd_item_service(X, l, m, t);
+          else bwd_item(X, l, m, t);
+        }
+      for (int X = 0; X < ntl; ++X) bwd_tail(X, l, m, more_after);
+    }
+    ctx.tc_sync();                                         // all accumulator reads of this window done
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // per-pass epilogues (service threads)
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void store_costs() {
+    if (service) {
+      for (int X = 0; X < kTiles; ++X) {
+        float mine = 0.f;
+        int b = (tile0 + X) * kTileP + row;
+        if (X < ntl && b < p.B) {
+          const float inv = 1.f / (float)p.N;
+          const float* cg = w_cost(X);
+          mine = Ctx::ldcg(cg + row) * inv;                                    // :1458-1460
+          p.cost[b] = mine;
+          p.command[b] = Ctx::ldcg(cg + kTileP + row) * inv;
+          p.error[b] = Ctx::ldcg(cg + 2 * kTileP + row) * inv;
+        }
+        sm[kSmGxP + X * kTileP + row] = mine;              // gx area is free between the sweeps
+      }
+    }
+    ctx.sync();
+    if (tid == 0) {
+      double acc = 0.0;
+      for (int i = 0; i < kTiles * kTileP; ++i) acc += (double)sm[kSmGxP + i];
+      *reinterpret_cast<double*>(sm + kSmRedP) += acc;
+    }
+    ctx.sync();
+  }
+
+  FC_HD_CTX void store_du0() {
+    if (service)
+      for (int X = 0; X < ntl; ++X) {
+        int b = (tile0 + X) * kTileP + row;
+        if (b < p.B) {
+          const float s = p.grad_scale;
+          const float* rows = w_rows(X);
+          float u0 = Ctx::ldcg(rows + (size_t)((kLook - 1) * kFeat + 4) * kTileP + row);
+          float um1 = Ctx::ldcg(rows + (size_t)((kLook - 2) * kFeat + 4) * kTileP + row);
+          float g = Ctx::ldcg(w_grow(X) + 4 * kTileP + row) - 2.f * p.alpha * (um1 - u0) * s;
+          if (p.N > 1) {
+            float u1 = Ctx::ldcg(rows + (size_t)(kLook * kFeat + 4) * kTileP + row);
+            g += 2.f * p.alpha * (u0 - u1) * s;
+          }
+          p.du0[b] = g;
+        }
+      }
+  }
+
+  // zero padding of the dG operands (k = 200..207): TMEM columns 100..103 of tile 0, the last 16-byte piece of tile 1
+  FC_HD_CTX void zero_dg_padding() {
+    if (service) {
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      ctx.template tmem_st<4>(kColGhi + 100, z);
+      ctx.template tmem_st<4>(kColGlo + 100, z);
+      ctx.tmem_st_wait();
+      const F4 z4 = {0.f, 0.f, 0.f, 0.f};
+      Ctx::sts4(op_ptr(0, kGates), z4);
+      Ctx::sts4(op_ptr(kOpGLoHalves, kGates), z4);
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // persistent loop over tile pairs
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void run() {
+    ctx.tc_setup(sm + kSmBarP);
+#ifdef FC_TC_TIMING
+    tlast = Ctx::clock();
+#endif
+    if (tid == 0) {
+      ctx.bar_init(kBarReady, kWarpsP);
+      ctx.bar_init(kBarReady + 1, kWarpsP);
+    }
+    for (int i = tid; i < kSmallFloats; i += kThreadsP) sm[kSmSmallP + i] = p.wpack[kSmallOff + i];
+    for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsP) reinterpret_cast<double*>(sm + kSmPgP)[i] = 0.0;
+    if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedP) = 0.0;
+    ctx.bar_init_fence();
+    ctx.sync();
+    const int npairs = (p.num_tiles + kTiles - 1) / kTiles;
+    if (tid == 0 && ctx.bid() < npairs) request_weights(false, 0);
+    for (int pp = ctx.bid(); pp < npairs; pp += ctx.nblk()) {
+      const bool more = pp + ctx.nblk() < npairs;
+      tile0 = pp * kTiles;
+      ntl = p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles;
+      if (service)
+        for (int X = 0; X < ntl; ++X) load_tile(X);
+      ctx.sync();
+      for (int m = 0; m < p.N; ++m) fwd_window(m, more);
+      store_costs();
+      if (p.with_grad) {
+        if (service)
+          for (int X = 0; X < ntl; ++X) {
+            float* grow = w_grow(X);
+            for (int k = 0; k < p.N; ++k)
+#pragma unroll
+              for (int f = 0; f < kFeat; ++f) grow[(size_t)(k * kFeat + f) * kTileP + row] = 0.f;
+          }
+        zero_dg_padding();
+        ctx.sync();
+        for (int m = p.N - 1; m >= 0; --m) bwd_window(m, more);
+        store_du0();
+      }
+      ctx.tc_sync();
+    }
+    double* part = p.partial + (size_t)ctx.bid() * kPartialStride;
+    const double* pgd = reinterpret_cast<const double*>(sm + kSmPgP);
+    for (int i = tid; i < kNumFnnGrad; i += kThreadsP)
+      part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
+    if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedP);
+    ctx.sync();
+#ifdef FC_TC_TIMING
+    if (p.debug_timing && (tid == 0 || tid == 160) && ctx.bid() == 0) Ctx::report_pair(tid, tm);
+#endif
+    ctx.tc_teardown();
+  }
+};
+
+}  // namespace pr
+}  // namespace fc

@@ -10,12 +10,14 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
 #define FC_HD_CTX inline
 #include "../../forging_control_b200/csrc/fc_mpc_kernel.inl"
 #include "../../forging_control_b200/csrc/fc_mpc_tc_kernel.inl"
+#include "../../forging_control_b200/csrc/fc_mpc_pair_kernel.inl"
 #include <atomic>
 #include <cstdint>
 
@@ -55,10 +57,14 @@ struct EmuCtx {
 // thread with tf32-truncated operands, mbarriers = counters --------------------------------------------
 struct EmuBlockTC : EmuBlock {
   std::vector<float> tmem;
-  std::atomic<unsigned> bars[8];
-  EmuBlockTC(int b, int n) : EmuBlock(b, n, fc::tc::kThreadsTC), tmem(128 * 512, 0.f) {
-    smem.assign(fc::tc::kSmFloatsTC, 0.f);
+  std::atomic<unsigned> bars[8];      // arrivals
+  unsigned counts[8];                 // arrivals per phase
+  std::vector<std::unique_ptr<std::barrier<>>> wbar;   // one barrier per warp (__syncwarp)
+  EmuBlockTC(int b, int n, int smem_floats = fc::tc::kSmFloatsTC) : EmuBlock(b, n, fc::tc::kThreadsTC), tmem(128 * 512, 0.f) {
+    smem.assign(smem_floats, 0.f);
     for (auto& x : bars) x.store(0);
+    for (auto& x : counts) x = 1;
+    for (int w = 0; w < fc::tc::kThreadsTC / 32; ++w) wbar.emplace_back(new std::barrier<>(32));
   }
 };
 
@@ -106,7 +112,27 @@ struct EmuCtxTC : EmuCtx {
   }
   void commit(int bar) const { tb->bars[bar].fetch_add(1); }
   void bar_wait(int bar, unsigned phase) const {
-    while (tb->bars[bar].load() <= phase) std::this_thread::yield();
+    while (tb->bars[bar].load() / tb->counts[bar] <= phase) std::this_thread::yield();
+  }
+  // pair kernel
+  void bar_init(int bar, int count) const { tb->counts[bar] = (unsigned)count; tb->bars[bar].store(0); }
+  void bar_init_fence() const {}
+  void warp_sync() const { tb->wbar[t >> 5]->arrive_and_wait(); }
+  static void report_pair(int, const long long*) {}
+  void bar_arrive(int bar) const { tb->bars[bar].fetch_add(1); }
+  void operand_fence() const {}
+  static void sts2(float* p, float a, float b) { p[0] = a; p[1] = b; }
+  void mma_ss(int d_col, int n, const float* a_img, const float* b_img, int n_img, int ksteps, bool accumulate) const {
+    const int K = ksteps * 16;
+    const uint16_t* ah = reinterpret_cast<const uint16_t*>(a_img);
+    const uint16_t* bh = reinterpret_cast<const uint16_t*>(b_img);
+    for (int m = 0; m < 128; ++m)
+      for (int j = 0; j < n; ++j) {
+        double s = accumulate ? (double)tb->tmem[m * 512 + d_col + j] : 0.0;
+        for (int k = 0; k < K; ++k)
+          s += (double)h_val(ah[(k / 8) * (128 * 8) + m * 8 + (k & 7)]) * (double)h_val(bh[(k / 8) * (n_img * 8) + j * 8 + (k & 7)]);
+        tb->tmem[m * 512 + d_col + j] = (float)s;
+      }
   }
   void bulk_load(float* dst, const float* src, int nfloats, int bar) const {
     std::memcpy(dst, src, (size_t)nfloats * 4);
@@ -230,4 +256,64 @@ int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const fl
   return 0;
 }
 
+
+int fc_emu_pack_floats_pair() { return fc::pr::kPackFloatsP; }
+
+void fc_emu_pack_weights_pair(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
+                              const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
+                              const float* inp_w, const float* inp_b, const float* out_w, float* out) {
+  fc::RawWeights w;
+  w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
+  w.fc_w = fc_w; w.fc_b = fc_b; w.inp_w = inp_w; w.inp_b = inp_b; w.out_w = out_w;
+  uint16_t* oh = reinterpret_cast<uint16_t*>(out);
+  const long n_halves = 2L * fc::pr::kSmallOff;
+  for (long i = 0; i < n_halves; ++i) {
+    const fc::pr::PrSlot s = fc::pr::decode_half(i);
+    const float v = (s.kind == 0 ? fc::pr::fwd_weight(w, s.l, s.h) : fc::pr::bwd_weight(w, s.l, s.h)) * fc::pr::kScaleW;
+    const uint16_t hi = EmuCtxTC::h_bits(v);
+    oh[i] = s.lo ? EmuCtxTC::h_bits(v - EmuCtxTC::h_val(hi)) : hi;
+  }
+  for (int j = 0; j < fc::kSmallFloats; ++j) out[fc::pr::kSmallOff + j] = fc::packed_value(w, fc::kFCW + j);
+}
+
+int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                         long long B_global, int with_grad, int grid, float* cost, float* command, float* error,
+                         float* pred, float* du0, float* gl /*[256]*/) {
+  fc::MpcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.X = X; p.u0 = u0; p.Z = Z; p.wpack = wpack;
+  p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
+  p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
+  p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.acc_comp = 1.0f;
+  { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
+  p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;
+  const int npairs = (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles;
+  if (grid > npairs) grid = npairs;
+  fc::pr::WorkLayoutP wl = fc::pr::work_layout_p(N, with_grad);
+  p.work_stride = fc::pr::kTiles * wl.total;
+  std::vector<float> work((size_t)grid * p.work_stride, 0.f);
+  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
+  p.work = work.data();
+  p.partial = partial.data();
+  for (int b = 0; b < grid; ++b) {
+    EmuBlockTC blk(b, grid, fc::pr::kSmFloatsP);
+    std::vector<std::thread> th;
+    th.reserve(fc::pr::kThreadsP);
+    for (int t = 0; t < fc::pr::kThreadsP; ++t)
+      th.emplace_back([&blk, &p, t]() {
+        EmuCtxTC ctx(&blk, t);
+        fc::pr::MpcPair<EmuCtxTC> k(ctx, p);
+        k.run();
+      });
+    for (auto& x : th) x.join();
+  }
+  for (int i = 0; i < 256; ++i) gl[i] = 0.f;
+  for (int i = 0; i <= fc::kNumFnnGrad; ++i) {
+    double a = 0.0;
+    for (int b = 0; b < grid; ++b) a += partial[(size_t)b * fc::kPartialStride + i];
+    gl[i] = (float)(i == fc::kNumFnnGrad ? a / (double)B_global : a);
+  }
+  return 0;
+}
 }  // extern "C"
