@@ -276,7 +276,9 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved = F_ALG * B * N / (kern_ms * 1e-3) / 1e12
         kernel = os.environ.get("FC_MPC_KERNEL", "auto")
-        use_tc = kernel in ("tc", "auto")
+        use_tc = kernel in ("tc", "pair", "auto")
+        kname = {"ffma": "FP32 FFMA (fc::mpc_loss_kernel)", "tc": "tcgen05 fp16 hi/lo split, one tile per CTA (fc::mpc_loss_tc_kernel)"}.get(
+            kernel, "tcgen05 fp16 hi/lo split, two tiles per CTA (fc::mpc_loss_pair_kernel)")
         # kind::f16 runs at the bf16 rate; MEASURED_PEAKS.json holds the dense bf16 figure of this pool (sustained:
         # the kernel runs for 70+ ms under the power cap), fallback 1.4 PFLOP/s (B200_PROFILING.md)
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
@@ -295,10 +297,10 @@ def run_ours(args):
             roof = dict(fp32, bound="fp32")
         # DRAM traffic per launch: ncu --set full capture of the same kernel at B=71040, N=10 (profiles/), scaled
         # linearly in B (the traffic is the per-trajectory activation records, written once and read once)
-        traffic_per_traj = (27.86e9 if use_tc else 25.67e9) / 71040.0
+        traffic_per_traj = (17.18e9 / 37888.0 if kernel in ("pair", "auto") else (27.86e9 if use_tc else 25.67e9) / 71040.0)
         roof.update({"flop_per_trajectory_step": F_ALG, "kernel_ms": kern_ms,
                      "traffic": traffic_per_traj * B if N == 10 else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu capture at B=71040 scaled by B (profiles/r01_*)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full capture of the same kernel (B=37888 pair / 71040 others) scaled by B (profiles/r01_*)",
                      "hbm": {"algorithmic_gbs": ALG_BYTES_PER_TRAJ * B / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}})
         line = {
@@ -308,7 +310,7 @@ def run_ours(args):
             "config": {"workload": f"fused MPC-loss fwd+bwd, N={N}, {B} synthetic trajectories per GPU "
                                    f"(BASELINE config 5: 4194304 / 8), U(-1,1) inputs, shipped surrogate + controller weights",
                        "horizon": N, "alpha": ALPHA, "batch_per_gpu": B, "global_batch": B_global,
-                       "kernel": "tcgen05 fp16 hi/lo split (fc::mpc_loss_tc_kernel)" if use_tc else "FP32 FFMA (fc::mpc_loss_kernel)",
+                       "kernel": kname,
                        "parallelism": f"dp{world}", "l2": "inputs (105 MB Z + GBs of activation records) exceed the 126 MB L2"},
             "loss": loss_val,
             "e2e": {"value": B_global * N / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",

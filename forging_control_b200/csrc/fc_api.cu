@@ -421,15 +421,17 @@ struct MpcPlan {
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
-// Automatic choice = tcgen05 kernel for every batch size: measured on B200 (profiles/r01_bench_configs_both_kernels.jsonl)
-// it is 2.5x faster than the FFMA kernel from the reference's own B=15 (2.9 ms vs 7.5 ms per step; one M=128 tile is
-// the smallest MMA either way) up to B=524288 (57 M vs 23 M trajectory-steps/s).  The FFMA kernel stays selectable.
+// Automatic choice (measured on B200, profiles/): one 128-trajectory tile or less -> the one-tile tcgen05 kernel
+// (B=15: 2.9 ms per step against 7.5 ms for the FFMA kernel; one M=128 tile is the smallest MMA either way);
+// more -> the pair kernel, which keeps two tiles per CTA in flight (78 M against 74 M trajectory-steps/s at
+// B=524288; the FFMA kernel reaches 23 M).  All three stay selectable (fc_mpc_select_kernel / FC_MPC_KERNEL).
 static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
   pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
+  if (mode == 0 && B > tc::kTileTC) pl->kind = 2;
   const int tile = pl->kind ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
   const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items

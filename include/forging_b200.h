@@ -58,9 +58,10 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
  *   du0 [B] = d loss / d output_controller), gl[250] = sum_b cost[b] / B_global (the loss).
  *   with_grad = 0 computes the forward only (du0 may be NULL, gl[0..249] are zero).              */
 size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad);
-/* Kernel behind fc_mpc_loss: 0 = automatic (the tcgen05 3xTF32 kernel; measured faster at every batch size),
- * 1 = always the FP32 FFMA kernel, 2 = always the tcgen05 kernel.  Also settable with the environment
- * variable FC_MPC_KERNEL=ffma|tc before the first call.  Both kernels meet the same parity bar.      */
+/* Kernel behind fc_mpc_loss: 0 = automatic (B <= 128: the one-tile tcgen05 kernel, else the two-tile tcgen05
+ * pair kernel; measured fastest), 1 = always the FP32 FFMA kernel, 2 = always the one-tile tcgen05 kernel,
+ * 3 = always the pair kernel.  Also settable with the environment variable FC_MPC_KERNEL=ffma|tc|pair before
+ * the first call.  All kernels meet the same parity bar.                                            */
 int fc_mpc_select_kernel(int mode);
 int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N,
                 float alpha, long long B_global, int with_grad, float* cost, float* command,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert _native.lib().fc_version() == 100
-    assert _native.lib().fc_pack_floats() == 123456 + 120264
+    assert _native.lib().fc_pack_floats() == 123456 + 120264 + 120264
 
 
 def test_state_dict_layout_loads_shipped_checkpoints_strictly(golden_weights):
