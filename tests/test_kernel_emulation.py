@@ -15,7 +15,9 @@ from conftest import REPO, rel_max, state_dicts
 
 EMU_SRC = os.path.join(REPO, "tests", "emu", "fc_emu.cpp")
 EMU_LIB = os.path.join(REPO, "tests", "emu", "libfc_emu.so")
-DEPS = [EMU_SRC] + [os.path.join(REPO, "forging_control_b200", "csrc", f) for f in ("fc_mpc_kernel.inl", "fc_layout.h")]
+DEPS = [EMU_SRC] + [os.path.join(REPO, "forging_control_b200", "csrc", f) for f in
+                    ("fc_mpc_kernel.inl", "fc_layout.h", "fc_mpc_tc_kernel.inl", "fc_tc_layout.h",
+                     "fc_mpc_pair_kernel.inl", "fc_pair_layout.h")]
 FP = ctypes.POINTER(ctypes.c_float)
 
 
@@ -88,3 +90,66 @@ def test_emulated_forward_only_and_sharding(emu, golden_cases, golden_weights):
     b = _run(emu, wp, np.ascontiguousarray(X[9:]), np.ascontiguousarray(u0[9:]), np.ascontiguousarray(Z[9:]), N, 20.0, b_global=B)
     assert rel_max(a["gl"][:251] + b["gl"][:251], full["gl"][:251]) < 2e-6
     assert rel_max(np.concatenate((a["du0"], b["du0"])), full["du0"]) < 1e-6
+
+
+# ---- tcgen05 kernel sources (one-tile and pair): TMEM = array, MMA = fp16 hi/lo dot products executed by the issuing
+# thread, mbarriers = counters.  Checks operand layouts, the hi/lo split, the per-tile hand-shakes and the dataflow;
+# the truncating hardware accumulator is not modelled (its compensation is switched off in the emulation).
+def _pack_v(emu, lstm, fnn, variant):
+    names = [("l", "lstm.weight_ih_l0"), ("l", "lstm.weight_hh_l0"), ("l", "lstm.weight_ih_l1"), ("l", "lstm.weight_hh_l1"),
+             ("l", "lstm.weight_ih_l2"), ("l", "lstm.weight_hh_l2"), ("l", "fc.weight"), ("l", "fc.bias"),
+             ("f", "fc_inp.weight"), ("f", "fc_inp.bias"), ("f", "fc_out.weight")]
+    arrs = [np.ascontiguousarray((lstm if s == "l" else fnn)[n], dtype=np.float32) for s, n in names]
+    out = np.zeros(getattr(emu, f"fc_emu_pack_floats_{variant}")(), np.float32)
+    getattr(emu, f"fc_emu_pack_weights_{variant}")(*[_p(a) for a in arrs], _p(out))
+    return out
+
+
+def _run_v(emu, variant, wp, X, u0, Z, N, alpha, with_grad=1, grid=2):
+    B = len(X)
+    o = {k: np.zeros(B, np.float32) for k in ("cost", "command", "error", "du0")}
+    o["pred"] = np.zeros((B, N), np.float32)
+    o["gl"] = np.zeros(256, np.float32)
+    getattr(emu, f"fc_emu_mpc_loss_{variant}")(_p(X), _p(u0), _p(Z), _p(wp), B, N, ctypes.c_float(alpha), ctypes.c_longlong(B),
+                                               with_grad, grid, _p(o["cost"]), _p(o["command"]), _p(o["error"]), _p(o["pred"]),
+                                               _p(o["du0"]), _p(o["gl"]))
+    return o
+
+
+def _check_v(o, out, g, tol=1e-5):
+    assert abs(o["gl"][250] - out["loss"]) / abs(out["loss"]) < tol
+    for k, ok in (("cost", "cost"), ("command", "command"), ("error", "error"), ("pred", "prediction")):
+        assert rel_max(o[k], out[ok]) < tol, k
+    assert rel_max(o["du0"], g["u0"]) < tol
+    assert rel_max(o["gl"][:150].reshape(50, 3), g["inp_w"]) < tol
+    assert rel_max(o["gl"][150:200], g["inp_b"]) < tol
+    assert rel_max(o["gl"][200:250], g["out_w"][0]) < tol
+
+
+@pytest.mark.parametrize("variant,name", [("tc", "n1_b3"), ("tc", "n2_b5"), ("pair", "n1_b3"), ("pair", "n2_b5")])
+def test_emulated_tcgen05_kernels_match_oracle(emu, golden_cases, golden_weights, variant, name):
+    C = golden_cases
+    N, B, wd = (int(v) for v in C[f"{name}/meta"])
+    lstm, fnn = state_dicts(golden_weights, str(C[f"{name}/ctl"]))
+    X, Z = C[f"{name}/X"], C[f"{name}/Z"]
+    u0 = np.ascontiguousarray(C[f"{name}/f32/u0"])
+    o = _run_v(emu, variant, _pack_v(emu, lstm, fnn, variant), X, u0, Z, N, 20.0)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
+    _check_v(o, out, g)
+
+
+def test_emulated_pair_kernel_two_tiles_and_odd_tail(emu, golden_cases, golden_weights):
+    """B = 300 on one emulated CTA: a pass with two tiles in flight, then a pass with a single (ragged) tile."""
+    C, name, rep = golden_cases, "n2_b5", 60
+    N = int(C[f"{name}/meta"][0])
+    lstm, fnn = state_dicts(golden_weights, str(C[f"{name}/ctl"]))
+    rng = np.random.default_rng(0)
+    X = np.ascontiguousarray(np.tile(C[f"{name}/X"], (rep, 1)), dtype=np.float32)
+    Z = np.tile(C[f"{name}/Z"], (rep, 1, 1))
+    Z = np.ascontiguousarray(Z * (1 + 0.05 * rng.standard_normal(Z.shape)), dtype=np.float32)
+    u0 = np.ascontiguousarray(np.tile(C[f"{name}/f32/u0"], rep))
+    o = _run_v(emu, "pair", _pack_v(emu, lstm, fnn, "pair"), X, u0, Z, N, 20.0, grid=1)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
+    _check_v(o, out, g)
