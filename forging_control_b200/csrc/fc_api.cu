@@ -228,9 +228,8 @@ struct DevCtxTC : DevCtx {
     const uint32_t addr = bar0 + bar * 8, parity = phase & 1u;
     uint32_t done = 0;
     while (!done) {
-      // the suspend-time hint lets the hardware park the warp until the phase completes instead of spinning
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                   : "=r"(done) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
@@ -247,6 +246,7 @@ struct DevCtxTC : DevCtx {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  static __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
   static __device__ __forceinline__ void sts2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
   // D[128 x n] (+)= A[128 x 16*ksteps] * B[n x 16*ksteps]^T with BOTH operands in shared memory:
   // A image = [k/8][128][8 halves], B image = [k/8][n_img][8 halves]

@@ -12,8 +12,10 @@
 // Hand-shakes are per tile and by mbarrier, never CTA-wide: full[tile] (tcgen05.commit: accumulator complete, operand
 // free) and ready[tile] (512 arrivals: accumulator consumed, next operand written).  See fc_pair_layout.h for where
 // the operands live (TMEM / shared memory budget) and DESIGN.md section 2.3.
-// Warps 0..3 are service warps (thread 0 = the MMA issuer; per-trajectory scalar work of both tiles), warps 4..15 do
-// the cell updates: third th = w/4 - 1 owns the hidden units [16 th, 16 th + 16) (18 for th = 2).
+// Thread 0 is the MMA issuer and does nothing else (tcgen05.mma blocks its issuer for about the duration of the
+// chain).  Warps 4..15 do the cell updates: third th = w/4 - 1 owns the hidden units [16 th, 16 th + 16) (18 for
+// th = 2).  The per-trajectory scalar work of a row (roll-out rows, layer-0 features, read-out, cost terms,
+// controller) belongs to the otherwise idle warps 1..3 for their TMEM quadrants and to warp 4 for quadrant 0.
 #pragma once
 #include "fc_pair_layout.h"
 
@@ -26,7 +28,9 @@ struct MpcPair {
   const MpcParams& p;
   float* sm;
   int tid, warp, lane, row, th, nown, u_first, uw;
-  bool service;          // warps 0..3
+  bool service;          // warps 0..3: thread 0 issues the MMAs, the rest only joins the CTA-wide barriers
+  bool owner;            // third 0 of the cell-update warps: also collects the row-feature gradients of its row
+  bool scalar;           // does the per-trajectory scalar work of its row: warps 1..3, and warp 4 for the rows of warp 0
   bool last;             // third 2: 18 units (else 16)
   float* wbase;          // workspace of tile 0 of this CTA; tile 1 follows at +tstride
   size_t tstride;
@@ -54,6 +58,8 @@ struct MpcPair {
     nown = units_of(th);
     u_first = first_unit(th);
     last = th == 2;
+    owner = !service && th == 0;
+    scalar = (service && warp != 0) || warp == 4;
     uw = service ? 0 : warp - 4;                             // index among the cell-update warps
     tstride = work_layout_p(p.N, p.with_grad).total;
     wbase = p.work + (size_t)ctx.bid() * p.work_stride;
@@ -166,6 +172,7 @@ struct MpcPair {
   }
   // the owned units' values v[0..nown) (scaled here) as fp16 hi/lo pieces of 8 halves (third 2: the third piece
   // holds units 48,49 and the zero padding up to slot 56)
+  // (no saturation needed: the values are hidden states, |h| < 1, times kScaleA = 2^10)
   FC_HD_CTX void split_units(const float* v, float scale, F4* hi4, F4* lo4) const {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -173,8 +180,8 @@ struct MpcPair {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j = ch * 8 + 2 * i;
-        const float x0 = j < kMaxOwn ? fminf(fmaxf(v[j < kMaxOwn ? j : 0] * scale, -kHalfMax), kHalfMax) : 0.f;
-        const float x1 = j + 1 < kMaxOwn ? fminf(fmaxf(v[j + 1 < kMaxOwn ? j + 1 : 0] * scale, -kHalfMax), kHalfMax) : 0.f;
+        const float x0 = j < kMaxOwn ? v[j < kMaxOwn ? j : 0] * scale : 0.f;
+        const float x1 = j + 1 < kMaxOwn ? v[j + 1 < kMaxOwn ? j + 1 : 0] * scale : 0.f;
         Ctx::split_h2(x0, x1, hi[i], lo[i]);
       }
       hi4[ch] = F4{hi[0], hi[1], hi[2], hi[3]};
@@ -280,7 +287,7 @@ struct MpcPair {
   }
 
   // ---------------------------------------------------------------------------------------------
-  // tile set-up (service thread of each trajectory)
+  // tile set-up (scalar-work thread of each trajectory)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void load_tile(int X) {
     const int b = (tile0 + X) * kTileP + row;
@@ -359,7 +366,7 @@ struct MpcPair {
     }
   }
 
-  // layer 0: the 5 row features of step t (service thread of the row): k = 0..7, 3 zero
+  // layer 0: the 5 row features of step t (scalar-work thread of the row): k = 0..7, 3 zero
   FC_HD_CTX void load_features(int X, int m, int t, float* xin) {
     const float* rp = w_rows(X) + (size_t)(m + t) * kFeat * kTileP + row;
 #pragma unroll
@@ -382,20 +389,25 @@ struct MpcPair {
     // operand of step 0: zero recurrent block, input of step 0 (the previous MMA on this tile has been waited for)
     const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
     lap(18);
-    if (service) {
+    if (!service) {
+      st_units_zero(img_hi, img_lo, l == 0 ? kRec0 : kRec);
+      if (l > 0) {
+        copy_input(X, 0);
+        Ctx::template cp_wait<0>();
+      } else if (scalar) {
+        float xin[kFeat];
+        load_features(X, m, 0, xin);
+        store_features(X, xin);
+      }
+      arrive_ready(X);
+    } else if (scalar) {
       if (l == 0) {
         float xin[kFeat];
         load_features(X, m, 0, xin);
         store_features(X, xin);
       }
-    } else {
-      st_units_zero(img_hi, img_lo, l == 0 ? kRec0 : kRec);
-      if (l > 0) {
-        copy_input(X, 0);
-        Ctx::template cp_wait<0>();
-      }
+      arrive_ready(X);
     }
-    arrive_ready(X);
     if (tid == 0) {
       wait_ready(X);
       if (X == 0) wait_weights();                            // operand image of this layer landed
@@ -404,38 +416,43 @@ struct MpcPair {
     lap(14);
   }
 
-  FC_HD_CTX void fwd_item_service(int X, int l, int m, int t, bool more_after) {
-    float xin[kFeat];
-    if (l == 0 && t + 1 < kLook) load_features(X, m, t + 1, xin);
+  // thread 0: one step of the issue loop
+  FC_HD_CTX void fwd_item_issuer(int X, int l, int m, int t, bool more_after) {
     lap(23);
-    wait_full(X);                                            // accumulator complete; operand and (last tile) image free
+    wait_full(X);                                            // MMA(X, l, t) complete (keeps the phase count; no stall)
     lap(1);
-    if (t == kLook - 1 && X == ntl - 1 && tid == 0) {        // stream the next weight image under the cell updates
+    if (t == kLook - 1 && X == ntl - 1) {                    // stream the next weight image under the cell updates
       if (l + 1 < kLayers) request_weights(false, l + 1);
       else if (m + 1 < p.N) request_weights(false, 0);
       else if (p.with_grad) request_weights(true, kLayers - 1);
       else if (more_after) request_weights(false, 0);
     }
     if (t + 1 < kLook) {
+      wait_ready(X);
+      lap(4);
+      issue_fwd(X, l, kf_of(l) / 16);
+      lap(5);
+    }
+  }
+
+  // warps 1..3: layer-0 features of their rows, in step with the cell-update warps
+  FC_HD_CTX void fwd_item_scalar(int X, int l, int m, int t) {
+    float xin[kFeat];
+    if (l == 0 && t + 1 < kLook) load_features(X, m, t + 1, xin);
+    wait_full(X);
+    if (t + 1 < kLook) {
       if (l == 0) store_features(X, xin);
-      lap(2);
       arrive_ready(X);
-      lap(3);
-      if (tid == 0) {
-        wait_ready(X);
-        lap(4);
-        issue_fwd(X, l, kf_of(l) / 16);
-        lap(5);
-      }
     }
   }
 
   FC_HD_CTX void fwd_item(int X, int l, int m, int t) {
     const int tmin = t_min_of(m);
-    float h[kMaxOwn];
+    float h[kMaxOwn], xin[kFeat];
     lap(16);
     swap_cells();
     lap(11);
+    if (l == 0 && scalar && t + 1 < kLook) load_features(X, m, t + 1, xin);
     float* rec_out = nullptr;
     if (p.with_grad && t >= tmin)
       rec_out = w_rec(X) + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsP;
@@ -446,6 +463,7 @@ struct MpcPair {
     wait_full(X);                                            // accumulator complete; operand free
     lap(1);
     if (l > 0 && t + 1 < kLook) copy_input(X, t + 1);        // input block of step t+1: lands during the cell update
+    if (l == 0 && scalar && t + 1 < kLook) store_features(X, xin);
     fwd_pointwise(X, t == 0, corr, h, rec_out);
     if (l + 1 < kLayers || t + 1 < kLook) {
       F4 hi4[3], lo4[3];
@@ -459,7 +477,7 @@ struct MpcPair {
       arrive_ready(X);
       lap(3);
     } else if (l == kLayers - 1) {
-      // read-out partial sums over the owned units (Functions.py:377), handed to the service thread of the row
+      // read-out partial sums over the owned units (Functions.py:377), handed to the scalar-work thread of the row
       // through spare TMEM columns of the own lane
       const float* fw = sm + kSmSmallP;
       float xq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -480,19 +498,20 @@ struct MpcPair {
       for (int X = 0; X < ntl; ++X) fwd_prologue(X, l, m);
       for (int t = 0; t < kLook; ++t)
         for (int X = 0; X < ntl; ++X) {
-          if (service) fwd_item_service(X, l, m, t, more_after);
-          else fwd_item(X, l, m, t);
+          if (tid == 0) fwd_item_issuer(X, l, m, t, more_after);
+          else if (!service) fwd_item(X, l, m, t);
+          else if (scalar) fwd_item_scalar(X, l, m, t);
         }
     }
     lap(19);
     ctx.tc_sync();                                           // read-out partial sums visible
-    if (service)
+    if (scalar)
       for (int X = 0; X < ntl; ++X) fwd_glue(X, m);
     lap(15);
   }
 
   // ---------------------------------------------------------------------------------------------
-  // after window m (service thread of each trajectory): read-out, cost terms, next command
+  // after window m (scalar-work thread of each trajectory): read-out, cost terms, next command
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void fwd_glue(int X, int m) {
     const float* sw = sm + kSmSmallP;
@@ -536,7 +555,7 @@ struct MpcPair {
   }
 
   // ---------------------------------------------------------------------------------------------
-  // before the reverse sweep of window m (service thread per trajectory, then 200 accumulation threads)
+  // before the reverse sweep of window m (scalar-work thread per trajectory, then 200 accumulation threads)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void bwd_glue_tile(int X, int m) {
     const int k = m + 1;
@@ -598,12 +617,12 @@ struct MpcPair {
     const float* iw = sw + (kINPW - kFCW);
     const float* ib = sw + (kINPB - kFCW);
     const float* ow = sw + (kOUTW - kFCW);
-    if (service)
+    if (scalar)
       for (int X = 0; X < ntl; ++X) bwd_glue_tile(X, m);
     ctx.sync();
-    // controller weight gradients, unit-parallel: the 200 threads behind the service warps
-    if (has_u && tid >= 128 && tid < 128 + 4 * kFnnHid) {
-      const int u = (tid - 128) % kFnnHid, part = (tid - 128) / kFnnHid;
+    // controller weight gradients, unit-parallel: warps 0..6 (the idle warps first)
+    if (has_u && tid < 4 * kFnnHid) {
+      const int u = tid % kFnnHid, part = tid / kFnnHid;
       double a_ow = 0.0, a_b = 0.0, a_w0 = 0.0, a_w1 = 0.0, a_w2 = 0.0;   // batch sums cancel heavily: fp64
       const float w0 = iw[u * 3 + 0], w1 = iw[u * 3 + 1], w2 = iw[u * 3 + 2], bb = ib[u], owu = ow[u];
       for (int X = 0; X < ntl; ++X)
@@ -720,7 +739,7 @@ struct MpcPair {
       for (int j = 0; j < kMaxOwn; ++j) { d[j] *= unscale_b; dh[j] = fmaf(d[j], corr_b, d[j]); }
     }
   }
-  // layer 0: gradient of the row features of step t (service thread of the row)
+  // layer 0: gradient of the row features of step t (owner thread of the row)
   FC_HD_CTX void bwd_collect_features(int X, int m, int t) {
     const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
     const float unscale_b = p.g_unscale / kScaleW;
@@ -732,28 +751,29 @@ struct MpcPair {
 #pragma unroll
       for (int f = 0; f < kFeat; ++f) {
         const float v = df[f] * unscale_b;
-        gp[f * kTileP] = Ctx::ldcg(gp + f * kTileP) + fmaf(v, corr_b, v);
+        Ctx::red_add(gp + f * kTileP, fmaf(v, corr_b, v));   // same thread, one add per step: deterministic order
       }
     }
   }
 
-  FC_HD_CTX void bwd_item_service(int X, int l, int m, int t) {
+  // thread 0: one step of the issue loop
+  FC_HD_CTX void bwd_item_issuer(int X, int l, int t) {
     if (t < kLook - 1) {
       lap(23);
-      wait_full(X);                                        // MMA(X, l, t+1) complete
+      wait_full(X);                                        // MMA(X, l, t+1) complete (keeps the phase count)
       lap(6);
-      if (l == 0) bwd_collect_features(X, m, t + 1);
     }
-    lap(7);
+    wait_ready(X);
+    if (X == 0 && t == kLook - 1) wait_weights();          // backward image of this layer landed
+    lap(9);
+    issue_bwd(X, l);
+    lap(10);
+  }
+
+  // warps 1..3: stay in step (phase counts of the hand-shakes)
+  FC_HD_CTX void bwd_item_scalar(int X, int t) {
+    if (t < kLook - 1) wait_full(X);
     arrive_ready(X);
-    lap(8);
-    if (tid == 0) {
-      wait_ready(X);
-      if (X == 0 && t == kLook - 1) wait_weights();        // backward image of this layer landed
-      lap(9);
-      issue_bwd(X, l);
-      lap(10);
-    }
   }
 
   FC_HD_CTX void bwd_item(int X, int l, int m, int t) {
@@ -781,6 +801,7 @@ struct MpcPair {
         wait_full(X);                                      // MMA(X, l, t+1) complete
         lap(6);
         bwd_collect(X, l, t + 1, dh);
+        if (l == 0 && owner) bwd_collect_features(X, m, t + 1);
 #pragma unroll
         for (int j = 0; j < kMaxOwn; ++j) dh[j] += extra[j];
       }
@@ -810,6 +831,7 @@ struct MpcPair {
   // after the last step of a layer: collect the result of MMA(X, l, tmin)
   FC_HD_CTX void bwd_tail(int X, int l, int m, bool more_after) {
     const int tmin = t_min_of(m);
+    if (service && tid != 0 && !scalar) return;
     lap(22);
     wait_full(X);
     lap(6);
@@ -818,11 +840,13 @@ struct MpcPair {
       else if (m > 0) request_weights(true, kLayers - 1);
       else if (more_after) request_weights(false, 0);
     }
-    if (service) {
-      if (l == 0) bwd_collect_features(X, m, tmin);
-    } else if (l > 0) {
-      float dh[kMaxOwn];
-      bwd_collect(X, l, tmin, dh);                         // d(h) before the first kept step is not needed
+    if (!service) {
+      if (l > 0) {
+        float dh[kMaxOwn];
+        bwd_collect(X, l, tmin, dh);                       // d(h) before the first kept step is not needed
+      } else if (owner) {
+        bwd_collect_features(X, m, tmin);
+      }
     }
     lap(14);
   }
@@ -836,8 +860,9 @@ struct MpcPair {
     for (int l = kLayers - 1; l >= 0; --l) {
       for (int t = kLook - 1; t >= tmin; --t)
         for (int X = 0; X < ntl; ++X) {
-          if (service) bwd_item_service(X, l, m, t);
-          else bwd_item(X, l, m, t);
+          if (tid == 0) bwd_item_issuer(X, l, t);
+          else if (!service) bwd_item(X, l, m, t);
+          else if (scalar) bwd_item_scalar(X, t);
         }
       for (int X = 0; X < ntl; ++X) bwd_tail(X, l, m, more_after);
     }
@@ -845,10 +870,10 @@ struct MpcPair {
   }
 
   // ---------------------------------------------------------------------------------------------
-  // per-pass epilogues (service threads)
+  // per-pass epilogues (scalar-work threads)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void store_costs() {
-    if (service) {
+    if (scalar) {
       for (int X = 0; X < kTiles; ++X) {
         float mine = 0.f;
         int b = (tile0 + X) * kTileP + row;
@@ -873,7 +898,7 @@ struct MpcPair {
   }
 
   FC_HD_CTX void store_du0() {
-    if (service)
+    if (scalar)
       for (int X = 0; X < ntl; ++X) {
         int b = (tile0 + X) * kTileP + row;
         if (b < p.B) {
@@ -893,7 +918,7 @@ struct MpcPair {
 
   // zero padding of the dG operands (k = 200..207): TMEM columns 100..103 of tile 0, the last 16-byte piece of tile 1
   FC_HD_CTX void zero_dg_padding() {
-    if (service) {
+    if (scalar) {
       float z[4] = {0.f, 0.f, 0.f, 0.f};
       ctx.template tmem_st<4>(kColGhi + 100, z);
       ctx.template tmem_st<4>(kColGlo + 100, z);
@@ -913,8 +938,8 @@ struct MpcPair {
     tlast = Ctx::clock();
 #endif
     if (tid == 0) {
-      ctx.bar_init(kBarReady, kWarpsP);
-      ctx.bar_init(kBarReady + 1, kWarpsP);
+      ctx.bar_init(kBarReady, kUpdWarps + 3);                // cell-update warps + warps 1..3
+      ctx.bar_init(kBarReady + 1, kUpdWarps + 3);
     }
     for (int i = tid; i < kSmallFloats; i += kThreadsP) sm[kSmSmallP + i] = p.wpack[kSmallOff + i];
     for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsP) reinterpret_cast<double*>(sm + kSmPgP)[i] = 0.0;
@@ -927,13 +952,13 @@ struct MpcPair {
       const bool more = pp + ctx.nblk() < npairs;
       tile0 = pp * kTiles;
       ntl = p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles;
-      if (service)
+      if (scalar)
         for (int X = 0; X < ntl; ++X) load_tile(X);
       ctx.sync();
       for (int m = 0; m < p.N; ++m) fwd_window(m, more);
       store_costs();
       if (p.with_grad) {
-        if (service)
+        if (scalar)
           for (int X = 0; X < ntl; ++X) {
             float* grow = w_grow(X);
             for (int k = 0; k < p.N; ++k)
