@@ -189,13 +189,15 @@ struct DevCtxTC : DevCtx {
     TmemIO<N>::st(lane_addr + col, r);
   }
   __device__ __forceinline__ void tmem_st_wait() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-  // fp16 hi/lo split of two pre-scaled values, packed (first value in the low half) as 32-bit TMEM words
+  // fp16 hi/lo split of two pre-scaled values, packed (first value in the low half) as 32-bit operand words.
+  // The conversions saturate to the largest finite fp16 (F2FP.SATFINITE): no infinities reach the tensor core.
   static __device__ __forceinline__ void split_h2(float x0, float x1, float& hi, float& lo) {
-    const __half2 h = __floats2half2_rn(x0, x1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    hi = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
-    lo = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
+    uint32_t h, l;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    hi = __uint_as_float(h);
+    lo = __uint_as_float(l);
   }
   // D[128 x n] (+)= A[128 x 16*ksteps] * B[n x 16*ksteps]^T, one hi/lo term (kind::f16, fp32 accumulate);
   // A: 8 TMEM columns per k-step (two fp16 per column); B image = [k/8][n_img][8 halves]

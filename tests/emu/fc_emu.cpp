@@ -81,7 +81,7 @@ struct EmuCtxTC : EmuCtx {
   void tmem_ld_wait() const {}
   template <int N> void tmem_st(int col, const float* v) const { for (int i = 0; i < N; ++i) tb->tmem[row() * 512 + col + i] = v[i]; }
   void tmem_st_wait() const {}
-  static uint16_t h_bits(float x) { _Float16 h = (_Float16)x; uint16_t u; std::memcpy(&u, &h, 2); return u; }
+  static uint16_t h_bits(float x) { x = x > 65504.f ? 65504.f : (x < -65504.f ? -65504.f : x); _Float16 h = (_Float16)x; uint16_t u; std::memcpy(&u, &h, 2); return u; }
   static float h_val(uint16_t u) { _Float16 h; std::memcpy(&h, &u, 2); return (float)h; }
   static void split_h2(float x0, float x1, float& hi, float& lo) {
     uint16_t h0 = h_bits(x0), h1 = h_bits(x1);
