@@ -271,6 +271,18 @@ struct DevCtxTC : DevCtx {
       adesc += astep; bdesc += bstep;
     }
   }
+  // wait of a warp that is off the critical path: back off between polls (frees issue slots, saves power)
+  __device__ __forceinline__ void bar_wait_relaxed(int bar, unsigned phase) const {
+    const uint32_t addr = bar0 + bar * 8, parity = phase & 1u;
+    uint32_t done = 0;
+    while (true) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+      if (done) break;
+      __nanosleep(200);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   // one thread: bulk (TMA) copy global -> shared, completion on an mbarrier
   __device__ __forceinline__ void bulk_load(float* dst, const float* src, int nfloats, int bar) const {
     const uint32_t baddr = bar0 + bar * 8;

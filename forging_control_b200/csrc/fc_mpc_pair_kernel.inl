@@ -132,7 +132,8 @@ struct MpcPair {
   // hand-shakes
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void wait_full(int X) {
-    ctx.bar_wait(kBarFull + X, X ? phF1 : phF0);
+    if (service && tid != 0) ctx.bar_wait_relaxed(kBarFull + X, X ? phF1 : phF0);   // warps 1..3: off the critical path
+    else ctx.bar_wait(kBarFull + X, X ? phF1 : phF0);
     if (X) phF1 += 1; else phF0 += 1;
   }
   FC_HD_CTX void swap_cells() {                            // cell-update warps only
@@ -645,6 +646,7 @@ struct MpcPair {
 
   // ---------------------------------------------------------------------------------------------
   // backward cell gradient of NU unit slots: record(t) -> factors, dh -> d(cell), d(gates)
+  //   (saving tanh(c) in the record instead of recomputing it was measured 12 % slower: +20 % record traffic)
   //   A = o(1-tanh^2 c), Ko = tanh(c) o(1-o), Ki = g i(1-i), Kf = c_prev f(1-f), Kg = i(1-g^2)
   //   dct = dc + dh A; dG = (dct Ki, dct Kf, dct Kg, dh Ko); dc = dct f
   // ---------------------------------------------------------------------------------------------

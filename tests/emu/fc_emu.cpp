@@ -114,6 +114,7 @@ struct EmuCtxTC : EmuCtx {
   void bar_wait(int bar, unsigned phase) const {
     while (tb->bars[bar].load() / tb->counts[bar] <= phase) std::this_thread::yield();
   }
+  void bar_wait_relaxed(int bar, unsigned phase) const { bar_wait(bar, phase); }
   // pair kernel
   void bar_init(int bar, int count) const { tb->counts[bar] = (unsigned)count; tb->bars[bar].store(0); }
   void bar_init_fence() const {}
