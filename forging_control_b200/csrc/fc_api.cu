@@ -279,7 +279,7 @@ struct DevCtxTC : DevCtx {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                    : "=r"(done) : "r"(addr), "r"(parity) : "memory");
       if (done) break;
-      __nanosleep(200);
+      __nanosleep(1000);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
