@@ -330,9 +330,10 @@ def run_ours(args):
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kind::f16 runs at the bf16 rate)"
                                     if peaks else "fallback 1.4 PFLOP/s dense bf16"),
                     "note": "gate contraction on tcgen05 with fp16 hi/lo split operands (three kind::f16 MMAs per fp32-accurate "
-                            "product): the tensor pipe executes ~3.3x the algorithmic FLOPs (split terms + padding) and the "
-                            "cell update (MUFU-bound) alternates with it; ncu tensor-pipe-active and the FP32-FFMA-equivalent "
-                            "fraction are in profiles/",
+                            "product): the tensor pipe executes ~3.3x the algorithmic FLOPs (split terms + padding); the pair "
+                            "kernel runs it under the cell update of a second tile, and that cell update (FP32/MUFU, "
+                            "instruction-issue bound, ncu issue-active 57 %) is what limits the kernel, with the activation-record "
+                            "traffic at about half of the HBM peak (hbm.traffic_frac); ncu summaries in profiles/",
                     "fp32_equivalent": fp32}
         else:
             roof = dict(fp32, bound="fp32")
@@ -343,6 +344,8 @@ def run_ours(args):
                      "traffic": traffic_per_traj * B if N == 10 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full capture of the same kernel (B=37888 pair / 71040 others) scaled by B (profiles/r01_*)",
                      "hbm": {"algorithmic_gbs": ALG_BYTES_PER_TRAJ * B / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                             "traffic_gbs": (traffic_per_traj * B / (kern_ms * 1e-3) / 1e9) if N == 10 else None,
+                             "traffic_frac": (traffic_per_traj * B / (kern_ms * 1e-3) / 1e9 / hbm_peak) if N == 10 else None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}})
         line = {
             "metric": "mpc_loss_fwd_bwd_trajectory_steps_per_s", "value": value, "unit": "trajectory-steps/s",

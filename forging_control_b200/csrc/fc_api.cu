@@ -435,17 +435,18 @@ struct MpcPlan {
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
-// Automatic choice (measured on B200, profiles/): one 128-trajectory tile or less -> the one-tile tcgen05 kernel
-// (B=15: 2.9 ms per step against 7.5 ms for the FFMA kernel; one M=128 tile is the smallest MMA either way);
-// more -> the pair kernel, which keeps two tiles per CTA in flight (78 M against 74 M trajectory-steps/s at
-// B=524288; the FFMA kernel reaches 23 M).  All three stay selectable (fc_mpc_select_kernel / FC_MPC_KERNEL).
+// Automatic choice (measured on B200, profiles/r01_bench_configs_three_kernels.jsonl): while every 128-trajectory tile
+// can have an SM of its own (B <= 128 * #SMs) the one-tile tcgen05 kernel is fastest (B=15: 2.2 ms per step against
+// 7.6 ms for the FFMA kernel; B=4096: 0.94 ms against 1.6 ms for the pair kernel, which would leave SMs idle); beyond
+// that the pair kernel, which keeps two tiles per CTA in flight, wins (B=524288: 80 M against 73 M trajectory-steps/s;
+// the FFMA kernel reaches 23 M).  All three stay selectable (fc_mpc_select_kernel / FC_MPC_KERNEL).
 static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
   pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
-  if (mode == 0 && B > tc::kTileTC) pl->kind = 2;
+  if (mode == 0 && (B + tc::kTileTC - 1) / tc::kTileTC > sms) pl->kind = 2;
   const int tile = pl->kind ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
   const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
