@@ -26,6 +26,8 @@ import random
 import weakref
 from time import time
 
+import ctypes
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -123,11 +125,21 @@ def _check_models(simulator: nn.Module, controller: nn.Module):
         raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports the ReLU controller only")
 
 
+_NO_CONTROLLER = {}
+
+
 def _weight_tensors(simulator, controller):
     l = simulator.lstm
+    if controller is None:      # surrogate-only calls (LSTM shadow roll-out): zero controller block
+        dev = l.weight_ih_l0.device
+        z = _NO_CONTROLLER.get(dev)
+        if z is None:
+            z = _NO_CONTROLLER[dev] = [torch.zeros(50, 3, device=dev), torch.zeros(50, device=dev), torch.zeros(1, 50, device=dev)]
+        ctl = z
+    else:
+        ctl = [controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight]
     return [l.weight_ih_l0, l.weight_hh_l0, l.weight_ih_l1, l.weight_hh_l1, l.weight_ih_l2, l.weight_hh_l2,
-            simulator.fc.weight, simulator.fc.bias,
-            controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight]
+            simulator.fc.weight, simulator.fc.bias] + ctl
 
 
 def pack_weights(simulator: nn.Module, controller: nn.Module) -> torch.Tensor:
@@ -373,30 +385,49 @@ class NeuralNetwork:
 
     @staticmethod
     def _lstm_shadow(simulator_LSTM, model_scalers, x0, meas, u, lookback):
-        """Diagnostic LSTM prediction logged next to the plant (Functions.py:1196-1231): the window at
+        """Diagnostic LSTM prediction logged next to the plant (Functions.py:969-1011, :1196-1231): the window at
         step t holds the shadow's own previous predictions and the applied commands; it is never fed
-        back to the controller, so it runs after the roll-out, batched over trajectories."""
+        back to the controller, so it runs after the roll-out, batched over trajectories, in ONE launch of the
+        forward-only windowed-LSTM kernel (``fc_lstm_shadow_rollout``)."""
         if simulator_LSTM is None or model_scalers is None:
             return {}
+        if lookback != 10:
+            raise NotImplementedError("LSTM shadow: the kernel is specialised for the reference's look-back of 10")
         B, T1, _ = meas.shape
         T = T1 - 1
         s_in = np.asarray(model_scalers["input"].scale_, dtype=np.float64)
         s_out = np.asarray(model_scalers["output"].scale_, dtype=np.float64)
-        dev = next(simulator_LSTM.parameters()).device
         out = np.zeros((B, T + 1, 4))
         out[:, 0] = x0[:, 1:5]
-        x_next = x0[:, 1:5].copy()
-        window = None
-        simulator_LSTM.eval()
-        with torch.no_grad():
-            for t in range(T):
-                row = np.concatenate((x_next, u[:, t:t + 1]), axis=1) / s_in
-                window = np.repeat(row[:, None], lookback, axis=1) if t == 0 else \
-                    np.concatenate((window[:, 1:lookback], row[:, None]), axis=1)
-                y = simulator_LSTM(torch.as_tensor(window).float().to(dev), dev).double().cpu().numpy()
-                x_next = y * s_out
-                out[:, t + 1] = x_next
+        if T > 0:
+            row0 = np.concatenate((x0[:, 1:5], u[:, 0:1]), axis=1) / s_in
+            y = lstm_shadow_native(simulator_LSTM, row0, np.asarray(u, dtype=np.float64) / s_in[4], s_out / s_in[:4])
+            out[:, 1:] = y.astype(np.float64) * s_out
         return {"y_dot": out[:, :, 0], "p1": out[:, :, 1], "p2": out[:, :, 2], "z": out[:, :, 3]}
+
+
+def lstm_shadow_native(simulator_LSTM, row0, u_scaled, ratio):
+    """``fc_lstm_shadow_rollout``: row0 [B,5], u_scaled [B,T] (scaled domain, numpy or tensors), ratio [4] ->
+    y [B,T,4] float32 numpy (scaled surrogate outputs).  The surrogate must live on a CUDA device."""
+    dev = next(simulator_LSTM.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("forging_control_b200: the LSTM shadow roll-out needs the surrogate on a CUDA device (no CPU path)")
+    wpack = pack_weights(simulator_LSTM, None)
+    row0_d = torch.as_tensor(np.ascontiguousarray(row0), dtype=torch.float32).to(dev).contiguous()
+    u_d = torch.as_tensor(np.ascontiguousarray(u_scaled), dtype=torch.float32).to(dev).contiguous()
+    B, T = u_d.shape
+    y = torch.empty(B, T, 4, dtype=torch.float32, device=dev)
+    L = _native.lib()
+    r = (ctypes.c_float * 4)(*[float(v) for v in np.asarray(ratio).reshape(-1)[:4]])
+    with torch.cuda.device(dev):
+        nbytes = int(L.fc_lstm_shadow_workspace_bytes(B, T))
+        if nbytes == 0:
+            raise RuntimeError("fc_lstm_shadow_workspace_bytes failed: " + L.fc_last_error().decode())
+        work = _workspace(dev, nbytes)
+        rc = L.fc_lstm_shadow_rollout(_native.ptr(row0_d), _native.ptr(u_d), r, _native.ptr(wpack), B, T, _native.ptr(y),
+                                      _native.ptr(work), nbytes, _native.stream_ptr(dev))
+    _native.check(rc, "fc_lstm_shadow_rollout")
+    return y.cpu().numpy()
 
 
 # ----------------------------------------------------------------------------------------------

@@ -572,6 +572,55 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
   return FC_OK;
 }
 
+size_t fc_lstm_shadow_workspace_bytes(int B, int T) {
+  if (B <= 0 || T <= 0) return 0;
+  int sms = 0;
+  if (sm_count(&sms)) return 0;
+  const int tiles = (B + pr::kTileP - 1) / pr::kTileP, pairs = (tiles + pr::kTiles - 1) / pr::kTiles;
+  const int grid = pairs < sms ? pairs : sms;
+  return (size_t)grid * kPartialStride * sizeof(double) + (size_t)grid * pr::kTiles * pr::work_layout_p(T, 0).total * sizeof(float);
+}
+
+int fc_lstm_shadow_rollout(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, float* y,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || T <= 0) return fail(FC_ERR_BAD_SHAPE, "fc_lstm_shadow_rollout: bad shape%s B=%lld T=%lld", "", B, T);
+  if (T > 65536) return fail(FC_ERR_UNSUPPORTED, "fc_lstm_shadow_rollout: roll-out%s T=%lld too long", "", T);
+  if (!row0 || !u || !ratio || !wpack || !y || !workspace) return fail(FC_ERR_NULL_POINTER, "fc_lstm_shadow_rollout: null pointer%s");
+  if (!aligned16(wpack) || !aligned16(workspace))
+    return fail(FC_ERR_MISALIGNED, "fc_lstm_shadow_rollout: wpack/workspace must be 16-byte aligned%s");
+  const size_t need = fc_lstm_shadow_workspace_bytes(B, T);
+  if (need == 0) return fail(FC_ERR_CUDA, "fc_lstm_shadow_rollout: no CUDA device%s");
+  if (workspace_bytes < need)
+    return fail(FC_ERR_WORKSPACE, "fc_lstm_shadow_rollout: workspace too small%s: have %lld need %lld bytes", "", (long long)workspace_bytes,
+                (long long)need);
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
+            "cudaFuncSetAttribute(smem, pair)");
+    attr_set = true;
+  }
+  const int tiles = (B + pr::kTileP - 1) / pr::kTileP, pairs = (tiles + pr::kTiles - 1) / pr::kTiles;
+  const int grid = pairs < sms ? pairs : sms;
+  MpcParams p;
+  memset(&p, 0, sizeof(p));
+  p.wpack = wpack + kPackFloats + tc::kPackFloatsTC;
+  p.partial = reinterpret_cast<double*>(workspace);
+  p.work = reinterpret_cast<float*>(p.partial + (size_t)grid * kPartialStride);
+  p.work_stride = pr::kTiles * pr::work_layout_p(T, 0).total;
+  p.B = B; p.N = T; p.with_grad = 0; p.num_tiles = tiles;
+  p.acc_comp = 1.3f;
+  p.g_scale = p.g_unscale = 1.0f;
+  p.shadow = 1; p.sh_row0 = row0; p.sh_u = u; p.sh_y = y;
+  // ratio is a HOST array of 4 floats
+  for (int q = 0; q < 4; ++q) p.sh_ratio[q] = ratio[q];
+  mpc_loss_pair_kernel<<<grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
+  FC_CUDA(cudaGetLastError(), "mpc_loss_pair_kernel (shadow) launch");
+  return FC_OK;
+}
+
 int fc_closed_loop_rk4(const float* x0, const float* ref, int n_ref, int steps_per_ref, int B, int T, float ts,
                        int substeps, const float* scale_in, const float* scale_out, const float* fnn_inp_w,
                        const float* fnn_inp_b, const float* fnn_out_w, float* meas, float* u, float* x_final,

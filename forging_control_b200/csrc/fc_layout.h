@@ -201,6 +201,13 @@ struct MpcParams {
   int debug_timing;      // CTA 0 prints a cycle breakdown (development aid)
   float g_scale;         // tcgen05 kernel: power-of-two scale of the gate gradients before the fp16 split
   float g_unscale;       // 1 / g_scale
+  // LSTM shadow roll-out (pair kernel, forward only; Functions.py:969-1011, 1196-1231): N windows, the command of
+  // every step is an input, no cost / controller / reverse sweep
+  int shadow;
+  const float* sh_row0;  // [B][5]  first window row (scaled), repeated 10 times
+  const float* sh_u;     // [B][N]  scaled commands; sh_u[b][m+1] closes the row appended after window m
+  float* sh_y;           // [B][N][4] surrogate outputs (scaled)
+  float sh_ratio[4];     // scale_out / scale_in: output -> next input row
 };
 
 }  // namespace fc

@@ -503,8 +503,43 @@ struct MpcPair {
     lap(19);
     ctx.tc_sync();                                           // read-out partial sums visible
     if (scalar)
-      for (int X = 0; X < ntl; ++X) fwd_glue(X, m);
+      for (int X = 0; X < ntl; ++X) {
+        if (p.shadow) shadow_glue(X, m);
+        else fwd_glue(X, m);
+      }
     lap(15);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // LSTM shadow roll-out (Functions.py:969-1011, 1196-1231): the window starts as ten copies of the first row; after
+  // window m the surrogate output is logged and [output * scale_out / scale_in, u_{m+1}] becomes the newest row
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX void load_tile_shadow(int X) {
+    const int b = (tile0 + X) * kTileP + row;
+    const bool ok = b < p.B;
+    float* rows = w_rows(X);
+#pragma unroll
+    for (int f = 0; f < kFeat; ++f) {
+      const float v = ok ? p.sh_row0[(size_t)b * kFeat + f] : 0.f;
+      for (int r = 0; r < kLook; ++r) rows[(size_t)(r * kFeat + f) * kTileP + row] = v;
+    }
+  }
+  FC_HD_CTX void shadow_glue(int X, int m) {
+    const float* sw = sm + kSmSmallP;
+    float fp[12];
+    ctx.template tmem_ld_nowait<8>(kColFcp + 12 * X, fp);
+    ctx.template tmem_ld_nowait<4>(kColFcp + 12 * X + 8, fp + 8);
+    ctx.tmem_ld_wait();
+    const int b = (tile0 + X) * kTileP + row;
+    const bool ok = b < p.B;
+    float* rnew = w_rows(X) + (size_t)(kLook + m) * kFeat * kTileP + row;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x = ((fp[q] + fp[4 + q]) + fp[8 + q]) + sw[(kFCB - kFCW) + q];
+      if (ok) p.sh_y[((size_t)b * p.N + m) * 4 + q] = x;
+      rnew[q * kTileP] = x * p.sh_ratio[q];
+    }
+    rnew[4 * kTileP] = (ok && m + 1 < p.N) ? p.sh_u[(size_t)b * p.N + m + 1] : 0.f;
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -951,10 +986,13 @@ struct MpcPair {
       tile0 = pp * kTiles;
       ntl = p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles;
       if (scalar)
-        for (int X = 0; X < ntl; ++X) load_tile(X);
+        for (int X = 0; X < ntl; ++X) {
+          if (p.shadow) load_tile_shadow(X);
+          else load_tile(X);
+        }
       ctx.sync();
       for (int m = 0; m < p.N; ++m) fwd_window(m, more);
-      store_costs();
+      if (!p.shadow) store_costs();
       if (p.with_grad) {
         if (scalar)
           for (int X = 0; X < ntl; ++X) {

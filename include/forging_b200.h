@@ -68,6 +68,16 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
                 float* error, float* pred, float* du0, float* gl, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* LSTM shadow roll-out of the closed loop (replaces the per-step `simulator_make_step` loop of
+ * NeuralNetwork.loop, UL/Functions.py:969-1011 and :1196-1231): T windowed-LSTM inferences per trajectory, batched
+ * over B trajectories, forward only.  The window starts as ten copies of row0[b] (scaled: x/scale_in, u_0/scale_in);
+ * after window m the surrogate output y[b][m][0..3] (scaled) is logged and [y * ratio, u[b][m+1]] becomes the
+ * newest row, ratio[q] = scale_out[q] / scale_in[q] (HOST array of 4 floats).  row0 [B][5], u [B][T] (scaled
+ * commands; u[b][0] is not read), y [B][T][4] are device pointers.                                         */
+size_t fc_lstm_shadow_workspace_bytes(int B, int T);
+int fc_lstm_shadow_rollout(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T,
+                           float* y, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- closed-loop deployment: replaces the body of NeuralNetwork.loop (Functions.py:1157-1237)
  * = FeasibilityRecovery.NN_make_step (:1596-1604) + simulator.make_step on the plant of
  * template_model.py:10-161, integrated with the fixed-step RK4 of Ruge_Kuta (:1759-1775) ----------

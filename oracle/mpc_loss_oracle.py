@@ -131,6 +131,22 @@ def lstm_window_backward(w: dict, saved, gx: np.ndarray, t_min: int = 0) -> np.n
 # ----------------------------------------------------------------------------------------------
 # controller (FNNModel.forward, UL/Functions.py:261-289)
 # ----------------------------------------------------------------------------------------------
+def lstm_shadow_rollout(w: dict, row0: np.ndarray, u: np.ndarray, ratio: np.ndarray):
+    """LSTM shadow roll-out of the closed loop, restating ``NeuralNetwork.simulator_make_step``
+    (UL/Functions.py:969-1011) as driven by ``NeuralNetwork.loop`` (:1196-1231), in the scaled domain: the window
+    starts as ten copies of ``row0`` [B,5]; after window m the surrogate output y_m [B,4] is logged and
+    ``[y_m * ratio, u[:, m+1]]`` (ratio = scale_out / scale_in) becomes the newest row.  Returns y [B,T,4]."""
+    B, T = u.shape
+    window = np.repeat(row0[:, None, :], LOOKBACK, axis=1).astype(row0.dtype)
+    out = np.empty((B, T, 4), row0.dtype)
+    for m in range(T):
+        y = lstm_window_forward(w, window)
+        out[:, m] = y
+        nxt = np.concatenate((y * ratio[None, :], (u[:, m + 1:m + 2] if m + 1 < T else np.zeros((B, 1), row0.dtype))), axis=1)
+        window = np.concatenate((window[:, 1:], nxt[:, None, :]), axis=1)
+    return out
+
+
 def fnn_forward(w: dict, x: np.ndarray, width_dim: int = 1, keep: bool = False):
     pre = [x @ w["inp_w"].T + w["inp_b"]]
     act = [np.maximum(pre[0], 0)]

@@ -318,4 +318,36 @@ int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const 
   }
   return 0;
 }
+
+int fc_emu_lstm_shadow_pair(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, int grid,
+                            float* y /*[B][T][4]*/) {
+  fc::MpcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.wpack = wpack;
+  p.B = B; p.N = T; p.with_grad = 0;
+  p.acc_comp = 1.0f; p.g_scale = p.g_unscale = 1.0f;
+  p.shadow = 1; p.sh_row0 = row0; p.sh_u = u; p.sh_y = y;
+  for (int q = 0; q < 4; ++q) p.sh_ratio[q] = ratio[q];
+  p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;
+  const int npairs = (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles;
+  if (grid > npairs) grid = npairs;
+  p.work_stride = fc::pr::kTiles * fc::pr::work_layout_p(T, 0).total;
+  std::vector<float> work((size_t)grid * p.work_stride, 0.f);
+  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
+  p.work = work.data();
+  p.partial = partial.data();
+  for (int b = 0; b < grid; ++b) {
+    EmuBlockTC blk(b, grid, fc::pr::kSmFloatsP);
+    std::vector<std::thread> th;
+    th.reserve(fc::pr::kThreadsP);
+    for (int t = 0; t < fc::pr::kThreadsP; ++t)
+      th.emplace_back([&blk, &p, t]() {
+        EmuCtxTC ctx(&blk, t);
+        fc::pr::MpcPair<EmuCtxTC> k(ctx, p);
+        k.run();
+      });
+    for (auto& x : th) x.join();
+  }
+  return 0;
+}
 }  // extern "C"

@@ -153,3 +153,20 @@ def test_emulated_pair_kernel_two_tiles_and_odd_tail(emu, golden_cases, golden_w
     w = O.weights_from_state_dicts(lstm, fnn, np.float64)
     out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
     _check_v(o, out, g)
+
+
+def test_emulated_lstm_shadow_rollout_matches_oracle(emu, golden_weights):
+    """Forward-only shadow mode of the pair kernel (fc_lstm_shadow_rollout) against the oracle restatement of
+    simulator_make_step / loop (UL/Functions.py:969-1011, :1196-1231)."""
+    lstm, fnn = state_dicts(golden_weights, "c0")
+    wp = _pack_v(emu, lstm, fnn, "pair")
+    rng = np.random.default_rng(3)
+    B, T = 7, 4
+    row0 = np.ascontiguousarray(rng.uniform(-1, 1, (B, 5)), dtype=np.float32)
+    u = np.ascontiguousarray(rng.uniform(-1, 1, (B, T)), dtype=np.float32)
+    ratio = np.array([1.0, 0.9, 1.1, 1.0], np.float32)
+    y = np.zeros((B, T, 4), np.float32)
+    emu.fc_emu_lstm_shadow_pair(_p(row0), _p(u), _p(ratio), _p(wp), B, T, 1, _p(y))
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    ref = O.lstm_shadow_rollout(w, row0.astype(np.float64), u.astype(np.float64), ratio.astype(np.float64))
+    assert rel_max(y, ref) < 1e-5
