@@ -276,9 +276,11 @@ class NeuralNetwork:
 
     @staticmethod
     def train_model(data_loader, simulator, model, loss_function, optimizer, device, enable_noise=False):
-        """One epoch of controller training, Functions.py:594-676."""
+        """One epoch of controller training, Functions.py:594-676.  The running loss is accumulated on the device
+        (float64) and read back once per epoch instead of the reference's per-step ``loss.item()`` (:661): the
+        kernel launches of consecutive steps queue back to back."""
         model.train()
-        running = 0.0
+        running = None
         feats = {"loss": [], "command": [], "error": [], "prediction": []}
         for X, _, z in data_loader:
             X, z = X.to(device, non_blocking=True), z.to(device, non_blocking=True)
@@ -289,20 +291,21 @@ class NeuralNetwork:
                 feats[k].append(loss_features[k])
             loss.backward()
             optimizer.step()
-            running += loss.item()
+            running = loss.detach().double() if running is None else running + loss.detach().double()
         out = {k: torch.cat(v, dim=0) for k, v in feats.items()}
-        return running / len(data_loader), out
+        return (running.item() if running is not None else 0.0) / len(data_loader), out
 
     @staticmethod
     def validate_model(data_loader, model, loss_function, device):
         """Functions.py:679-717."""
         model.eval()
-        total = 0.0
+        total = None
         with torch.no_grad():
             for X, y, _ in data_loader:
                 X, y = X.to(device), y.to(device)
-                total += loss_function(model(X), y).item()
-        return total / len(data_loader)
+                v = loss_function(model(X), y).double()
+                total = v if total is None else total + v
+        return (total.item() if total is not None else 0.0) / len(data_loader)
 
     @staticmethod
     def train_loop(controller, simulator, train_loader, val_loader, loss_function, optimizer, n_epochs, device,
