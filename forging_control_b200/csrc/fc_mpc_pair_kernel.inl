@@ -224,26 +224,26 @@ struct MpcPair {
       if (ch < 2 || last) { Ctx::sts4(op_ptr(img_hi, k0 + ch * 8), z); Ctx::sts4(op_ptr(img_lo, k0 + ch * 8), z); }
   }
 
-  // hi/lo fp16 split of 2*NP pre-scaled values into NP consecutive TMEM operand columns of the own lane
+  // hi/lo fp16 split of 2*NP values (already in the scaled domain) into NP consecutive TMEM operand columns of the own lane
   template <int NP>
-  FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v, float scale) {
+  FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v) {
     float hi[NP], lo[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      Ctx::split_h2(v[2 * i] * scale, v[2 * i + 1] * scale, hi[i], lo[i]);   // saturating conversion
+      Ctx::split_h2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);   // saturating conversion
     }
     ctx.template tmem_st<NP>(col_hi, hi);
     ctx.template tmem_st<NP>(col_lo, lo);
   }
   // the same into 2*NP halves of the shared-memory dG image (tile 1), k0 multiple of 8, NP multiple of 4
   template <int NP>
-  FC_HD_CTX void st_pairs_smem(int k0, const float* v, float scale) {
+  FC_HD_CTX void st_pairs_smem(int k0, const float* v) {
 #pragma unroll
     for (int ch = 0; ch < NP / 4; ++ch) {
       float hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        Ctx::split_h2(v[ch * 8 + 2 * i] * scale, v[ch * 8 + 2 * i + 1] * scale, hi[i], lo[i]);
+        Ctx::split_h2(v[ch * 8 + 2 * i], v[ch * 8 + 2 * i + 1], hi[i], lo[i]);
       }
       Ctx::sts4(op_ptr(0, k0 + ch * 8), F4{hi[0], hi[1], hi[2], hi[3]});
       Ctx::sts4(op_ptr(kOpGLoHalves, k0 + ch * 8), F4{lo[0], lo[1], lo[2], lo[3]});
@@ -727,7 +727,7 @@ struct MpcPair {
       if (t == kLook - 1) {
         float gxv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + row];
+        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + row] * p.g_scale;   // into the scaled domain
 #pragma unroll
         for (int j = 0; j < kMaxOwn; ++j) {
           const int u = u_first + j < kHid ? u_first + j : kHid - 1;
@@ -748,7 +748,9 @@ struct MpcPair {
   // result of MMA(X, l, t): d(input) of step t -> the layer below, d(h_prev) -> dh   (cell-update warps)
   FC_HD_CTX void bwd_collect(int X, int l, int t, float* dh) {
     const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
-    const float unscale_b = p.g_unscale / kScaleW;         // exact power of two
+    // the whole reverse sweep of a window runs in the scaled domain (gradients x g_scale, an exact power of two):
+    // the gate gradients then need no multiplication before their fp16 split; only the weight scale is removed here
+    const float unscale_b = 1.0f / kScaleW;
     const int dcol = col_d_bwd(X);
     if (l > 0) {
       float d[36];
@@ -846,14 +848,14 @@ struct MpcPair {
       else if (last) rec_load<2>(rp, 20, rv[(gi + 1) & 1]);
       float dg[16];
       bwd_units<4>(gi * 4, rv[gi & 1], dh, dg);
-      if (X == 0) st_pairs<8>(kColGhi + 2 * u_first + gi * 8, kColGlo + 2 * u_first + gi * 8, dg, p.g_scale);
-      else st_pairs_smem<8>(4 * u_first + gi * 16, dg, p.g_scale);
+      if (X == 0) st_pairs<8>(kColGhi + 2 * u_first + gi * 8, kColGlo + 2 * u_first + gi * 8, dg);
+      else st_pairs_smem<8>(4 * u_first + gi * 16, dg);
     }
     if (last) {
       float dg[8];
       bwd_units<2>(16, rv[0], dh, dg);
-      if (X == 0) st_pairs<4>(kColGhi + 2 * u_first + 32, kColGlo + 2 * u_first + 32, dg, p.g_scale);
-      else st_pairs_smem<4>(4 * u_first + 64, dg, p.g_scale);
+      if (X == 0) st_pairs<4>(kColGhi + 2 * u_first + 32, kColGlo + 2 * u_first + 32, dg);
+      else st_pairs_smem<4>(4 * u_first + 64, dg);
     }
     if (X == 0) ctx.tmem_st_wait();
     lap(7);
