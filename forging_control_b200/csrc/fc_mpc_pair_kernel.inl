@@ -12,8 +12,8 @@
 // Hand-shakes are per tile and by mbarrier, never CTA-wide: full[tile] (tcgen05.commit: accumulator complete, operand
 // free) and ready[tile] (512 arrivals: accumulator consumed, next operand written).  See fc_pair_layout.h for where
 // the operands live (TMEM / shared memory budget) and DESIGN.md section 2.3.
-// Thread 0 is the MMA issuer and does nothing else (tcgen05.mma blocks its issuer for about the duration of the
-// chain).  Warps 4..15 do the cell updates: third th = w/4 - 1 owns the hidden units [16 th, 16 th + 16) (18 for
+// Warp 0 is the MMA issuer and does nothing else (tcgen05.mma blocks its issuer for about the duration of the
+// chain; all 32 lanes walk the issue loop together, lane 0 issues).  Warps 4..15 do the cell updates: third th = w/4 - 1 owns the hidden units [16 th, 16 th + 16) (18 for
 // th = 2).  The per-trajectory scalar work of a row (roll-out rows, layer-0 features, read-out, cost terms,
 // controller) belongs to the otherwise idle warps 1..3 for their TMEM quadrants and to warp 4 for quadrant 0.
 #pragma once
@@ -132,7 +132,7 @@ struct MpcPair {
   // hand-shakes
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void wait_full(int X) {
-    if (service && tid != 0) ctx.bar_wait_relaxed(kBarFull + X, X ? phF1 : phF0);   // warps 1..3: off the critical path
+    if (service && warp != 0) ctx.bar_wait_relaxed(kBarFull + X, X ? phF1 : phF0);  // warps 1..3: off the critical path
     else ctx.bar_wait(kBarFull + X, X ? phF1 : phF0);
     if (X) phF1 += 1; else phF0 += 1;
   }
@@ -156,11 +156,11 @@ struct MpcPair {
     ctx.warp_sync();
     if (lane == 0) ctx.bar_arrive(kBarReady + X);            // one arrival per warp
   }
-  FC_HD_CTX void wait_ready(int X) {                                                             // tid 0 only
+  FC_HD_CTX void wait_ready(int X) {                                                             // issuer warp
     ctx.bar_wait(kBarReady + X, X ? phR1 : phR0);
     if (X) phR1 += 1; else phR0 += 1;
   }
-  FC_HD_CTX void wait_weights() { ctx.bar_wait(kBarWeightsP, phW); phW += 1; }                    // tid 0 only
+  FC_HD_CTX void wait_weights() { ctx.bar_wait(kBarWeightsP, phW); phW += 1; }                    // issuer warp
   FC_HD_CTX void request_weights(bool bwd, int l) {                                              // tid 0 only
     const int n = bwd ? bwd_img_halves(l) : fwd_img_halves(l);   // hi + lo images of halves = that many floats
     ctx.bulk_load(sm + kSmWP, p.wpack + (bwd ? wb_off(l) : wf_off(l)), n, kBarWeightsP);
@@ -405,20 +405,21 @@ struct MpcPair {
       }
       arrive_ready(X);
     }
-    if (tid == 0) {
+    if (warp == 0) {                                         // issuer warp: all lanes follow, lane 0 issues
       wait_ready(X);
       if (X == 0) wait_weights();                            // operand image of this layer landed
-      issue_fwd(X, l, l == 0 ? 1 : 4);                       // recurrent part is zero: only the k-steps over the input
+      if (lane == 0) issue_fwd(X, l, l == 0 ? 1 : 4);        // recurrent part is zero: only the k-steps over the input
+      ctx.warp_sync();
     }
     lap(14);
   }
 
-  // thread 0: one step of the issue loop
+  // issuer warp (warp 0, all 32 lanes stay together; lane 0 issues): one step of the issue loop
   FC_HD_CTX void fwd_item_issuer(int X, int l, int m, int t, bool more_after) {
     lap(23);
     wait_full(X);                                            // MMA(X, l, t) complete (keeps the phase count; no stall)
     lap(1);
-    if (t == kLook - 1 && X == ntl - 1) {                    // stream the next weight image under the cell updates
+    if (t == kLook - 1 && X == ntl - 1 && lane == 0) {       // stream the next weight image under the cell updates
       if (l + 1 < kLayers) request_weights(false, l + 1);
       else if (m + 1 < p.N) request_weights(false, 0);
       else if (p.with_grad) request_weights(true, kLayers - 1);
@@ -427,7 +428,8 @@ struct MpcPair {
     if (t + 1 < kLook) {
       wait_ready(X);
       lap(4);
-      issue_fwd(X, l, kf_of(l) / 16);
+      if (lane == 0) issue_fwd(X, l, kf_of(l) / 16);
+      ctx.warp_sync();
       lap(5);
     }
   }
@@ -495,7 +497,7 @@ struct MpcPair {
       for (int X = 0; X < ntl; ++X) fwd_prologue(X, l, m);
       for (int t = 0; t < kLook; ++t)
         for (int X = 0; X < ntl; ++X) {
-          if (tid == 0) fwd_item_issuer(X, l, m, t, more_after);
+          if (warp == 0) fwd_item_issuer(X, l, m, t, more_after);
           else if (!service) fwd_item(X, l, m, t);
           else if (scalar) fwd_item_scalar(X, l, m, t);
         }
@@ -791,7 +793,7 @@ struct MpcPair {
     }
   }
 
-  // thread 0: one step of the issue loop
+  // issuer warp: one step of the issue loop
   FC_HD_CTX void bwd_item_issuer(int X, int l, int t) {
     if (t < kLook - 1) {
       lap(23);
@@ -801,7 +803,8 @@ struct MpcPair {
     wait_ready(X);
     if (X == 0 && t == kLook - 1) wait_weights();          // backward image of this layer landed
     lap(9);
-    issue_bwd(X, l);
+    if (lane == 0) issue_bwd(X, l);
+    ctx.warp_sync();
     lap(10);
   }
 
@@ -866,11 +869,11 @@ struct MpcPair {
   // after the last step of a layer: collect the result of MMA(X, l, tmin)
   FC_HD_CTX void bwd_tail(int X, int l, int m, bool more_after) {
     const int tmin = t_min_of(m);
-    if (service && tid != 0 && !scalar) return;
+    if (service && warp != 0 && !scalar) return;
     lap(22);
     wait_full(X);
     lap(6);
-    if (X == ntl - 1 && tid == 0) {                        // all MMAs that read this image are complete
+    if (X == ntl - 1 && tid == 0) {                        // all MMAs that read this image are complete (issuer lane)
       if (l > 0) request_weights(true, l - 1);
       else if (m > 0) request_weights(true, kLayers - 1);
       else if (more_after) request_weights(false, 0);
@@ -895,7 +898,7 @@ struct MpcPair {
     for (int l = kLayers - 1; l >= 0; --l) {
       for (int t = kLook - 1; t >= tmin; --t)
         for (int X = 0; X < ntl; ++X) {
-          if (tid == 0) bwd_item_issuer(X, l, t);
+          if (warp == 0) bwd_item_issuer(X, l, t);
           else if (!service) bwd_item(X, l, m, t);
           else if (scalar) bwd_item_scalar(X, t);
         }
