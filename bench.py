@@ -339,7 +339,7 @@ def run_ours(args):
             roof = dict(fp32, bound="fp32")
         # DRAM traffic per launch: ncu --set full capture of the same kernel at B=71040, N=10 (profiles/), scaled
         # linearly in B (the traffic is the per-trajectory activation records, written once and read once)
-        traffic_per_traj = (17.16e9 / 37888.0 if kernel in ("pair", "auto") else (27.86e9 if use_tc else 25.67e9) / 71040.0)
+        traffic_per_traj = (17.38e9 / 37888.0 if kernel in ("pair", "auto") else (27.86e9 if use_tc else 25.67e9) / 71040.0)
         roof.update({"flop_per_trajectory_step": F_ALG, "kernel_ms": kern_ms,
                      "traffic": traffic_per_traj * B if N == 10 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full capture of the same kernel (B=37888 pair / 71040 others) scaled by B (profiles/r01_*)",
