@@ -178,9 +178,10 @@ def _workspace(dev, nbytes: int) -> torch.Tensor:
     return buf
 
 
-def mpc_loss_native(wpack, X, u0, Z, N: int, alpha: float, with_grad: bool, global_batch: int | None = None):
-    """Thin wrapper over ``fc_mpc_loss``.  X [B,3], u0 [B], Z [B,10,5] float32 CUDA, contiguous.
-    Returns dict(cost, command, error, pred [B,N], gl [256], du0 [B] or None)."""
+def mpc_loss_native(wpack, X, u0, Z, N: int, alpha: float, with_grad: bool, global_batch: int | None = None,
+                    noise_std: float = 0.0, noise_seed: int = 0):
+    """Thin wrapper over ``fc_mpc_loss`` / ``fc_mpc_loss_noise``.  X [B,3], u0 [B], Z [B,10,5] float32 CUDA,
+    contiguous.  Returns dict(cost, command, error, pred [B,N], gl [256], du0 [B] or None)."""
     B = X.shape[0]
     dev = X.device
     L = _native.lib()
@@ -194,11 +195,12 @@ def mpc_loss_native(wpack, X, u0, Z, N: int, alpha: float, with_grad: bool, glob
         if nbytes == 0:
             raise RuntimeError("fc_mpc_loss_workspace_bytes failed: " + L.fc_last_error().decode())
         work = _workspace(dev, nbytes)
-        rc = L.fc_mpc_loss(_native.ptr(X), _native.ptr(u0), _native.ptr(Z), _native.ptr(wpack), B, N, float(alpha),
-                           int(global_batch if global_batch is not None else B), int(with_grad),
-                           _native.ptr(out["cost"]), _native.ptr(out["command"]), _native.ptr(out["error"]),
-                           _native.ptr(out["pred"]), _native.ptr(out["du0"]), _native.ptr(out["gl"]),
-                           _native.ptr(work), nbytes, _native.stream_ptr(dev))
+        rc = L.fc_mpc_loss_noise(_native.ptr(X), _native.ptr(u0), _native.ptr(Z), _native.ptr(wpack), B, N, float(alpha),
+                                 int(global_batch if global_batch is not None else B), int(with_grad),
+                                 _native.ptr(out["cost"]), _native.ptr(out["command"]), _native.ptr(out["error"]),
+                                 _native.ptr(out["pred"]), _native.ptr(out["du0"]), _native.ptr(out["gl"]),
+                                 _native.ptr(work), nbytes, float(noise_std), int(noise_seed) & (2 ** 64 - 1),
+                                 _native.stream_ptr(dev))
     _native.check(rc, "fc_mpc_loss")
     return out
 
@@ -208,8 +210,9 @@ class _FusedMPCLoss(torch.autograd.Function):
     linear in the upstream gradient, so ``backward`` only scales)."""
 
     @staticmethod
-    def forward(ctx, u0, inp_w, inp_b, out_w, X, Z, wpack, N, alpha, with_grad, global_batch):
-        res = mpc_loss_native(wpack, X, u0.detach().reshape(-1).contiguous(), Z, N, alpha, with_grad, global_batch)
+    def forward(ctx, u0, inp_w, inp_b, out_w, X, Z, wpack, N, alpha, with_grad, global_batch, noise_std=0.0, noise_seed=0):
+        res = mpc_loss_native(wpack, X, u0.detach().reshape(-1).contiguous(), Z, N, alpha, with_grad, global_batch,
+                              noise_std, noise_seed)
         ctx.with_grad = with_grad
         ctx.u0_shape = u0.shape
         if with_grad:
@@ -227,7 +230,7 @@ class _FusedMPCLoss(torch.autograd.Function):
         g_u0 = (du0 * g_loss).reshape(ctx.u0_shape)
         g = gl * g_loss
         return (g_u0, g[0:150].reshape(50, 3), g[150:200], g[200:250].reshape(1, 50),
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -236,7 +239,14 @@ class _FusedMPCLoss(torch.autograd.Function):
 class MPCLoss(nn.Module):
     """Loss that mimics the MPC cost, Functions.py:1336-1472 (same constructor and ``forward``
     signature, same ``(loss, loss_features)`` return).  ``global_batch`` (extension, default None)
-    is the batch size the mean runs over when the batch is sharded across ranks."""
+    is the batch size the mean runs over when the batch is sharded across ranks.
+
+    ``enable_noise=True`` adds ``NOISE_STD * N(0,1)`` to every surrogate output (Functions.py:1400-1402, :1438-1440).
+    The normals come from the kernel's counter-based Philox generator, seeded per call from torch's CPU generator
+    (so ``torch.manual_seed`` makes a run reproducible); they are not ``torch.randn``'s stream -- the reference is
+    not bit-reproducible in this mode either."""
+
+    NOISE_STD = 0.01     # Functions.py:1401
 
     def __init__(self, prediction_horizon=10, alpha=0.1):
         super().__init__()
@@ -247,9 +257,6 @@ class MPCLoss(nn.Module):
 
     def forward(self, simulator: nn.Module, controller: nn.Module, input_controller: torch.Tensor,
                 output_controller: torch.Tensor, states: torch.Tensor, device: torch.device, enable_noise=False):
-        if enable_noise:
-            raise NotImplementedError(
-                "MPCLoss (fused sm_100a kernel): enable_noise=True (Functions.py:1400-1402) is not implemented")
         _check_models(simulator, controller)
         X, Z, u0 = input_controller, states, output_controller
         if X.device.type != "cuda" or Z.device.type != "cuda" or u0.device.type != "cuda":
@@ -263,8 +270,12 @@ class MPCLoss(nn.Module):
         wpack = pack_weights(simulator, controller)
         params = (controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight)
         with_grad = torch.is_grad_enabled() and (u0.requires_grad or any(p.requires_grad for p in params))
+        noise_std, noise_seed = 0.0, 0
+        if enable_noise:
+            noise_std, noise_seed = self.NOISE_STD, int(torch.randint(0, 2 ** 62, (1,)).item())
         loss, cost, command, error, pred = _FusedMPCLoss.apply(
-            u0, *params, X, Z, wpack, int(self.N), float(self.alpha), bool(with_grad), self.global_batch)
+            u0, *params, X, Z, wpack, int(self.N), float(self.alpha), bool(with_grad), self.global_batch,
+            float(noise_std), noise_seed)
         return loss, {"loss": cost, "command": command, "error": error, "prediction": pred}
 
 

@@ -23,7 +23,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # every symbol include/forging_b200.h declares
 EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
            "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_closed_loop_rk4",
-           "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout")
+           "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout",
+           "fc_mpc_loss_noise")
 
 _c_float_p = ctypes.c_void_p   # raw device pointers are passed as integers
 _lib = None
@@ -69,6 +70,9 @@ def lib() -> ctypes.CDLL:
     L.fc_mpc_select_kernel.argtypes = [i32]
     L.fc_mpc_loss.restype = i32
     L.fc_mpc_loss.argtypes = [vp, vp, vp, vp, i32, i32, f32, i64, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.fc_mpc_loss_noise.restype = i32
+    L.fc_mpc_loss_noise.argtypes = [vp, vp, vp, vp, i32, i32, f32, i64, i32, vp, vp, vp, vp, vp, vp, vp, sz, f32,
+                                    ctypes.c_ulonglong, vp]
     L.fc_closed_loop_rk4.restype = i32
     L.fc_closed_loop_rk4.argtypes = [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fc_closed_loop_rk4_f64.restype = i32

@@ -519,6 +519,15 @@ size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad) {
 int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
                 long long B_global, int with_grad, float* cost, float* command, float* error, float* pred, float* du0,
                 float* gl, void* workspace, size_t workspace_bytes, void* stream) {
+  return fc_mpc_loss_noise(X, u0, Z, wpack, B, N, alpha, B_global, with_grad, cost, command, error, pred, du0, gl, workspace,
+                           workspace_bytes, 0.0f, 0ull, stream);
+}
+
+int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                      long long B_global, int with_grad, float* cost, float* command, float* error, float* pred, float* du0,
+                      float* gl, void* workspace, size_t workspace_bytes, float noise_std, unsigned long long noise_seed,
+                      void* stream) {
+  if (!(noise_std >= 0.f)) return fail(FC_ERR_BAD_SHAPE, "fc_mpc_loss: noise_std%s must be >= 0");
   if (B <= 0 || N <= 0 || B_global < B) return fail(FC_ERR_BAD_SHAPE, "fc_mpc_loss: bad shape%s B=%lld N=%lld", "", B, N);
   if (N > 4096) return fail(FC_ERR_UNSUPPORTED, "fc_mpc_loss: horizon%s N=%lld too long", "", N);
   if (!X || !u0 || !Z || !wpack || !cost || !command || !error || !pred || !gl || !workspace || (with_grad && !du0))
@@ -562,6 +571,7 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
   p.acc_comp = 1.3f;
   if (const char* e = getenv("FC_TC_ACC_COMP")) p.acc_comp = (float)atof(e);   // calibration experiments only
   p.debug_timing = getenv("FC_TC_TIMING") ? 1 : 0;
+  p.noise_std = noise_std; p.noise_seed = noise_seed;
   cudaStream_t st = (cudaStream_t)stream;
   if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
   else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, tc::kSmBytesTC, st>>>(p);

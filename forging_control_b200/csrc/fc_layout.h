@@ -201,6 +201,10 @@ struct MpcParams {
   int debug_timing;      // CTA 0 prints a cycle breakdown (development aid)
   float g_scale;         // tcgen05 kernel: power-of-two scale of the gate gradients before the fp16 split
   float g_unscale;       // 1 / g_scale
+  // enable_noise (UL/Functions.py:1400-1402, :1438-1440): x += noise_std * N(0,1) after every surrogate call;
+  // counter-based generator (Philox4x32-10, key = seed, counter = (trajectory, window)), see philox_normal4
+  float noise_std;
+  unsigned long long noise_seed;
   // LSTM shadow roll-out (pair kernel, forward only; Functions.py:969-1011, 1196-1231): N windows, the command of
   // every step is an input, no cost / controller / reverse sweep
   int shadow;
@@ -209,5 +213,24 @@ struct MpcParams {
   float* sh_y;           // [B][N][4] surrogate outputs (scaled)
   float sh_ratio[4];     // scale_out / scale_in: output -> next input row
 };
+
+// Four standard normals for (trajectory b, window m): Philox4x32-10 + Box-Muller.  Counter-based, so every kernel
+// (and the oracle's restatement, oracle/mpc_loss_oracle.py::philox_normal4) draws the same noise for the same seed.
+FC_HD void philox_normal4(unsigned long long seed, unsigned b, unsigned m, float* out) {
+  unsigned c0 = b, c1 = m, c2 = 0u, c3 = 0u;
+  unsigned k0 = (unsigned)(seed & 0xffffffffull), k1 = (unsigned)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const float s = 2.3283064365386963e-10f;                      // 2^-32
+  const float u0 = ((float)c0 + 0.5f) * s, u1 = ((float)c1 + 0.5f) * s, u2 = ((float)c2 + 0.5f) * s, u3 = ((float)c3 + 0.5f) * s;
+  const float r0 = sqrtf(-2.0f * logf(u0 < 1e-30f ? 1e-30f : (u0 > 0.99999994f ? 0.99999994f : u0)));
+  const float r1 = sqrtf(-2.0f * logf(u2 < 1e-30f ? 1e-30f : (u2 > 0.99999994f ? 0.99999994f : u2)));
+  const float t0 = 6.2831853071795865f * u1, t1 = 6.2831853071795865f * u3;
+  out[0] = r0 * cosf(t0); out[1] = r0 * sinf(t0); out[2] = r1 * cosf(t1); out[3] = r1 * sinf(t1);
+}
 
 }  // namespace fc

@@ -196,6 +196,12 @@ struct MpcTile {
 #pragma unroll
         for (int q = 0; q < 4; ++q) x[q] = fmaf(sw[q * kHid + u], hv, x[q]);
       }
+      if (p.noise_std > 0.f) {                                                 // enable_noise, :1400-1402 / :1438-1440
+        float e[4];
+        philox_normal4(p.noise_seed, (unsigned)(tile * kTile + traj), (unsigned)m, e);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
+      }
       const float ref = sm[kSmRef + traj];
       const float ucur = sm[kSmUcur + traj], uprev = sm[kSmUprev + traj];
       float du = uprev - ucur;

@@ -556,6 +556,12 @@ struct MpcPair {
     float x[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) x[q] = ((fp[q] + fp[4 + q]) + fp[8 + q]) + sw[(kFCB - kFCW) + q];
+    if (p.noise_std > 0.f) {                                                   // enable_noise, :1400-1402 / :1438-1440
+      float e[4];
+      philox_normal4(p.noise_seed, (unsigned)((tile0 + X) * kTileP + row), (unsigned)m, e);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
+    }
     float* rows = w_rows(X);
     const float ref = sm[kSmRefP + X * kTileP + row];
     const float ucur = Ctx::ldcg(rows + (size_t)((kLook - 1 + m) * kFeat + 4) * kTileP + row);

@@ -354,6 +354,12 @@ struct MpcTileTC {
     for (int q = 0; q < 4; ++q)
       x[q] = ((hrec[q] + sm[kSmFcpTC + q * kTileTC + row]) + (sm[kSmFcpTC + (4 + q) * kTileTC + row] + sm[kSmFcpTC + (8 + q) * kTileTC + row])) +
              sw[(kFCB - kFCW) + q];
+    if (p.noise_std > 0.f) {                                                   // enable_noise, :1400-1402 / :1438-1440
+      float e[4];
+      philox_normal4(p.noise_seed, (unsigned)(tile * kTileTC + row), (unsigned)m, e);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
+    }
     const float ref = sm[kSmRefTC + row];
     const float ucur = sm[kSmUcurTC + row], uprev = sm[kSmUprevTC + row];
     float du = uprev - ucur;

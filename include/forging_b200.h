@@ -67,6 +67,15 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
                 float alpha, long long B_global, int with_grad, float* cost, float* command,
                 float* error, float* pred, float* du0, float* gl, void* workspace,
                 size_t workspace_bytes, void* stream);
+/* Same with `enable_noise=True` of MPCLoss.forward (UL/Functions.py:1400-1402, :1438-1440): noise_std * N(0,1) is added
+ * to every surrogate output before the cost and the next controller call (the reference uses 0.01).  The normals
+ * come from a counter-based Philox4x32-10 generator keyed by noise_seed with counter (trajectory, window), so a call is
+ * reproducible for a given seed and independent of the kernel chosen; they are NOT torch.randn's stream.
+ * noise_std = 0 is fc_mpc_loss.                                                                            */
+int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N,
+                      float alpha, long long B_global, int with_grad, float* cost, float* command,
+                      float* error, float* pred, float* du0, float* gl, void* workspace,
+                      size_t workspace_bytes, float noise_std, unsigned long long noise_seed, void* stream);
 
 /* LSTM shadow roll-out of the closed loop (replaces the per-step `simulator_make_step` loop of
  * NeuralNetwork.loop, UL/Functions.py:969-1011 and :1196-1231): T windowed-LSTM inferences per trajectory, batched

@@ -186,8 +186,33 @@ def _constraint(x):
 # ----------------------------------------------------------------------------------------------
 # loss (MPCLoss.forward, UL/Functions.py:1353-1472)
 # ----------------------------------------------------------------------------------------------
-def mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim=1, keep=False):
-    """X [B,3], u0 [B] (= output_controller.squeeze()), Z [B,10,5].
+def philox_normal4(seed: int, B: int, N: int) -> np.ndarray:
+    """The kernels' noise for ``enable_noise`` (forging_control_b200/csrc/fc_layout.h::philox_normal4): four standard
+    normals per (trajectory b, window m) from Philox4x32-10 (key = seed, counter = (b, m, 0, 0)) + Box-Muller in
+    float32.  Returns [B,N,4] float64.  (The reference draws ``0.01*torch.randn_like(x)``, UL/Functions.py:1401; its
+    stream cannot be reproduced, the distribution is the same.)"""
+    b = np.repeat(np.arange(B, dtype=np.uint64)[:, None], N, axis=1)
+    m = np.repeat(np.arange(N, dtype=np.uint64)[None, :], B, axis=0)
+    c = [b.copy(), m.copy(), np.zeros_like(b), np.zeros_like(b)]
+    k0, k1 = np.uint64(seed & 0xffffffff), np.uint64((seed >> 32) & 0xffffffff)
+    M32 = np.uint64(0xffffffff)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & M32, p1 & M32, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & M32, p0 & M32]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M32, (k1 + np.uint64(0xBB67AE85)) & M32
+    f32 = np.float32
+    s = f32(2.3283064365386963e-10)
+    u = [(ci.astype(f32) + f32(0.5)) * s for ci in c]
+    clip = lambda v: np.clip(v, f32(1e-30), f32(0.99999994))
+    r0 = np.sqrt(f32(-2.0) * np.log(clip(u[0])))
+    r1 = np.sqrt(f32(-2.0) * np.log(clip(u[2])))
+    t0, t1 = f32(6.2831853071795865) * u[1], f32(6.2831853071795865) * u[3]
+    return np.stack((r0 * np.cos(t0), r0 * np.sin(t0), r1 * np.cos(t1), r1 * np.sin(t1)), axis=-1).astype(np.float64)
+
+
+def mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim=1, keep=False, noise=None):
+    """X [B,3], u0 [B] (= output_controller.squeeze()), Z [B,10,5].  ``noise`` [B,N,4] (already scaled by the
+    standard deviation) is added to the surrogate output of every window (enable_noise, UL/Functions.py:1400-1402).
 
     Returns dict(loss, cost[B], command[B], error[B], prediction[B,N]) (+ tape when ``keep``)."""
     B = X.shape[0]
@@ -207,6 +232,8 @@ def mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim=1, keep=False):
     for m in range(N):
         res = lstm_window_forward(w, rows[:, m:m + LOOKBACK], keep=keep)
         x = res[0] if keep else res
+        if noise is not None:
+            x = x + noise[:, m].astype(dt)
         if keep:
             tape["lstm"].append(res[1])
         cmd[m] = alpha * np.square(u_prev - u_cur)
@@ -235,10 +262,10 @@ def mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim=1, keep=False):
     return out
 
 
-def mpc_loss_forward_backward(w, X, u0, Z, N, alpha, width_dim=1, prune=True):
+def mpc_loss_forward_backward(w, X, u0, Z, N, alpha, width_dim=1, prune=True, noise=None):
     """Forward + hand-derived reverse sweep.  Returns (forward dict, grads dict) with
     ``grads`` = d loss / d {u0 [B], inp_w, inp_b, out_w, (int_w, int_b)}."""
-    out, tape = mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim, keep=True)
+    out, tape = mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim, keep=True, noise=noise)
     B = X.shape[0]
     dt = X.dtype
     rows = tape["rows"]

@@ -144,7 +144,13 @@ struct EmuCtxTC : EmuCtx {
 
 }  // namespace
 
+static float g_noise_std = 0.f;
+static unsigned long long g_noise_seed = 0ull;
+
 extern "C" {
+
+// enable_noise for the following emulated launches (0 = off)
+void fc_emu_set_noise(float std, unsigned long long seed) { g_noise_std = std; g_noise_seed = seed; }
 
 int fc_emu_pack_floats() { return fc::kPackFloats; }
 
@@ -167,6 +173,7 @@ int fc_emu_mpc_loss(const float* X, const float* u0, const float* Z, const float
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
   p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
   p.acc_comp = 1.0f;
   { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
   p.num_tiles = (B + fc::kTile - 1) / fc::kTile;
@@ -227,6 +234,7 @@ int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const fl
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
   p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
   p.acc_comp = 1.0f;
   { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
   p.num_tiles = (B + fc::tc::kTileTC - 1) / fc::tc::kTileTC;
@@ -287,6 +295,7 @@ int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const 
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
   p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
   p.acc_comp = 1.0f;
   { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
   p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;

@@ -59,7 +59,7 @@ def test_no_cpu_fallback(golden_weights):
     X, Z = torch.zeros(4, 3), torch.zeros(4, 10, 5)
     with pytest.raises(RuntimeError, match="CUDA"):
         fb.MPCLoss(10, 20.0)(sim, ctl, X, ctl(X), Z, "cpu")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         fb.MPCLoss(10, 20.0)(sim, ctl, X, ctl(X), Z, "cpu", enable_noise=True)
     with pytest.raises(NotImplementedError):
         fb.MPCLoss(10, 20.0)(fb.LSTMModel(5, 64, 4, 3), ctl, X, ctl(X), Z, "cpu")

@@ -248,3 +248,47 @@ def test_c_abi_error_codes(dev, golden_weights):
     rc = L.fc_mpc_loss(0, p(u0), p(Z), p(wp), 10, 10, 20.0, 10, 1, p(o[0]), p(o[1]), p(o[2]), p(pred), p(o[3]),
                        p(gl), p(work), 64, 0)
     assert rc == -3
+
+
+def test_enable_noise_matches_oracle_with_the_same_noise(dev, golden_weights):
+    """enable_noise=True (UL/Functions.py:1400-1402, :1438-1440) through fc_mpc_loss_noise: the counter-based generator
+    is restated in the oracle (philox_normal4), so the noisy roll-out is checked like the clean one; runs for the three
+    kernels (autouse fixture) with the same seed -> same noise."""
+    sim, ctl, lstm, fnn = _models(golden_weights, "c0", dev)
+    B, N, seed, std = 700, 6, 0xC0FFEE1234, 0.01
+    g = torch.Generator().manual_seed(11)
+    X = (torch.rand(B, 3, generator=g) * 2 - 1)
+    Z = (torch.rand(B, 10, 5, generator=g) * 2 - 1)
+    Xd, Zd = X.to(dev), Z.to(dev)
+    with torch.no_grad():
+        u0 = ctl(Xd).reshape(-1).contiguous()
+    r = fb.mpc_loss_native(fb.pack_weights(sim, ctl), Xd, u0, Zd, N, ALPHA, True, None, std, seed)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    noise = std * O.philox_normal4(seed, B, N)
+    out, gr = O.mpc_loss_forward_backward(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, ALPHA, noise=noise)
+    clean, _ = O.mpc_loss_forward_backward(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, ALPHA)
+    gl = r["gl"].cpu().numpy()
+    assert abs(gl[250] - out["loss"]) / abs(out["loss"]) < TOL
+    assert abs(out["loss"] - clean["loss"]) / abs(clean["loss"]) > 1e-5
+    assert rel_max(r["cost"].cpu().numpy(), out["cost"]) < TOL
+    assert rel_max(r["pred"].cpu().numpy(), out["prediction"]) < TOL
+    d = np.abs(r["du0"].cpu().numpy() - gr["u0"]) / np.abs(gr["u0"]).max()
+    assert (d > TOL).sum() <= 3          # kink flips, see test_native_call_matches_fp64_oracle
+    assert rel_max(gl[:150].reshape(50, 3), gr["inp_w"]) < 5e-5 and rel_max(gl[200:250], gr["out_w"][0]) < 5e-5
+
+
+def test_enable_noise_module_api_is_seeded_by_torch(dev, golden_weights):
+    sim, ctl, _, _ = _models(golden_weights, "c0", dev)
+    g = torch.Generator().manual_seed(3)
+    X = (torch.rand(64, 3, generator=g) * 2 - 1).to(dev)
+    Z = (torch.rand(64, 10, 5, generator=g) * 2 - 1).to(dev)
+    loss_fn = fb.MPCLoss(prediction_horizon=5, alpha=ALPHA)
+    def run(seed):
+        torch.manual_seed(seed)
+        loss, feats = loss_fn(sim, ctl, X, ctl(X), Z, dev, enable_noise=True)
+        loss.backward()
+        return loss.item()
+    clean = loss_fn(sim, ctl, X, ctl(X), Z, dev)[0].item()
+    a, b, c = run(1), run(1), run(2)
+    assert a == b and a != c and a != clean
+    assert abs(a - clean) / abs(clean) < 0.2         # 1 % noise on the surrogate outputs: a perturbation, not a different loss

@@ -170,3 +170,30 @@ def test_emulated_lstm_shadow_rollout_matches_oracle(emu, golden_weights):
     w = O.weights_from_state_dicts(lstm, fnn, np.float64)
     ref = O.lstm_shadow_rollout(w, row0.astype(np.float64), u.astype(np.float64), ratio.astype(np.float64))
     assert rel_max(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("variant", ["ffma", "pair"])
+def test_emulated_enable_noise_matches_oracle_with_the_same_noise(emu, golden_cases, golden_weights, variant):
+    """enable_noise (UL/Functions.py:1400-1402): the kernels' counter-based generator restated in the oracle
+    (philox_normal4) gives the same roll-out, costs and gradients."""
+    C, name = golden_cases, "n2_b5"
+    N, B, wd = (int(v) for v in C[f"{name}/meta"])
+    lstm, fnn = state_dicts(golden_weights, str(C[f"{name}/ctl"]))
+    X, Z = C[f"{name}/X"], C[f"{name}/Z"]
+    u0 = np.ascontiguousarray(C[f"{name}/f32/u0"])
+    seed, std = 0x1234567890ABCDEF, 0.01
+    emu.fc_emu_set_noise.argtypes = [ctypes.c_float, ctypes.c_ulonglong]
+    emu.fc_emu_set_noise(std, seed)
+    try:
+        if variant == "ffma":
+            o = _run(emu, _pack(emu, lstm, fnn), X, u0, Z, N, 20.0)
+        else:
+            o = _run_v(emu, variant, _pack_v(emu, lstm, fnn, variant), X, u0, Z, N, 20.0)
+    finally:
+        emu.fc_emu_set_noise(0.0, 0)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    noise = std * O.philox_normal4(seed, B, N)
+    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0, noise=noise)
+    _check_v(o, out, g)
+    clean, _ = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
+    assert abs(out["loss"] - clean["loss"]) / abs(clean["loss"]) > 1e-4      # the noise does change the result
