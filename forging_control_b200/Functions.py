@@ -371,13 +371,16 @@ class NeuralNetwork:
         their reference segment, so they run as ONE batch of the RK4 plant kernel (scaler -> FNN ->
         Hardtanh -> inverse scaler -> 4 RK4 sub-steps of the press ODE per sample).  ``simulator`` (the
         do-mpc CVODES object of the reference) is accepted for signature compatibility and returned
-        untouched.  Noise and the IPOPT feasibility branch are outside the hot path and raise.
+        untouched.  ``process_std`` / ``meas_std`` add the reference's process and measurement noise (:1176-1183) from
+        the kernel's counter-based generator, seeded from ``np.random`` (so ``np.random.seed`` makes a run
+        reproducible; the reference's own ``np.random.normal`` stream is not reproduced).  The IPOPT feasibility
+        branch is outside the hot path and raises.
         Extensions: ``device`` (default ``cuda``), ``dtype`` (plant precision, default float64 like the
         reference plant), ``substeps``."""
         if feasibility:
             raise NotImplementedError("NeuralNetwork.loop: the IPOPT feasibility-recovery branch is out of scope")
-        if np.any(np.asarray(process_std) != 0) or np.any(np.asarray(meas_std) != 0):
-            raise NotImplementedError("NeuralNetwork.loop: process / measurement noise is not implemented")
+        noisy = np.any(np.asarray(process_std) != 0) or np.any(np.asarray(meas_std) != 0)
+        noise_seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64)) if noisy else 0
         dev = torch.device(device) if device is not None else torch.device("cuda")
         x0 = np.array([[init_state.get(k, 0) for k in ("y", "y_dot", "p1", "p2", "z")]] * N_traj, dtype=np.float64)
         T_ref = Ts * T_traj
@@ -388,7 +391,8 @@ class NeuralNetwork:
         timer = ClosedLoopTimer()
         timer.tic()
         meas, u = closed_loop_rollout(controller, x0, ref, Ts, scale_in, scale_out, substeps=substeps,
-                                      device=dev, dtype=dtype)
+                                      device=dev, dtype=dtype, process_std=process_std if noisy else None,
+                                      meas_std=meas_std if noisy else None, noise_seed=noise_seed)
         timer.toc(n_steps=N_traj * T_traj)
         names = ("y", "y_dot", "p1", "p2", "z")
         results = {n: meas[:, :, i] for i, n in enumerate(names)}

@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
            "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_closed_loop_rk4",
            "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout",
-           "fc_mpc_loss_noise")
+           "fc_mpc_loss_noise", "fc_closed_loop_rk4_noise", "fc_closed_loop_rk4_f64_noise")
 
 _c_float_p = ctypes.c_void_p   # raw device pointers are passed as integers
 _lib = None
@@ -81,6 +81,13 @@ def lib() -> ctypes.CDLL:
     L.fc_lstm_shadow_workspace_bytes.argtypes = [i32, i32]
     L.fc_lstm_shadow_rollout.restype = i32
     L.fc_lstm_shadow_rollout.argtypes = [vp, vp, ctypes.POINTER(f32), vp, i32, i32, vp, vp, sz, vp]
+    fp5 = ctypes.POINTER(f32)
+    L.fc_closed_loop_rk4_noise.restype = i32
+    L.fc_closed_loop_rk4_noise.argtypes = [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp, fp5, fp5,
+                                           ctypes.c_ulonglong, vp]
+    L.fc_closed_loop_rk4_f64_noise.restype = i32
+    L.fc_closed_loop_rk4_f64_noise.argtypes = [vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp, vp, vp, vp, vp, fp5, fp5,
+                                               ctypes.c_ulonglong, vp]
     L.fc_fp32_peak.restype = i32
     L.fc_fp32_peak.argtypes = [i32, ctypes.POINTER(f64), vp]
     _lib = L

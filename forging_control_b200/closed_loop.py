@@ -64,10 +64,12 @@ def _controller_weights(controller, dev):
 
 
 def closed_loop_device(controller, x0, ref, Ts, scale_in, scale_out, substeps=4, steps_per_ref=1,
-                       want_meas=True, want_u=True):
+                       want_meas=True, want_u=True, process_std=None, meas_std=None, noise_seed=0):
     """Device-resident launch.  ``x0`` [B,5] and ``ref`` [n_ref,B] are CUDA tensors of the same dtype
     (float32 or float64).  Returns (meas [T+1,5,B] or None, u [T,B] or None, x_final [B,5]); the
-    number of steps is ``T = n_ref * steps_per_ref``."""
+    number of steps is ``T = n_ref * steps_per_ref``.  ``process_std`` / ``meas_std`` (5 values each) switch on the
+    process / measurement noise of ``NeuralNetwork.loop`` (Functions.py:1176-1183) from the kernel's counter-based
+    generator keyed by ``noise_seed``."""
     if x0.device.type != "cuda":
         raise RuntimeError("closed loop: CUDA tensors required (forging_control_b200 has no CPU fallback)")
     dev, dt = x0.device, x0.dtype
@@ -86,21 +88,25 @@ def closed_loop_device(controller, x0, ref, Ts, scale_in, scale_out, substeps=4,
     u = torch.empty((T, B), dtype=dt, device=dev) if want_u else None
     xf = torch.empty((B, 5), dtype=dt, device=dev)
     L = _native.lib()
-    fn = L.fc_closed_loop_rk4 if dt == torch.float32 else L.fc_closed_loop_rk4_f64
+    fn = L.fc_closed_loop_rk4_noise if dt == torch.float32 else L.fc_closed_loop_rk4_f64_noise
+    import ctypes
+    as5 = lambda v: (ctypes.c_float * 5)(*[float(a) for a in (np.zeros(5) if v is None else np.asarray(v, dtype=np.float64).reshape(5))])
     with torch.cuda.device(dev):
         rc = fn(_native.ptr(x0), _native.ptr(ref), n_ref, steps_per_ref, B, T, float(Ts), int(substeps),
                 _native.ptr(s_in), _native.ptr(s_out), _native.ptr(w_in), _native.ptr(b_in), _native.ptr(w_out),
-                _native.ptr(meas), _native.ptr(u), _native.ptr(xf), _native.stream_ptr(dev))
+                _native.ptr(meas), _native.ptr(u), _native.ptr(xf), as5(process_std), as5(meas_std),
+                int(noise_seed) & (2 ** 64 - 1), _native.stream_ptr(dev))
     _native.check(rc, "fc_closed_loop_rk4")
     return meas, u, xf
 
 
 def closed_loop_rollout(controller, x0, ref, Ts, scale_in, scale_out, substeps=4, device="cuda",
-                        dtype=torch.float64):
+                        dtype=torch.float64, process_std=None, meas_std=None, noise_seed=0):
     """numpy in / numpy out convenience used by ``NeuralNetwork.loop``: ``x0`` [B,5], ``ref`` [B,T]
     (physical units).  Returns (meas [B,T+1,5], u [B,T]) as float64 numpy arrays."""
     dev = torch.device(device)
     x0_t = torch.as_tensor(np.ascontiguousarray(x0), dtype=dtype).to(dev)
     ref_t = torch.as_tensor(np.ascontiguousarray(np.asarray(ref).T), dtype=dtype).to(dev)
-    meas, u, _ = closed_loop_device(controller, x0_t, ref_t, Ts, scale_in, scale_out, substeps)
+    meas, u, _ = closed_loop_device(controller, x0_t, ref_t, Ts, scale_in, scale_out, substeps,
+                                    process_std=process_std, meas_std=meas_std, noise_seed=noise_seed)
     return (meas.permute(2, 0, 1).double().cpu().numpy(), u.t().double().cpu().numpy())

@@ -460,14 +460,25 @@ static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl) {
 template <typename R>
 static int closed_loop_launch(const R* x0, const R* ref, int n_ref, int steps_per_ref, int B, int T, R ts, int substeps,
                               const R* scale_in, const R* scale_out, const float* inp_w, const float* inp_b,
-                              const float* out_w, R* meas, R* u, R* x_final, void* stream) {
+                              const float* out_w, R* meas, R* u, R* x_final, void* stream,
+                              const float* process_std = nullptr, const float* meas_std = nullptr, unsigned long long seed = 0) {
   if (B <= 0 || T < 0 || n_ref <= 0 || steps_per_ref <= 0 || substeps <= 0 || !(ts > 0))
     return fail(FC_ERR_BAD_SHAPE, "fc_closed_loop_rk4: bad shape%s B=%lld T=%lld", "", B, T);
   if (!x0 || !ref || !scale_in || !scale_out || !inp_w || !inp_b || !out_w)
     return fail(FC_ERR_NULL_POINTER, "fc_closed_loop_rk4: null pointer%s");
   const int threads = 128;
+  ClosedLoopNoise nz;
+  memset(&nz, 0, sizeof(nz));
+  nz.seed = seed;
+  for (int i = 0; i < 5; ++i) {                         // HOST arrays of 5 floats (may be NULL = no noise)
+    nz.process_std[i] = process_std ? process_std[i] : 0.f;
+    nz.meas_std[i] = meas_std ? meas_std[i] : 0.f;
+    if (!(nz.process_std[i] >= 0.f) || !(nz.meas_std[i] >= 0.f))
+      return fail(FC_ERR_BAD_SHAPE, "fc_closed_loop_rk4: noise standard deviations%s must be >= 0");
+    if (nz.process_std[i] > 0.f || nz.meas_std[i] > 0.f) nz.on = 1;
+  }
   closed_loop_kernel<R><<<(B + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-      x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, inp_w, inp_b, out_w, meas, u, x_final);
+      x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, inp_w, inp_b, out_w, meas, u, x_final, nz);
   FC_CUDA(cudaGetLastError(), "closed_loop_kernel launch");
   return FC_OK;
 }
@@ -645,6 +656,22 @@ int fc_closed_loop_rk4_f64(const double* x0, const double* ref, int n_ref, int s
                            void* stream) {
   return closed_loop_launch<double>(x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, fnn_inp_w,
                                     fnn_inp_b, fnn_out_w, meas, u, x_final, stream);
+}
+
+int fc_closed_loop_rk4_noise(const float* x0, const float* ref, int n_ref, int steps_per_ref, int B, int T, float ts,
+                             int substeps, const float* scale_in, const float* scale_out, const float* fnn_inp_w,
+                             const float* fnn_inp_b, const float* fnn_out_w, float* meas, float* u, float* x_final,
+                             const float* process_std, const float* meas_std, unsigned long long seed, void* stream) {
+  return closed_loop_launch<float>(x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, fnn_inp_w,
+                                   fnn_inp_b, fnn_out_w, meas, u, x_final, stream, process_std, meas_std, seed);
+}
+
+int fc_closed_loop_rk4_f64_noise(const double* x0, const double* ref, int n_ref, int steps_per_ref, int B, int T, double ts,
+                                 int substeps, const double* scale_in, const double* scale_out, const float* fnn_inp_w,
+                                 const float* fnn_inp_b, const float* fnn_out_w, double* meas, double* u, double* x_final,
+                                 const float* process_std, const float* meas_std, unsigned long long seed, void* stream) {
+  return closed_loop_launch<double>(x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, fnn_inp_w,
+                                    fnn_inp_b, fnn_out_w, meas, u, x_final, stream, process_std, meas_std, seed);
 }
 
 int fc_fp32_peak(int iters, double* flops_host, void* stream) {

@@ -101,13 +101,24 @@ __device__ __forceinline__ void rk4_substep(R (&x)[5], R u, R h) {            //
   for (int i = 0; i < 5; ++i) x[i] = x[i] + h / R(6) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + k4[i]);
 }
 
+// process / measurement noise of do-mpc's Simulator.make_step(u0, v0, w0) as driven by NeuralNetwork.loop
+// (UL/Functions.py:1176-1183): x_next = integrate(x, u) + w0, y = measurement(x_next) + v0, w0 ~ N(0, process_std),
+// v0 ~ N(0, meas_std) per state; the controller reads the noisy measurement.  Normals: philox_normal4 with counter
+// (trajectory, 3*step + k).  std all zero = off.
+struct ClosedLoopNoise {
+  float process_std[5];
+  float meas_std[5];
+  unsigned long long seed;
+  int on;
+};
+
 // closed loop: scaler -> FNN (float32) -> saturation -> inverse scaler -> RK4 plant step
 template <typename R>
 __global__ void __launch_bounds__(128) closed_loop_kernel(
     const R* __restrict__ x0, const R* __restrict__ ref, int n_ref, int steps_per_ref, int B, int T, R ts,
     int substeps, const R* __restrict__ scale_in, const R* __restrict__ scale_out,
     const float* __restrict__ inp_w, const float* __restrict__ inp_b, const float* __restrict__ out_w,
-    R* __restrict__ meas, R* __restrict__ ucmd, R* __restrict__ x_final) {
+    R* __restrict__ meas, R* __restrict__ ucmd, R* __restrict__ x_final, ClosedLoopNoise nz) {
   __shared__ float s_w[50 * 3], s_b[50], s_o[50];
   for (int i = threadIdx.x; i < 150; i += blockDim.x) s_w[i] = inp_w[i];
   for (int i = threadIdx.x; i < 50; i += blockDim.x) { s_b[i] = inp_b[i]; s_o[i] = out_w[i]; }
@@ -123,12 +134,13 @@ __global__ void __launch_bounds__(128) closed_loop_kernel(
     for (int i = 0; i < 5; ++i) meas[(size_t)i * B + b] = x[i];           // Functions.py:1134-1138
   }
   const R h = ts / R(substeps);
+  R ym1 = x[1], ym4 = x[4];                                                  // measured y_dot, z seen by the controller
   for (int t = 0; t < T; ++t) {
     int ir = t / steps_per_ref;
     ir = ir < n_ref ? ir : n_ref - 1;
     const R r = ref[(size_t)ir * B + b];
     // NN_make_step, Functions.py:1596-1604: MaxAbs scale, reference scaled by the y_dot scaler
-    const float f0 = (float)(x[1] / si0), f1 = (float)(x[4] / si1), f2 = (float)(r / si0);
+    const float f0 = (float)(ym1 / si0), f1 = (float)(ym4 / si1), f2 = (float)(r / si0);
     float vv = 0.f;
 #pragma unroll 10
     for (int k = 0; k < 50; ++k) {
@@ -139,13 +151,23 @@ __global__ void __launch_bounds__(128) closed_loop_kernel(
     const R u = (R)us * so;
     if (ucmd) ucmd[(size_t)t * B + b] = u;
     for (int s = 0; s < substeps; ++s) rk4_substep(x, u, h);
+    R y[5] = {x[0], x[1], smooth_floor(x[2]), smooth_floor(x[3]), x[4]};     // template_model.py:154-155
+    if (nz.on) {
+      float e[12];
+      philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t, e);
+      philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t + 1u, e + 4);
+      philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t + 2u, e + 8);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) x[i] += (R)(nz.process_std[i] * e[i]);
+      y[0] = x[0]; y[1] = x[1]; y[2] = smooth_floor(x[2]); y[3] = smooth_floor(x[3]); y[4] = x[4];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) y[i] += (R)(nz.meas_std[i] * e[5 + i]);
+    }
+    ym1 = y[1]; ym4 = y[4];
     if (meas) {
       R* mp = meas + (size_t)(t + 1) * 5 * B + b;
-      mp[0] = x[0];
-      mp[(size_t)B] = x[1];
-      mp[(size_t)2 * B] = smooth_floor(x[2]);                              // template_model.py:154-155
-      mp[(size_t)3 * B] = smooth_floor(x[3]);
-      mp[(size_t)4 * B] = x[4];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) mp[(size_t)i * B] = y[i];
     }
   }
   if (x_final) {

@@ -109,6 +109,19 @@ int fc_closed_loop_rk4_f64(const double* x0, const double* ref, int n_ref, int s
                            const double* scale_out, const float* fnn_inp_w, const float* fnn_inp_b,
                            const float* fnn_out_w, double* meas, double* u, double* x_final,
                            void* stream);
+/* The same with the process / measurement noise of NeuralNetwork.loop (UL/Functions.py:1176-1183, do-mpc
+ * Simulator.make_step(u0, v0, w0)): x_next = integrate(x, u) + w0, y = measurement(x_next) + v0, the controller reads the
+ * noisy measurement.  process_std, meas_std: HOST arrays of 5 floats (NULL = zeros); normals from the counter-based
+ * generator of fc_mpc_loss_noise, keyed by seed.                                                            */
+int fc_closed_loop_rk4_noise(const float* x0, const float* ref, int n_ref, int steps_per_ref, int B, int T, float ts,
+                             int substeps, const float* scale_in, const float* scale_out, const float* fnn_inp_w,
+                             const float* fnn_inp_b, const float* fnn_out_w, float* meas, float* u, float* x_final,
+                             const float* process_std, const float* meas_std, unsigned long long seed, void* stream);
+int fc_closed_loop_rk4_f64_noise(const double* x0, const double* ref, int n_ref, int steps_per_ref, int B, int T,
+                                 double ts, int substeps, const double* scale_in, const double* scale_out,
+                                 const float* fnn_inp_w, const float* fnn_inp_b, const float* fnn_out_w, double* meas,
+                                 double* u, double* x_final, const float* process_std, const float* meas_std,
+                                 unsigned long long seed, void* stream);
 
 /* ---- measurement helper: register-resident FFMA loop used by bench.py to measure the FP32
  * roofline denominator on the device it runs on; writes achieved FLOP/s to *flops_host.           */

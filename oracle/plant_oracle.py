@@ -152,17 +152,30 @@ def tvp_reference(t_now, ref_step, bias_work, bias_return, epsilon=1e-7):
     return -0.8 * random.random() - 0.1
 
 
-def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np.float64):
+def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np.float64,
+                process_std=None, meas_std=None, normals=None):
     """x0 [B,5] raw initial state, ref [B,T] physical reference per step.
-    Returns (meas [B,T+1,5], u [B,T]); meas[:,0] = x0 as given (Functions.py:1134-1138)."""
+    Returns (meas [B,T+1,5], u [B,T]); meas[:,0] = x0 as given (Functions.py:1134-1138).
+
+    Noise (NeuralNetwork.loop, UL/Functions.py:1176-1183 -> do-mpc ``Simulator.make_step(u0, v0, w0)``):
+    ``x_next = integrate(x, u) + w0``, ``y = measurement(x_next) + v0``, the controller reads ``y``.  ``normals``
+    [B, 3T, 4] are the standard normals of the kernels' generator (mpc_loss_oracle.philox_normal4(seed, B, 3T)):
+    step k uses the 12 values normals[:, 3k:3k+3].reshape(B,12): w0 = process_std * [0:5], v0 = meas_std * [5:10]."""
     x = np.asarray(x0, dtype=dtype).copy()
     Bn, T = ref.shape
     meas = np.empty((Bn, T + 1, 5), dtype)
     us = np.empty((Bn, T), dtype)
     meas[:, 0] = x
+    y = x
     for k in range(T):
-        u = controller_step(fnn, scale_in, scale_out, x[:, 1].astype(np.float64), x[:, 4].astype(np.float64), ref[:, k])
+        u = controller_step(fnn, scale_in, scale_out, y[:, 1].astype(np.float64), y[:, 4].astype(np.float64), ref[:, k])
         us[:, k] = u
         x = rk4_step(x, u.astype(dtype), ts, substeps)
-        meas[:, k + 1] = measurement(x)
+        if normals is not None:
+            e = normals[:, 3 * k:3 * k + 3].reshape(Bn, 12)
+            x = x + (np.asarray(process_std, np.float32)[None, :] * e[:, 0:5].astype(np.float32)).astype(dtype)
+            y = measurement(x) + (np.asarray(meas_std, np.float32)[None, :] * e[:, 5:10].astype(np.float32)).astype(dtype)
+        else:
+            y = measurement(x)
+        meas[:, k + 1] = y
     return meas, us

@@ -127,3 +127,31 @@ def test_large_batch_properties(golden_weights):
     # isolated trajectories separate after if_else switching events (stiff plant), hence the looser tail
     assert err[:, 1].max() < 1e-4 and np.median(err) < 1e-5 and np.percentile(err, 90) < 1e-4
     assert np.percentile(err, 99) < 5e-3
+
+
+def test_process_and_measurement_noise_match_oracle_with_the_same_normals(golden_weights):
+    """NeuralNetwork.loop's noise (UL/Functions.py:1176-1183): x_next += w0, y = measurement(x_next) + v0, controller
+    reads y.  The kernel's counter-based normals are restated in the oracle, so the noisy loop is checked step by step."""
+    import mpc_loss_oracle as O
+    ctl, fnn = _ctl(golden_weights)
+    si, so = golden_weights["scale/scaler_input"], golden_weights["scale/scaler_output"]
+    dev = torch.device("cuda:0")
+    B, T, seed = 64, 40, 0xABCDEF987
+    x0, seg = _inputs(B, T, seed=5)
+    ref = np.repeat(seg, 150, axis=1)[:, :T]
+    pstd = np.array([1e-5, 1e-3, 2e3, 2e3, 1e-4])
+    mstd = np.array([1e-5, 2e-3, 1e3, 1e3, 2e-4])
+    meas, u, xf = fb.closed_loop_device(ctl, torch.tensor(x0, dtype=torch.float64).to(dev), torch.tensor(ref.T.copy(), dtype=torch.float64).to(dev),
+                                        1e-3, si, so, 4, 1, process_std=pstd, meas_std=mstd, noise_seed=seed)
+    clean, _, _ = fb.closed_loop_device(ctl, torch.tensor(x0, dtype=torch.float64).to(dev), torch.tensor(ref.T.copy(), dtype=torch.float64).to(dev),
+                                        1e-3, si, so, 4, 1)
+    normals = O.philox_normal4(seed, B, 3 * T)
+    m_ref, u_ref = P.closed_loop(fnn, si, so, x0, ref, 1e-3, 4, np.float64, pstd, mstd, normals)
+    got = meas.permute(2, 0, 1).cpu().numpy()
+    err = np.abs(got - m_ref) / P.STATE_SCALE
+    assert err[:, 1].max() < 1e-6                          # first noisy step: same normals, same arithmetic
+    assert np.median(err) < 1e-6 and np.percentile(err, 99) < 1e-4
+    diff = np.abs(got - clean.permute(2, 0, 1).cpu().numpy()) / P.STATE_SCALE
+    assert diff[:, 1:].max() > 1e-5                        # the noise is there
+    # measurement-noise statistics of the logged y_dot against the noiseless measurement of the same noisy state
+    assert np.abs(u.t().cpu().numpy() - u_ref).max() < 5e-3
