@@ -4,6 +4,7 @@ deployment roll-out, behind the reference's own Python API (see ``Functions.py``
 from . import _native
 from .Functions import (Data, FNNModel, FeasibilityRecovery, LSTMModel, MPCLoss, NeuralNetwork,
                         mpc_loss_native, pack_weights, lstm_shadow_native)
+from .dataset import DeviceSequenceLoader, build_windows
 from .closed_loop import closed_loop_device, closed_loop_rollout, tvp_reference_table
 from .distributed import allreduce_loss_and_grads, shard_bounds, sharded_training_step
 

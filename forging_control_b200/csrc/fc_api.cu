@@ -363,6 +363,37 @@ __global__ void __launch_bounds__(1024) mpc_finalize_kernel(const double* __rest
   if (threadIdx.x > kNumFnnGrad && threadIdx.x < 256) gl[threadIdx.x] = 0.f;
 }
 
+// Training-sample construction on the device: SequenceDataset.__getitem__ (UL/Functions.py:109-132) over the
+// per-trajectory slices of Data.get_individual_dataset (:479-516), for a batch of global sample indices.
+// Pure gather (bit-exact); one thread per output float, outputs written coalesced.
+// I = index type of the element loop (unsigned when everything fits 32 bits: the divisions are the cost here),
+// LB = compile-time look-back (10 in the reference) or 0 = run-time value.
+template <typename I, int LB>
+__global__ void __launch_bounds__(256) build_windows_kernel(const float* __restrict__ Xtab, const float* __restrict__ ytab,
+                                                            const float* __restrict__ Ztab, I t_traj, int lookback_rt,
+                                                            const long long* __restrict__ idx, I B,
+                                                            float* __restrict__ X, float* __restrict__ y, float* __restrict__ Z) {
+  const I lookback = LB ? (I)LB : (I)lookback_rt;
+  const I zper = lookback * 5;
+  const I nz = B * zper, total = nz + B * 4;
+  // element order: all Z floats first (the bulk, contiguous [B][lookback][5]), then X [B][3], then y [B]
+  for (I e = (I)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (I)gridDim.x * blockDim.x) {
+    if (e < nz) {
+      const I s = e / zper, w = e - s * zper, r = w / 5, f = w - r * 5;
+      const I g = (I)idx[s], k = g / t_traj, i = g - k * t_traj;
+      const I back = lookback - 1 - r;                               // rows before the current one
+      const I loc = i >= back ? i - back : 0;                        // :117-123: front padding with the trajectory's row 0
+      Z[e] = __ldg(Ztab + ((size_t)k * t_traj + loc) * 5 + f);
+    } else if (e < nz + B * 3) {
+      const I q = e - nz, s = q / 3;
+      X[q] = __ldg(Xtab + (size_t)idx[s] * 3 + (q - s * 3));
+    } else {
+      const I s = e - nz - B * 3, g = (I)idx[s], k = g / t_traj, i = g - k * t_traj;
+      y[s] = __ldg(ytab + (size_t)k * t_traj + (i + 1 < t_traj ? i + 1 : t_traj - 1));   // :126-129: target of the next step
+    }
+  }
+}
+
 // register-resident FFMA loop: 8 independent chains per thread
 __global__ void __launch_bounds__(256) ffma_peak_kernel(int iters, float* sink) {
   float a[8];
@@ -672,6 +703,30 @@ int fc_closed_loop_rk4_f64_noise(const double* x0, const double* ref, int n_ref,
                                  const float* process_std, const float* meas_std, unsigned long long seed, void* stream) {
   return closed_loop_launch<double>(x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, fnn_inp_w,
                                     fnn_inp_b, fnn_out_w, meas, u, x_final, stream, process_std, meas_std, seed);
+}
+
+int fc_build_windows(const float* Xtab, const float* ytab, const float* Ztab, long long M, int t_traj, int lookback,
+                     const long long* idx, long long B, float* X, float* y, float* Z, void* stream) {
+  if (M <= 0 || t_traj <= 0 || M % t_traj != 0 || lookback <= 0 || B <= 0)
+    return fail(FC_ERR_BAD_SHAPE, "fc_build_windows: bad shape%s M=%lld B=%lld", "", M, B);
+  if (!Xtab || !ytab || !Ztab || !idx || !X || !y || !Z) return fail(FC_ERR_NULL_POINTER, "fc_build_windows: null pointer%s");
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const long long total = B * (4 + (long long)lookback * 5);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;      // grid-stride, a multiple of the SM count
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool small = M < (1ll << 31) && total < (1ll << 32) - (1ll << 24);
+  if (small && lookback == 10)
+    build_windows_kernel<unsigned, 10><<<(unsigned)blocks, 256, 0, st>>>(Xtab, ytab, Ztab, (unsigned)t_traj, lookback, idx, (unsigned)B, X, y, Z);
+  else if (small)
+    build_windows_kernel<unsigned, 0><<<(unsigned)blocks, 256, 0, st>>>(Xtab, ytab, Ztab, (unsigned)t_traj, lookback, idx, (unsigned)B, X, y, Z);
+  else
+    build_windows_kernel<unsigned long long, 0><<<(unsigned)blocks, 256, 0, st>>>(Xtab, ytab, Ztab, (unsigned long long)t_traj, lookback, idx,
+                                                                                 (unsigned long long)B, X, y, Z);
+  FC_CUDA(cudaGetLastError(), "build_windows_kernel launch");
+  return FC_OK;
 }
 
 int fc_fp32_peak(int iters, double* flops_host, void* stream) {

@@ -77,6 +77,15 @@ int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const flo
                       float* error, float* pred, float* du0, float* gl, void* workspace,
                       size_t workspace_bytes, float noise_std, unsigned long long noise_seed, void* stream);
 
+/* Training-sample construction on the device (replaces DataLoader collation of `SequenceDataset.__getitem__`,
+ * UL/Functions.py:109-132, over the per-trajectory slices of `Data.get_individual_dataset`, :479-516).  Tables
+ * Xtab [M][3], ytab [M], Ztab [M][5] = the concatenated per-trajectory datasets, M = n_traj * t_traj (device pointers);
+ * idx [B] global sample indices (device, int64, 0 <= idx < M; not checked).  Sample g = trajectory g / t_traj, step
+ * i = g % t_traj:  X[b] = Xtab[g];  Z[b] = rows max(i-lookback+1, 0)..i of the trajectory, front-padded with its
+ * row 0;  y[b] = ytab of the trajectory's next step (the last one for the final step).  Bit-exact gather.       */
+int fc_build_windows(const float* Xtab, const float* ytab, const float* Ztab, long long M, int t_traj, int lookback,
+                     const long long* idx, long long B, float* X, float* y, float* Z, void* stream);
+
 /* LSTM shadow roll-out of the closed loop (replaces the per-step `simulator_make_step` loop of
  * NeuralNetwork.loop, UL/Functions.py:969-1011 and :1196-1231): T windowed-LSTM inferences per trajectory, batched
  * over B trajectories, forward only.  The window starts as ten copies of row0[b] (scaled: x/scale_in, u_0/scale_in);

@@ -18,6 +18,8 @@ Fixtures (all small, numpy ``.npz``):
   loop, 600 steps: _x,_u,_y,_tvp,_time) = known answers for the controller step and the plant
   step; ``tvp_fun`` values (UL/Functions.py:926-966) on the same time grid; the reference's own
   ``FeasibilityRecovery.NN_make_step`` (:1560-1613) outputs on the recorded measurements.
+* ``sequence_dataset.npz``  every item of the reference's ``SequenceDataset`` (UL/Functions.py:66-132) over the
+  per-trajectory slices of ``Data.get_individual_dataset`` (:479-516) for a small random table.
 * ``trace_windows.npz``     scaled 10-row look-back windows cut from
   ``Model_NN/results/MPC_simulation.pkl`` (realistic state distribution).
 """
@@ -181,12 +183,33 @@ def make_trace(F, ctl):
     np.savez_compressed(os.path.join(OUT, "closed_loop_trace.npz"), **out)
 
 
+def make_sequence_dataset(F):
+    """Items of the reference's ``SequenceDataset`` (UL/Functions.py:66-132) over per-trajectory slices as built by
+    ``Data.get_individual_dataset`` (:479-516): 3 trajectories x 25 rows, look-back 10 -> every (x, y, z) item."""
+    import pandas as pd
+    rng = np.random.default_rng(2024)
+    n_traj, t_traj, lookback = 3, 25, 10
+    cols = ["y_dot", "p1", "p2", "z", "u", "ref"]
+    df = pd.DataFrame(rng.uniform(-1, 1, (n_traj * t_traj, len(cols))).astype(np.float32), columns=cols)
+    target, features, model_features = ["u"], ["y_dot", "z", "ref"], ["y_dot", "p1", "p2", "z", "u"]
+    datasets, _ = F.Data.get_individual_dataset(df, target, features, model_features, t_traj, lookback)
+    xs, ys, zs = [], [], []
+    for ds in datasets:
+        for i in range(len(ds)):
+            x, y, z = ds[i]
+            xs.append(x.numpy()); ys.append(y.numpy()); zs.append(z.numpy())
+    np.savez_compressed(os.path.join(OUT, "sequence_dataset.npz"), table=df.values.astype(np.float32), columns=np.array(cols),
+                        t_traj=t_traj, lookback=lookback, X=np.stack(xs), y=np.stack(ys), Z=np.stack(zs))
+    print("sequence_dataset.npz:", np.stack(xs).shape, np.stack(ys).shape, np.stack(zs).shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     F = ref_shim.load_reference_functions()
     lstm_sd, ctl = make_weights(F)
     make_cases(F, lstm_sd, ctl)
     make_trace(F, ctl)
+    make_sequence_dataset(F)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
