@@ -119,8 +119,8 @@ def _check_models(simulator: nn.Module, controller: nn.Module):
     if tuple(controller.fc_inp.weight.shape) != (50, 3) or tuple(controller.fc_out.weight.shape) != (1, 50) \
             or controller.fc_inp.bias is None:
         raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports FNNModel(3, 50, 1, width_dim, bias=True) only")
-    if getattr(controller, "width_dim", 1) != 1:
-        raise NotImplementedError("MPCLoss (fused sm_100a kernel): width_dim > 1 is not implemented yet")
+    if getattr(controller, "width_dim", 1) > 1 and (tuple(controller.fc_int.weight.shape) != (50, 50) or controller.fc_int.bias is None):
+        raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports the 50 x 50 hidden layer fc_int with bias only")
     if not isinstance(getattr(controller, "activation", None), nn.ReLU):
         raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports the ReLU controller only")
 
@@ -179,7 +179,7 @@ def _workspace(dev, nbytes: int) -> torch.Tensor:
 
 
 def mpc_loss_native(wpack, X, u0, Z, N: int, alpha: float, with_grad: bool, global_batch: int | None = None,
-                    noise_std: float = 0.0, noise_seed: int = 0):
+                    noise_std: float = 0.0, noise_seed: int = 0, int_w=None, int_b=None, width_dim: int = 1):
     """Thin wrapper over ``fc_mpc_loss`` / ``fc_mpc_loss_noise``.  X [B,3], u0 [B], Z [B,10,5] float32 CUDA,
     contiguous.  Returns dict(cost, command, error, pred [B,N], gl [256], du0 [B] or None)."""
     B = X.shape[0]
@@ -190,6 +190,22 @@ def mpc_loss_native(wpack, X, u0, Z, N: int, alpha: float, with_grad: bool, glob
     out["pred"] = torch.empty(B, N, **f32)
     out["gl"] = torch.empty(256, **f32)
     out["du0"] = torch.empty(B, **f32) if with_grad else None
+    if width_dim > 1:            # FNNModel with hidden-layer repeats: extra gradient block d fc_int.weight | d fc_int.bias
+        out["gl_wide"] = torch.zeros(2560, **f32)
+        with torch.cuda.device(dev):
+            nbytes = int(L.fc_mpc_loss_wide_workspace_bytes(B, N, int(with_grad), int(width_dim)))
+            if nbytes == 0:
+                raise RuntimeError("fc_mpc_loss_wide_workspace_bytes failed: " + L.fc_last_error().decode())
+            work = _workspace(dev, nbytes)
+            rc = L.fc_mpc_loss_wide(_native.ptr(X), _native.ptr(u0), _native.ptr(Z), _native.ptr(wpack), _native.ptr(int_w),
+                                    _native.ptr(int_b), int(width_dim), B, N, float(alpha),
+                                    int(global_batch if global_batch is not None else B), int(with_grad),
+                                    _native.ptr(out["cost"]), _native.ptr(out["command"]), _native.ptr(out["error"]),
+                                    _native.ptr(out["pred"]), _native.ptr(out["du0"]), _native.ptr(out["gl"]),
+                                    _native.ptr(out["gl_wide"]), _native.ptr(work), nbytes, float(noise_std),
+                                    int(noise_seed) & (2 ** 64 - 1), _native.stream_ptr(dev))
+        _native.check(rc, "fc_mpc_loss_wide")
+        return out
     with torch.cuda.device(dev):
         nbytes = int(L.fc_mpc_loss_workspace_bytes(B, N, int(with_grad)))
         if nbytes == 0:
@@ -210,13 +226,20 @@ class _FusedMPCLoss(torch.autograd.Function):
     linear in the upstream gradient, so ``backward`` only scales)."""
 
     @staticmethod
-    def forward(ctx, u0, inp_w, inp_b, out_w, X, Z, wpack, N, alpha, with_grad, global_batch, noise_std=0.0, noise_seed=0):
+    def forward(ctx, u0, inp_w, inp_b, out_w, X, Z, wpack, N, alpha, with_grad, global_batch, noise_std=0.0, noise_seed=0,
+                int_w=None, int_b=None, width_dim=1):
+        wide = width_dim > 1
         res = mpc_loss_native(wpack, X, u0.detach().reshape(-1).contiguous(), Z, N, alpha, with_grad, global_batch,
-                              noise_std, noise_seed)
+                              noise_std, noise_seed,
+                              int_w.detach().contiguous() if wide else None, int_b.detach().contiguous() if wide else None, width_dim)
         ctx.with_grad = with_grad
         ctx.u0_shape = u0.shape
+        ctx.wide = wide
         if with_grad:
-            ctx.save_for_backward(res["du0"], res["gl"])
+            if wide:
+                ctx.save_for_backward(res["du0"], res["gl"], res["gl_wide"])
+            else:
+                ctx.save_for_backward(res["du0"], res["gl"])
         loss = res["gl"][250].clone()
         pred = res["pred"].reshape(-1)
         ctx.mark_non_differentiable(res["cost"], res["command"], res["error"], pred)
@@ -226,11 +249,15 @@ class _FusedMPCLoss(torch.autograd.Function):
     def backward(ctx, g_loss, *unused):
         if not ctx.with_grad:
             raise RuntimeError("MPCLoss: backward called but the forward ran without gradients")
-        du0, gl = ctx.saved_tensors
+        du0, gl = ctx.saved_tensors[:2]
         g_u0 = (du0 * g_loss).reshape(ctx.u0_shape)
         g = gl * g_loss
+        g_int_w = g_int_b = None
+        if ctx.wide:
+            gw = ctx.saved_tensors[2] * g_loss
+            g_int_w, g_int_b = gw[0:2500].reshape(50, 50), gw[2500:2550]
         return (g_u0, g[0:150].reshape(50, 3), g[150:200], g[200:250].reshape(1, 50),
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, g_int_w, g_int_b, None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -269,13 +296,16 @@ class MPCLoss(nn.Module):
         Z = Z.detach().to(torch.float32).contiguous()
         wpack = pack_weights(simulator, controller)
         params = (controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight)
-        with_grad = torch.is_grad_enabled() and (u0.requires_grad or any(p.requires_grad for p in params))
+        width_dim = int(getattr(controller, "width_dim", 1))
+        wide = (controller.fc_int.weight, controller.fc_int.bias) if width_dim > 1 else (None, None)
+        with_grad = torch.is_grad_enabled() and (u0.requires_grad or any(p.requires_grad for p in params) or
+                                                 any(p is not None and p.requires_grad for p in wide))
         noise_std, noise_seed = 0.0, 0
         if enable_noise:
             noise_std, noise_seed = self.NOISE_STD, int(torch.randint(0, 2 ** 62, (1,)).item())
         loss, cost, command, error, pred = _FusedMPCLoss.apply(
             u0, *params, X, Z, wpack, int(self.N), float(self.alpha), bool(with_grad), self.global_batch,
-            float(noise_std), noise_seed)
+            float(noise_std), noise_seed, wide[0], wide[1], width_dim)
         return loss, {"loss": cost, "command": command, "error": error, "prediction": pred}
 
 

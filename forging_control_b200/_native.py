@@ -25,7 +25,7 @@ EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
            "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_closed_loop_rk4",
            "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout",
            "fc_mpc_loss_noise", "fc_closed_loop_rk4_noise", "fc_closed_loop_rk4_f64_noise",
-           "fc_build_windows")
+           "fc_build_windows", "fc_mpc_loss_wide_workspace_bytes", "fc_mpc_loss_wide")
 
 _c_float_p = ctypes.c_void_p   # raw device pointers are passed as integers
 _lib = None
@@ -89,6 +89,11 @@ def lib() -> ctypes.CDLL:
     L.fc_closed_loop_rk4_f64_noise.restype = i32
     L.fc_closed_loop_rk4_f64_noise.argtypes = [vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp, vp, vp, vp, vp, fp5, fp5,
                                                ctypes.c_ulonglong, vp]
+    L.fc_mpc_loss_wide_workspace_bytes.restype = sz
+    L.fc_mpc_loss_wide_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.fc_mpc_loss_wide.restype = i32
+    L.fc_mpc_loss_wide.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, f32,
+                                   ctypes.c_ulonglong, vp]
     L.fc_build_windows.restype = i32
     L.fc_build_windows.argtypes = [vp, vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp]
     L.fc_fp32_peak.restype = i32

@@ -394,6 +394,19 @@ __global__ void __launch_bounds__(256) build_windows_kernel(const float* __restr
   }
 }
 
+// out[i] = sum over CTAs of partial[b][i], i < n (one warp per output)
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __restrict__ partial, int grid, int stride, int n,
+                                                            float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 32 + warp; i < n; i += gridDim.x * 32) {
+    double a = 0.0;
+    for (int b = lane; b < grid; b += 32) a += partial[(size_t)b * stride + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[i] = (float)a;
+  }
+}
+
 // register-resident FFMA loop: 8 independent chains per thread
 __global__ void __launch_bounds__(256) ffma_peak_kernel(int iters, float* sink) {
   float a[8];
@@ -471,20 +484,22 @@ struct MpcPlan {
 // 7.6 ms for the FFMA kernel; B=4096: 0.94 ms against 1.6 ms for the pair kernel, which would leave SMs idle); beyond
 // that the pair kernel, which keeps two tiles per CTA in flight, wins (B=524288: 80 M against 73 M trajectory-steps/s;
 // the FFMA kernel reaches 23 M).  All three stay selectable (fc_mpc_select_kernel / FC_MPC_KERNEL).
-static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl) {
+static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
   pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
   if (mode == 0 && (B + tc::kTileTC - 1) / tc::kTileTC > sms) pl->kind = 2;
+  if (width_dim > 1) pl->kind = 1;        // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
   const int tile = pl->kind ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
   const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
   pl->grid = units < sms ? units : sms;
   pl->work_stride = pl->kind == 2 ? pr::kTiles * pr::work_layout_p(N, with_grad).total
-                                  : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad).total : work_layout(N, with_grad).total);
+                                  : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad, width_dim).total : work_layout(N, with_grad).total);
   pl->bytes = (size_t)pl->grid * kPartialStride * sizeof(double) + (size_t)pl->grid * pl->work_stride * sizeof(float);
+  if (width_dim > 1) pl->bytes += (size_t)pl->grid * kWidePartialStride * sizeof(double);
   return FC_OK;
 }
 
@@ -565,10 +580,41 @@ int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wp
                            workspace_bytes, 0.0f, 0ull, stream);
 }
 
+static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                         long long B_global, int with_grad, float* cost, float* command, float* error, float* pred, float* du0,
+                         float* gl, void* workspace, size_t workspace_bytes, float noise_std, unsigned long long noise_seed,
+                         const float* int_w, const float* int_b, int width_dim, float* gl_wide, void* stream);
+
 int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
                       long long B_global, int with_grad, float* cost, float* command, float* error, float* pred, float* du0,
                       float* gl, void* workspace, size_t workspace_bytes, float noise_std, unsigned long long noise_seed,
                       void* stream) {
+  return mpc_loss_impl(X, u0, Z, wpack, B, N, alpha, B_global, with_grad, cost, command, error, pred, du0, gl, workspace,
+                       workspace_bytes, noise_std, noise_seed, nullptr, nullptr, 1, nullptr, stream);
+}
+
+size_t fc_mpc_loss_wide_workspace_bytes(int B, int N, int with_grad, int width_dim) {
+  if (B <= 0 || N <= 0 || width_dim < 1) return 0;
+  MpcPlan pl;
+  if (mpc_plan(B, N, with_grad, &pl, width_dim)) return 0;
+  return pl.bytes;
+}
+
+int fc_mpc_loss_wide(const float* X, const float* u0, const float* Z, const float* wpack, const float* fnn_int_w,
+                     const float* fnn_int_b, int width_dim, int B, int N, float alpha, long long B_global, int with_grad,
+                     float* cost, float* command, float* error, float* pred, float* du0, float* gl, float* gl_wide,
+                     void* workspace, size_t workspace_bytes, float noise_std, unsigned long long noise_seed, void* stream) {
+  if (width_dim < 1 || width_dim > 64) return fail(FC_ERR_UNSUPPORTED, "fc_mpc_loss_wide: width_dim%s=%lld out of range", "", width_dim);
+  if (width_dim > 1 && (!fnn_int_w || !fnn_int_b || (with_grad && !gl_wide)))
+    return fail(FC_ERR_NULL_POINTER, "fc_mpc_loss_wide: null pointer%s");
+  return mpc_loss_impl(X, u0, Z, wpack, B, N, alpha, B_global, with_grad, cost, command, error, pred, du0, gl, workspace,
+                       workspace_bytes, noise_std, noise_seed, fnn_int_w, fnn_int_b, width_dim, gl_wide, stream);
+}
+
+static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                         long long B_global, int with_grad, float* cost, float* command, float* error, float* pred, float* du0,
+                         float* gl, void* workspace, size_t workspace_bytes, float noise_std, unsigned long long noise_seed,
+                         const float* int_w, const float* int_b, int width_dim, float* gl_wide, void* stream) {
   if (!(noise_std >= 0.f)) return fail(FC_ERR_BAD_SHAPE, "fc_mpc_loss: noise_std%s must be >= 0");
   if (B <= 0 || N <= 0 || B_global < B) return fail(FC_ERR_BAD_SHAPE, "fc_mpc_loss: bad shape%s B=%lld N=%lld", "", B, N);
   if (N > 4096) return fail(FC_ERR_UNSUPPORTED, "fc_mpc_loss: horizon%s N=%lld too long", "", N);
@@ -577,7 +623,7 @@ int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const flo
   if (!aligned16(wpack) || !aligned16(workspace))
     return fail(FC_ERR_MISALIGNED, "fc_mpc_loss: wpack/workspace must be 16-byte aligned%s");
   MpcPlan pl;
-  int rc = mpc_plan(B, N, with_grad, &pl);
+  int rc = mpc_plan(B, N, with_grad, &pl, width_dim);
   if (rc) return rc;
   if (workspace_bytes < pl.bytes)
     return fail(FC_ERR_WORKSPACE, "fc_mpc_loss: workspace too small%s: have %lld need %lld bytes", "", (long long)workspace_bytes,
@@ -586,7 +632,7 @@ int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const flo
   if (!attr_set) {
     FC_CUDA(cudaFuncSetAttribute(mpc_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes),
             "cudaFuncSetAttribute(smem)");
-    FC_CUDA(cudaFuncSetAttribute(mpc_loss_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmBytesTC),
+    FC_CUDA(cudaFuncSetAttribute(mpc_loss_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmBytesWide),
             "cudaFuncSetAttribute(smem, tc)");
     FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
             "cudaFuncSetAttribute(smem, pair)");
@@ -598,7 +644,10 @@ int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const flo
   p.wpack = pl.kind == 2 ? wpack + kPackFloats + tc::kPackFloatsTC : (pl.kind == 1 ? wpack + kPackFloats : wpack);
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.partial = reinterpret_cast<double*>(workspace);
-  p.work = reinterpret_cast<float*>(p.partial + (size_t)pl.grid * kPartialStride);
+  p.width_dim = width_dim; p.int_w = int_w; p.int_b = int_b;
+  double* after_partial = p.partial + (size_t)pl.grid * kPartialStride;
+  if (width_dim > 1) { p.partial_wide = after_partial; after_partial += (size_t)pl.grid * kWidePartialStride; }
+  p.work = reinterpret_cast<float*>(after_partial);
   p.work_stride = pl.work_stride;
   p.B = B; p.N = N; p.with_grad = with_grad ? 1 : 0; p.num_tiles = pl.tiles;
   p.alpha = alpha;
@@ -616,11 +665,15 @@ int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const flo
   p.noise_std = noise_std; p.noise_seed = noise_seed;
   cudaStream_t st = (cudaStream_t)stream;
   if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
-  else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, tc::kSmBytesTC, st>>>(p);
+  else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, width_dim > 1 ? tc::kSmBytesWide : tc::kSmBytesTC, st>>>(p);
   else mpc_loss_kernel<<<pl.grid, kThreads, kSmBytes, st>>>(p);
   FC_CUDA(cudaGetLastError(), "mpc_loss kernel launch");
   mpc_finalize_kernel<<<1, 1024, 0, st>>>(p.partial, pl.grid, 1.0 / (double)B_global, gl);
   FC_CUDA(cudaGetLastError(), "mpc_finalize_kernel launch");
+  if (width_dim > 1 && with_grad) {
+    sum_partials_kernel<<<8, 1024, 0, st>>>(p.partial_wide, pl.grid, kWidePartialStride, kWideGrads, gl_wide);
+    FC_CUDA(cudaGetLastError(), "sum_partials_kernel launch");
+  }
   return FC_OK;
 }
 

@@ -149,6 +149,8 @@ FC_HD WorkLayout work_layout(int N, int with_grad) {
 // per-CTA partial results (double precision: the batch reductions are cancellation-heavy): controller
 // gradients then loss sum
 constexpr int kNumFnnGrad = 250;            // inp_w[150] | inp_b[50] | out_w[50]
+constexpr int kWideGrads = kFnnHid * kFnnHid + kFnnHid;   // 2550: fc_int.weight | fc_int.bias
+constexpr int kWidePartialStride = 2560;
 constexpr int kPartialStride = 256;         // [0..249] grads, [250] sum of per-trajectory cost
 
 // ---- shared memory carve-up (floats) ---------------------------------------------------------------
@@ -201,6 +203,12 @@ struct MpcParams {
   int debug_timing;      // CTA 0 prints a cycle breakdown (development aid)
   float g_scale;         // tcgen05 kernel: power-of-two scale of the gate gradients before the fp16 split
   float g_unscale;       // 1 / g_scale
+  // width_dim > 1 controllers (FNNModel.forward, UL/Functions.py:261-289: width_dim-1 repeats of the weight-shared
+  // fc_int + ReLU); one-tile tcgen05 kernel only
+  int width_dim;            // 1 = no hidden repeat
+  const float* int_w;       // fc_int.weight [50][50]
+  const float* int_b;       // fc_int.bias [50]
+  double* partial_wide;     // [grid][kWidePartialStride]: d loss / d fc_int.weight [2500] | fc_int.bias [50]
   // enable_noise (UL/Functions.py:1400-1402, :1438-1440): x += noise_std * N(0,1) after every surrogate call;
   // counter-based generator (Philox4x32-10, key = seed, counter = (trajectory, window)), see philox_normal4
   float noise_std;

@@ -24,7 +24,7 @@ struct MpcTileTC {
   float* sm;
   int tid, warp, lane, row, quarter, nown, u_first;
   bool full;             // this quarter owns 13 units (else 12: unit slot 12 is a masked dummy)
-  float *rows, *seq, *dseq, *grow, *rec;
+  float *rows, *seq, *dseq, *grow, *rec, *actg;
   float c[kMaxOwn];      // forward: cell state, backward: d(cell state)
   float hrec[kMaxOwn];   // backward: d(h) from step t+1
   unsigned ph[8];        // completed phases per mbarrier
@@ -42,13 +42,14 @@ struct MpcTileTC {
     nown = units_of(quarter);
     u_first = first_unit(quarter);
     full = nown == kMaxOwn;
-    WorkLayoutTC wl = work_layout_tc(p.N, p.with_grad);
+    WorkLayoutTC wl = work_layout_tc(p.N, p.with_grad, p.width_dim);
     float* base = p.work + (size_t)ctx.bid() * p.work_stride;
     rows = base + wl.rows;
     seq = base + wl.seq;
     dseq = base + wl.dseq;
     grow = base + wl.grow;
     rec = base + wl.rec;
+    actg = base + wl.act;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ph[i] = 0;
 #ifdef FC_TC_TIMING
@@ -339,8 +340,12 @@ struct MpcTileTC {
       }
     }
     lap(0);
-    if (quarter == 0) fwd_glue(tile, m);
-    ctx.sync();
+    if (p.width_dim > 1) {
+      fwd_glue_wide(tile, m);
+    } else {
+      if (quarter == 0) fwd_glue(tile, m);
+      ctx.sync();
+    }
     lap(10);
   }
 
@@ -389,6 +394,237 @@ struct MpcTileTC {
       if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;                    // :1455
     }
     rnew[4 * kTileTC] = unext;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // width_dim > 1 controllers (FNNModel.forward, UL/Functions.py:261-289): the hidden layer fc_int + ReLU is applied
+  // width_dim - 1 times with shared weights.  All 512 threads take part: thread (row, quarter) computes the units of
+  // its quarter for its trajectory; layers are separated by CTA barriers; buffers are [50][129] in shared memory.
+  // ---------------------------------------------------------------------------------------------
+  FC_HD_CTX float* wide_buf(int i) const { return sm + kSmWideA + i * kActFloats; }
+  FC_HD_CTX void wide_layer0(float* dst) {                   // a_0 = ReLU(fc_inp(x0, x3, ref))
+    const float* sw = sm + kSmSmallTC;
+    const float* iw = sw + (kINPW - kFCW);
+    const float* ib = sw + (kINPB - kFCW);
+    const float x0 = sm[kSmWideIn + row], x3 = sm[kSmWideIn + kTileTC + row], ref = sm[kSmWideIn + 2 * kTileTC + row];
+    for (int j = 0; j < nown; ++j) {
+      const int u = u_first + j;
+      const float pre = fmaf(iw[u * 3 + 2], ref, fmaf(iw[u * 3 + 1], x3, fmaf(iw[u * 3 + 0], x0, ib[u])));
+      dst[u * kActStride + row] = fmaxf(pre, 0.f);
+    }
+  }
+  FC_HD_CTX void wide_hidden(const float* src, float* dst) { // a_r = ReLU(fc_int(a_{r-1}))
+    const float* wi = sm + kSmWideW;
+    const float* bi = wi + kFnnHid * kFnnHid;
+    for (int j = 0; j < nown; ++j) {
+      const int i = u_first + j;
+      float pre = bi[i];
+      for (int k = 0; k < kFnnHid; ++k) pre = fmaf(wi[i * kFnnHid + k], src[k * kActStride + row], pre);
+      dst[i * kActStride + row] = fmaxf(pre, 0.f);
+    }
+  }
+  FC_HD_CTX float wide_output(const float* a) const {        // fc_out (no bias)
+    const float* ow = sm + kSmSmallTC + (kOUTW - kFCW);
+    float v = 0.f;
+    for (int u = 0; u < kFnnHid; ++u) v = fmaf(ow[u], a[u * kActStride + row], v);
+    return v;
+  }
+  // all layers; with `keep` every a_r also goes to the global scratch actg[r][u][row].  Returns the buffer index of a_R.
+  FC_HD_CTX int wide_forward(bool keep) {
+    int cur = 0;
+    wide_layer0(wide_buf(0));
+    ctx.sync();
+    if (keep)
+      for (int j = 0; j < nown; ++j) actg[(size_t)(u_first + j) * kTileTC + row] = wide_buf(0)[(u_first + j) * kActStride + row];
+    for (int r = 1; r < p.width_dim; ++r) {
+      wide_hidden(wide_buf(cur), wide_buf(cur ^ 1));
+      ctx.sync();
+      cur ^= 1;
+      if (keep)
+        for (int j = 0; j < nown; ++j)
+          actg[((size_t)r * kFnnHid + u_first + j) * kTileTC + row] = wide_buf(cur)[(u_first + j) * kActStride + row];
+    }
+    return cur;
+  }
+
+  FC_HD_CTX void fwd_glue_wide(int tile, int m) {
+    float unext = 0.f;
+    float* rnew = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;
+    float ucur = 0.f;
+    if (quarter == 0) {                                      // read-out, cost terms: as fwd_glue
+      const float* sw = sm + kSmSmallTC;
+      float x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        x[q] = ((hrec[q] + sm[kSmFcpTC + q * kTileTC + row]) + (sm[kSmFcpTC + (4 + q) * kTileTC + row] + sm[kSmFcpTC + (8 + q) * kTileTC + row])) +
+               sw[(kFCB - kFCW) + q];
+      if (p.noise_std > 0.f) {
+        float e[4];
+        philox_normal4(p.noise_seed, (unsigned)(tile * kTileTC + row), (unsigned)m, e);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
+      }
+      const float ref = sm[kSmRefTC + row];
+      ucur = sm[kSmUcurTC + row];
+      const float uprev = sm[kSmUprevTC + row];
+      float du = uprev - ucur;
+      float cmd = p.alpha * du * du;
+      float er = (x[0] - ref) * (x[0] - ref);
+      float con = fmaxf(-x[1], 0.f) + fmaxf(-x[2], 0.f) + fmaxf(x[1] - kP1Max, 0.f) + fmaxf(x[2] - kP2Max, 0.f);
+      sm[kSmCostTC + row] += (er + cmd) + con;
+      sm[kSmCostTC + kTileTC + row] += cmd;
+      sm[kSmCostTC + 2 * kTileTC + row] += er;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rnew[q * kTileTC] = x[q];
+      sm[kSmWideIn + row] = x[0];
+      sm[kSmWideIn + kTileTC + row] = x[3];
+      sm[kSmWideIn + 2 * kTileTC + row] = ref;
+    }
+    ctx.sync();
+    if (m + 1 < p.N) {
+      const int cur = wide_forward(false);
+      if (quarter == 0) {
+        unext = fminf(fmaxf(wide_output(wide_buf(cur)), -1.f), 1.f);           // nn.Hardtanh
+        sm[kSmUprevTC + row] = ucur;
+        sm[kSmUcurTC + row] = unext;
+        int b = tile * kTileTC + row;
+        if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;
+      }
+    }
+    if (quarter == 0) rnew[4 * kTileTC] = unext;
+    ctx.sync();
+  }
+
+  // reverse: recompute the activations, then delta_R = dv * fc_out * ReLU', delta_{r-1} = ReLU' * fc_int^T delta_r;
+  // gradients of fc_int (weight-shared: summed over the repeats), fc_inp, fc_out accumulated in fp64 per CTA
+  FC_HD_CTX void bwd_glue_wide(int tile, int m) {
+    const int k = m + 1;
+    const float s = p.grad_scale;
+    const bool has_u = k <= p.N - 1;
+    const float* sw = sm + kSmSmallTC;
+    const float* iw = sw + (kINPW - kFCW);
+    const float* ow = sw + (kOUTW - kFCW);
+    const float* wi = sm + kSmWideW;
+    const bool valid = tile * kTileTC + row < p.B;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, gu = 0.f;
+    if (quarter == 0) {
+      const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;
+      float x0 = Ctx::ldcg(rx), x1 = Ctx::ldcg(rx + kTileTC), x2 = Ctx::ldcg(rx + 2 * kTileTC), x3 = Ctx::ldcg(rx + 3 * kTileTC);
+      const float ref = sm[kSmRefTC + row];
+      g0 = 2.f * (x0 - ref) * s;
+      g1 = s * ((x1 > kP1Max ? 1.f : 0.f) - (x1 < 0.f ? 1.f : 0.f));
+      g2 = s * ((x2 > kP2Max ? 1.f : 0.f) - (x2 < 0.f ? 1.f : 0.f));
+      if (has_u) {
+        const float* gr = grow + (size_t)k * kFeat * kTileTC + row;
+        float uk = Ctx::ldcg(rows + (size_t)((kLook - 1 + k) * kFeat + 4) * kTileTC + row);
+        float ukm1 = Ctx::ldcg(rows + (size_t)((kLook - 2 + k) * kFeat + 4) * kTileTC + row);
+        gu = Ctx::ldcg(gr + 4 * kTileTC) - 2.f * p.alpha * (ukm1 - uk) * s;
+        if (k + 1 <= p.N - 1) {
+          float ukp1 = Ctx::ldcg(rows + (size_t)((kLook + k) * kFeat + 4) * kTileTC + row);
+          gu += 2.f * p.alpha * (uk - ukp1) * s;
+        }
+        g0 += Ctx::ldcg(gr);
+        g1 += Ctx::ldcg(gr + kTileTC);
+        g2 += Ctx::ldcg(gr + 2 * kTileTC);
+        g3 += Ctx::ldcg(gr + 3 * kTileTC);
+        sm[kSmWideIn + row] = x0;
+        sm[kSmWideIn + kTileTC + row] = x3;
+        sm[kSmWideIn + 2 * kTileTC + row] = ref;
+      }
+    }
+    ctx.sync();
+    if (has_u) {
+      const int R = p.width_dim - 1;
+      const int top = wide_forward(true);                    // a_R in wide_buf(top), every a_r in actg
+      if (quarter == 0) {
+        const float v = wide_output(wide_buf(top));
+        sm[kSmDvTC + row] = (valid && v > -1.f && v < 1.f) ? gu : 0.f;         // hardtanh_backward
+      }
+      ctx.sync();
+      // fc_out gradient (needs a_R) and delta_R; buffers: cur = deltas, nxt = next deltas, stage = a_{r-1}
+      if (tid < 4 * kFnnHid) {
+        const int u = tid % kFnnHid, part = tid / kFnnHid;
+        double a_ow = 0.0;
+        for (int tr = part * 32; tr < part * 32 + 32; ++tr)
+          a_ow += (double)sm[kSmDvTC + tr] * (double)wide_buf(top)[u * kActStride + tr];
+        reinterpret_cast<double*>(sm + kSmPgTC)[part * kNumFnnGrad + 200 + u] += a_ow;
+      }
+      int cur = top ^ 1;                                     // free buffer
+      {
+        const float dv = sm[kSmDvTC + row];
+        for (int j = 0; j < nown; ++j) {
+          const int i = u_first + j;
+          wide_buf(cur)[i * kActStride + row] = wide_buf(top)[i * kActStride + row] > 0.f ? dv * ow[i] : 0.f;
+        }
+      }
+      ctx.sync();
+      int nxt = top;                                         // a_R no longer needed
+      float* stage = wide_buf(2);
+      double* acc = reinterpret_cast<double*>(sm + kSmWideAcc);
+      for (int r = R; r >= 1; --r) {
+        // stage a_{r-1} (global scratch -> shared, padded stride)
+        for (int e = tid; e < kFnnHid * kTileTC; e += kThreadsTC) {
+          const int u = e / kTileTC, tr = e - u * kTileTC;
+          stage[u * kActStride + tr] = Ctx::ldcg(actg + ((size_t)(r - 1) * kFnnHid + u) * kTileTC + tr);
+        }
+        ctx.sync();
+        // d fc_int.weight[i][j] += sum_tr delta_r[i][tr] * a_{r-1}[j][tr];  d fc_int.bias[i] += sum_tr delta_r[i][tr]
+        for (int e = tid; e < kWideGrads; e += kThreadsTC) {
+          double a = 0.0;
+          if (e < kFnnHid * kFnnHid) {
+            const int i = e / kFnnHid, j = e - i * kFnnHid;
+            for (int tr = 0; tr < kTileTC; ++tr) a += (double)wide_buf(cur)[i * kActStride + tr] * (double)stage[j * kActStride + tr];
+          } else {
+            const int i = e - kFnnHid * kFnnHid;
+            for (int tr = 0; tr < kTileTC; ++tr) a += (double)wide_buf(cur)[i * kActStride + tr];
+          }
+          acc[e] += a;
+        }
+        // delta_{r-1}[j] = ReLU'(a_{r-1}[j]) * sum_i fc_int.weight[i][j] * delta_r[i]
+        for (int jj = 0; jj < nown; ++jj) {
+          const int j = u_first + jj;
+          float sacc = 0.f;
+          for (int i = 0; i < kFnnHid; ++i) sacc = fmaf(wi[i * kFnnHid + j], wide_buf(cur)[i * kActStride + row], sacc);
+          wide_buf(nxt)[j * kActStride + row] = stage[j * kActStride + row] > 0.f ? sacc : 0.f;
+        }
+        ctx.sync();
+        const int t = cur; cur = nxt; nxt = t;
+      }
+      // cur = delta_0: input gradient of the controller and fc_inp gradients
+      if (quarter == 0) {
+        float d0 = 0.f, d1 = 0.f;
+        for (int u = 0; u < kFnnHid; ++u) {
+          const float dp = wide_buf(cur)[u * kActStride + row];
+          d0 = fmaf(dp, iw[u * 3 + 0], d0);
+          d1 = fmaf(dp, iw[u * 3 + 1], d1);
+        }
+        g0 += d0;
+        g3 += d1;
+      }
+      if (tid < 4 * kFnnHid) {
+        const int u = tid % kFnnHid, part = tid / kFnnHid;
+        double a_b = 0.0, a_w0 = 0.0, a_w1 = 0.0, a_w2 = 0.0;
+        for (int tr = part * 32; tr < part * 32 + 32; ++tr) {
+          const float dp = wide_buf(cur)[u * kActStride + tr];
+          a_b += dp;
+          a_w0 += (double)dp * (double)sm[kSmWideIn + tr];
+          a_w1 += (double)dp * (double)sm[kSmWideIn + kTileTC + tr];
+          a_w2 += (double)dp * (double)sm[kSmWideIn + 2 * kTileTC + tr];
+        }
+        double* pg = reinterpret_cast<double*>(sm + kSmPgTC) + part * kNumFnnGrad;
+        pg[u * 3 + 0] += a_w0;
+        pg[u * 3 + 1] += a_w1;
+        pg[u * 3 + 2] += a_w2;
+        pg[150 + u] += a_b;
+      }
+    }
+    if (quarter == 0) {
+      if (!valid) { g0 = g1 = g2 = g3 = 0.f; }
+      sm[kSmGxTC + row] = g0;
+      sm[kSmGxTC + kTileTC + row] = g1;
+      sm[kSmGxTC + 2 * kTileTC + row] = g2;
+      sm[kSmGxTC + 3 * kTileTC + row] = g3;
+    }
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -579,7 +815,8 @@ struct MpcTileTC {
     const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
     const float unscale_b = p.g_unscale / kScaleW;         // exact power of two
     lap(0);
-    bwd_glue(tile, m);
+    if (p.width_dim > 1) bwd_glue_wide(tile, m);
+    else bwd_glue(tile, m);
     ctx.sync();
     lap(11);
     for (int l = kLayers - 1; l >= 0; --l) {
@@ -713,6 +950,11 @@ struct MpcTileTC {
 #endif
     for (int i = tid; i < kSmallFloats; i += kThreadsTC) sm[kSmSmallTC + i] = p.wpack[kSmallOff + i];
     for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsTC) reinterpret_cast<double*>(sm + kSmPgTC)[i] = 0.0;
+    if (p.width_dim > 1) {
+      for (int i = tid; i < kFnnHid * kFnnHid; i += kThreadsTC) sm[kSmWideW + i] = p.int_w[i];
+      for (int i = tid; i < kFnnHid; i += kThreadsTC) sm[kSmWideW + kFnnHid * kFnnHid + i] = p.int_b[i];
+      for (int i = tid; i < kWideGrads; i += kThreadsTC) reinterpret_cast<double*>(sm + kSmWideAcc)[i] = 0.0;
+    }
     if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedTC) = 0.0;
     ctx.sync();
     if (tid == 0 && ctx.bid() < p.num_tiles) request_weights(false, 0);
@@ -740,6 +982,10 @@ struct MpcTileTC {
     for (int i = tid; i < kNumFnnGrad; i += kThreadsTC)
       part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
     if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedTC);
+    if (p.width_dim > 1 && p.with_grad) {
+      double* pw = p.partial_wide + (size_t)ctx.bid() * kWidePartialStride;
+      for (int i = tid; i < kWideGrads; i += kThreadsTC) pw[i] = reinterpret_cast<const double*>(sm + kSmWideAcc)[i];
+    }
     ctx.sync();
 #ifdef FC_TC_TIMING
     if (p.debug_timing && tid == 0 && ctx.bid() == 0) Ctx::report(tm);

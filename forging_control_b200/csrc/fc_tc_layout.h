@@ -157,9 +157,11 @@ constexpr int kSlot = kWarpsTC * kMaxOwn * 32;               // 6656
 constexpr int kRecF4 = 17;
 constexpr int kRecFloatsTC = kWarpsTC * kRecF4 * 32 * 4;    // 34816
 struct WorkLayoutTC {
-  size_t rows, seq, dseq, grow, rec, total;
+  size_t rows, seq, dseq, grow, rec, total, act;
 };
-FC_HD WorkLayoutTC work_layout_tc(int N, int with_grad) {
+constexpr int kActStride = kTileTC + 1;                      // padded row stride of the [50][128] controller buffers
+constexpr int kActFloats = kFnnHid * kActStride;             // 6450
+FC_HD WorkLayoutTC work_layout_tc(int N, int with_grad, int width_dim = 1) {
   WorkLayoutTC w;
   w.rows = 0;
   w.seq = w.rows + (size_t)(N + kLook) * kFeat * kTileTC;
@@ -168,6 +170,9 @@ FC_HD WorkLayoutTC work_layout_tc(int N, int with_grad) {
   w.rec = w.grow + (with_grad ? (size_t)N * kFeat * kTileTC : 0);
   w.rec = (w.rec + 31) / 32 * 32;
   w.total = w.rec + (with_grad ? (size_t)rec_base(N) * kRecFloatsTC : 0);
+  w.total = (w.total + 31) / 32 * 32;
+  w.act = w.total;                                            // width_dim > 1: hidden activations a_0..a_R, [R+1][50][128]
+  if (width_dim > 1 && with_grad) w.total += (size_t)width_dim * kFnnHid * kTileTC;
   w.total = (w.total + 31) / 32 * 32;
   return w;
 }
@@ -191,6 +196,14 @@ constexpr int kSmWFloats = kNB * kKB;                       // hi + lo fp16 imag
 constexpr int kSmFloatsTC = kSmWTC + kSmWFloats;
 constexpr size_t kSmBytesTC = (size_t)kSmFloatsTC * sizeof(float);
 static_assert(kSmBytesTC <= 227 * 1024, "shared memory budget exceeded (tcgen05 variant)");
+// width_dim > 1 controllers: extra shared memory behind the operand image (only launches with width_dim > 1 ask for it)
+constexpr int kSmWideW = kSmFloatsTC;                         // fc_int.weight [50][50] | fc_int.bias [50] (+2 pad)
+constexpr int kSmWideIn = kSmWideW + kFnnHid * kFnnHid + kFnnHid + 2;   // [3][128] controller inputs x0, x3, ref
+constexpr int kSmWideA = kSmWideIn + 3 * kTileTC;             // three [50][129] buffers (activations / deltas / staging)
+constexpr int kSmWideAcc = ((kSmWideA + 3 * kActFloats + 1) / 2) * 2;   // double [2550] gradient accumulators
+constexpr int kSmFloatsWide = kSmWideAcc + 2 * kWideGrads;
+constexpr size_t kSmBytesWide = (size_t)kSmFloatsWide * sizeof(float);
+static_assert(kSmBytesWide <= 227 * 1024, "shared memory budget exceeded (tcgen05 variant, wide controller)");
 static_assert(kNF * kKF <= kSmWFloats, "forward image does not fit");
 
 // Expected-value compensation of the tensor-core accumulator.  tcgen05.mma adds every K-block into the fp32

@@ -76,6 +76,16 @@ int fc_mpc_loss_noise(const float* X, const float* u0, const float* Z, const flo
                       float alpha, long long B_global, int with_grad, float* cost, float* command,
                       float* error, float* pred, float* du0, float* gl, void* workspace,
                       size_t workspace_bytes, float noise_std, unsigned long long noise_seed, void* stream);
+/* Controllers with hidden-layer repeats, FNNModel(width_dim > 1) (UL/Functions.py:261-289: fc_int + ReLU applied
+ * width_dim - 1 times with shared weights).  fnn_int_w [50][50], fnn_int_b [50] device pointers; gl_wide [2560] receives
+ * d loss / d fc_int.weight (2500, row-major) then d loss / d fc_int.bias (50).  Runs in the one-tile tcgen05 kernel.
+ * width_dim = 1 is fc_mpc_loss_noise (fnn_int_*, gl_wide may be NULL).                                          */
+size_t fc_mpc_loss_wide_workspace_bytes(int B, int N, int with_grad, int width_dim);
+int fc_mpc_loss_wide(const float* X, const float* u0, const float* Z, const float* wpack, const float* fnn_int_w,
+                     const float* fnn_int_b, int width_dim, int B, int N, float alpha, long long B_global,
+                     int with_grad, float* cost, float* command, float* error, float* pred, float* du0, float* gl,
+                     float* gl_wide, void* workspace, size_t workspace_bytes, float noise_std,
+                     unsigned long long noise_seed, void* stream);
 
 /* Training-sample construction on the device (replaces DataLoader collation of `SequenceDataset.__getitem__`,
  * UL/Functions.py:109-132, over the per-trajectory slices of `Data.get_individual_dataset`, :479-516).  Tables

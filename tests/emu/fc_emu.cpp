@@ -359,4 +359,54 @@ int fc_emu_lstm_shadow_pair(const float* row0, const float* u, const float* rati
   }
   return 0;
 }
+
+// one-tile tcgen05 kernel with a wide controller (width_dim > 1): gl_wide [2560] = d fc_int.weight | d fc_int.bias
+int fc_emu_mpc_loss_tc_wide(const float* X, const float* u0, const float* Z, const float* wpack, const float* int_w,
+                            const float* int_b, int width_dim, int B, int N, float alpha, long long B_global, int with_grad,
+                            int grid, float* cost, float* command, float* error, float* pred, float* du0, float* gl /*[256]*/,
+                            float* gl_wide /*[2560]*/) {
+  fc::MpcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.X = X; p.u0 = u0; p.Z = Z; p.wpack = wpack;
+  p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
+  p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
+  p.grad_scale = 1.0f / ((float)N * (float)B_global);
+  p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
+  p.acc_comp = 1.0f;
+  { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
+  p.width_dim = width_dim; p.int_w = int_w; p.int_b = int_b;
+  p.num_tiles = (B + fc::tc::kTileTC - 1) / fc::tc::kTileTC;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  fc::tc::WorkLayoutTC wl = fc::tc::work_layout_tc(N, with_grad, width_dim);
+  p.work_stride = wl.total;
+  std::vector<float> work((size_t)grid * wl.total, 0.f);
+  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0), partial_wide((size_t)grid * fc::kWidePartialStride, 0.0);
+  p.work = work.data();
+  p.partial = partial.data();
+  p.partial_wide = partial_wide.data();
+  for (int b = 0; b < grid; ++b) {
+    EmuBlockTC blk(b, grid, fc::tc::kSmFloatsWide);
+    std::vector<std::thread> th;
+    th.reserve(fc::tc::kThreadsTC);
+    for (int t = 0; t < fc::tc::kThreadsTC; ++t)
+      th.emplace_back([&blk, &p, t]() {
+        EmuCtxTC ctx(&blk, t);
+        fc::tc::MpcTileTC<EmuCtxTC> k(ctx, p);
+        k.run();
+      });
+    for (auto& x : th) x.join();
+  }
+  for (int i = 0; i < 256; ++i) gl[i] = 0.f;
+  for (int i = 0; i <= fc::kNumFnnGrad; ++i) {
+    double a = 0.0;
+    for (int b = 0; b < grid; ++b) a += partial[(size_t)b * fc::kPartialStride + i];
+    gl[i] = (float)(i == fc::kNumFnnGrad ? a / (double)B_global : a);
+  }
+  for (int i = 0; i < fc::kWideGrads; ++i) {
+    double a = 0.0;
+    for (int b = 0; b < grid; ++b) a += partial_wide[(size_t)b * fc::kWidePartialStride + i];
+    gl_wide[i] = (float)a;
+  }
+  return 0;
+}
 }  // extern "C"

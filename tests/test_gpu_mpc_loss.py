@@ -292,3 +292,60 @@ def test_enable_noise_module_api_is_seeded_by_torch(dev, golden_weights):
     a, b, c = run(1), run(1), run(2)
     assert a == b and a != c and a != clean
     assert abs(a - clean) / abs(clean) < 0.2         # 1 % noise on the surrogate outputs: a perturbation, not a different loss
+
+
+def test_width_dim_2_matches_reference_golden(dev, golden_cases, golden_weights):
+    """FNNModel(width_dim=2) (UL/Functions.py:261-289: one weight-shared fc_int + ReLU repeat): the reference's own
+    outputs and gradients, fc_int included, through the drop-in API.  Every kernel selection routes this controller
+    to the one-tile tcgen05 kernel."""
+    C, name = golden_cases, "n6_b7_w2"
+    N, B, wd = (int(v) for v in C[f"{name}/meta"])
+    assert wd == 2
+    lstm, fnn = state_dicts(golden_weights, "w2")
+    sim = fb.LSTMModel(5, 50, 4, 3)
+    sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()}, strict=True)
+    ctl = fb.FNNModel(3, 50, 1, 2)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()}, strict=True)
+    sim, ctl = sim.to(dev), ctl.to(dev)
+    X, Z = torch.tensor(C[f"{name}/X"]).to(dev), torch.tensor(C[f"{name}/Z"]).to(dev)
+    loss, feats = fb.MPCLoss(prediction_horizon=N, alpha=ALPHA)(sim, ctl, X, ctl(X), Z, dev)
+    loss.backward()
+    for prec in ("f32", "f64"):
+        ref = lambda k: C[f"{name}/{prec}/{k}"]
+        assert abs(loss.item() - ref("loss")) / abs(ref("loss")) < TOL
+        assert rel_max(feats["loss"].cpu().numpy(), ref("cost")) < TOL
+        assert rel_max(feats["prediction"].cpu().numpy().reshape(B, N), ref("prediction")) < TOL
+        for prm, k in ((ctl.fc_inp.weight, "fc_inp.weight"), (ctl.fc_inp.bias, "fc_inp.bias"), (ctl.fc_int.weight, "fc_int.weight"),
+                       (ctl.fc_int.bias, "fc_int.bias"), (ctl.fc_out.weight, "fc_out.weight")):
+            assert rel_max(prm.grad.cpu().numpy(), ref("grad/" + k)) < TOL, (prec, k)
+
+
+@pytest.mark.parametrize("width,B,N", [(2, 300, 5), (3, 1000, 4)])
+def test_wide_controller_matches_oracle(dev, golden_weights, width, B, N):
+    """width_dim 2 and 3 at multi-tile batch sizes against the fp64 oracle (which is pinned on the reference's width_dim=2
+    case, tests/test_oracle_mpc.py)."""
+    lstm, fnn = state_dicts(golden_weights, "w2")
+    sim = fb.LSTMModel(5, 50, 4, 3)
+    sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()}, strict=True)
+    ctl = fb.FNNModel(3, 50, 1, width)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()}, strict=True)
+    sim, ctl = sim.to(dev), ctl.to(dev)
+    g = torch.Generator().manual_seed(width * 100 + B)
+    X = (torch.rand(B, 3, generator=g) * 2 - 1)
+    Z = (torch.rand(B, 10, 5, generator=g) * 2 - 1)
+    Xd, Zd = X.to(dev), Z.to(dev)
+    with torch.no_grad():
+        u0 = ctl(Xd).reshape(-1).contiguous()
+    r = fb.mpc_loss_native(fb.pack_weights(sim, ctl), Xd, u0, Zd, N, ALPHA, True, None, 0.0, 0,
+                           ctl.fc_int.weight.detach().contiguous(), ctl.fc_int.bias.detach().contiguous(), width)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    out, gr = O.mpc_loss_forward_backward(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, ALPHA, width_dim=width)
+    gl, gw = r["gl"].cpu().numpy(), r["gl_wide"].cpu().numpy()
+    assert abs(gl[250] - out["loss"]) / abs(out["loss"]) < TOL
+    assert rel_max(r["cost"].cpu().numpy(), out["cost"]) < TOL
+    assert rel_max(r["pred"].cpu().numpy(), out["prediction"]) < TOL
+    d = np.abs(r["du0"].cpu().numpy() - gr["u0"]) / np.abs(gr["u0"]).max()
+    assert (d > TOL).sum() <= 3
+    for got, key in ((gl[:150].reshape(50, 3), "inp_w"), (gl[150:200], "inp_b"), (gl[200:250], "out_w"),
+                     (gw[:2500].reshape(50, 50), "int_w"), (gw[2500:2550], "int_b")):
+        assert rel_max(got, np.asarray(gr[key]).reshape(got.shape)) < 5e-5, key

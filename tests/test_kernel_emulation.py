@@ -197,3 +197,29 @@ def test_emulated_enable_noise_matches_oracle_with_the_same_noise(emu, golden_ca
     _check_v(o, out, g)
     clean, _ = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
     assert abs(out["loss"] - clean["loss"]) / abs(clean["loss"]) > 1e-4      # the noise does change the result
+
+
+def test_emulated_wide_controller_matches_reference_and_oracle(emu, golden_cases, golden_weights):
+    """FNNModel(width_dim=2) in the one-tile tcgen05 kernel source (fwd_glue_wide / bwd_glue_wide): the roll-out and all
+    controller gradients, fc_int included, against the oracle on the reference's own width_dim=2 case."""
+    C, name = golden_cases, "n6_b7_w2"
+    N, B, wd = (int(v) for v in C[f"{name}/meta"])
+    lstm, fnn = state_dicts(golden_weights, "w2")
+    X, Z = C[f"{name}/X"], C[f"{name}/Z"]
+    u0 = np.ascontiguousarray(C[f"{name}/f32/u0"])
+    wp = _pack_v(emu, lstm, fnn, "tc")
+    int_w = np.ascontiguousarray(fnn["fc_int.weight"], dtype=np.float32)
+    int_b = np.ascontiguousarray(fnn["fc_int.bias"], dtype=np.float32)
+    o = {k: np.zeros(B, np.float32) for k in ("cost", "command", "error", "du0")}
+    o["pred"] = np.zeros((B, N), np.float32)
+    o["gl"] = np.zeros(256, np.float32)
+    glw = np.zeros(2560, np.float32)
+    emu.fc_emu_mpc_loss_tc_wide(_p(X), _p(u0), _p(Z), _p(wp), _p(int_w), _p(int_b), wd, B, N, ctypes.c_float(20.0),
+                                ctypes.c_longlong(B), 1, 1, _p(o["cost"]), _p(o["command"]), _p(o["error"]), _p(o["pred"]),
+                                _p(o["du0"]), _p(o["gl"]), _p(glw))
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0, width_dim=wd)
+    _check_v(o, out, g)
+    assert rel_max(glw[:2500].reshape(50, 50), g["int_w"]) < 1e-5
+    assert rel_max(glw[2500:2550], np.asarray(g["int_b"]).reshape(-1)) < 1e-5
+    assert abs(o["gl"][250] - C[f"{name}/f32/loss"]) / abs(C[f"{name}/f32/loss"]) < 1e-5     # the reference itself
