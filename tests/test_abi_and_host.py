@@ -63,8 +63,10 @@ def test_no_cpu_fallback(golden_weights):
         fb.MPCLoss(10, 20.0)(sim, ctl, X, ctl(X), Z, "cpu", enable_noise=True)
     with pytest.raises(NotImplementedError):
         fb.MPCLoss(10, 20.0)(fb.LSTMModel(5, 64, 4, 3), ctl, X, ctl(X), Z, "cpu")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):          # width_dim > 1 is supported (one-tile kernel); still no CPU path
         fb.MPCLoss(10, 20.0)(sim, fb.FNNModel(3, 50, 1, 2), X, ctl(X), Z, "cpu")
+    with pytest.raises(NotImplementedError):
+        fb.MPCLoss(10, 20.0)(sim, fb.FNNModel(3, 64, 1, 1), X, ctl(X), Z, "cpu")
     with pytest.raises(RuntimeError, match="CUDA"):
         fb.closed_loop_device(ctl, torch.zeros(2, 5), torch.zeros(3, 2), 1e-3, [1, 1, 1], [1])
 
