@@ -25,7 +25,8 @@ EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
            "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_closed_loop_rk4",
            "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout",
            "fc_mpc_loss_noise", "fc_closed_loop_rk4_noise", "fc_closed_loop_rk4_f64_noise",
-           "fc_build_windows", "fc_mpc_loss_wide_workspace_bytes", "fc_mpc_loss_wide")
+           "fc_build_windows", "fc_mpc_loss_wide_workspace_bytes", "fc_mpc_loss_wide",
+           "fc_closed_loop_rk4_ex")
 
 _c_float_p = ctypes.c_void_p   # raw device pointers are passed as integers
 _lib = None
@@ -94,6 +95,9 @@ def lib() -> ctypes.CDLL:
     L.fc_mpc_loss_wide.restype = i32
     L.fc_mpc_loss_wide.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, f32,
                                    ctypes.c_ulonglong, vp]
+    L.fc_closed_loop_rk4_ex.restype = i32
+    L.fc_closed_loop_rk4_ex.argtypes = [i32, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp,
+                                        fp5, fp5, ctypes.c_ulonglong, vp]
     L.fc_build_windows.restype = i32
     L.fc_build_windows.argtypes = [vp, vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp]
     L.fc_fp32_peak.restype = i32

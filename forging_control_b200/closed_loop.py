@@ -56,11 +56,17 @@ def _controller_weights(controller, dev):
     for name in ("fc_inp", "fc_out"):
         if not hasattr(controller, name):
             raise TypeError("closed loop: controller must be an FNNModel")
-    if getattr(controller, "width_dim", 1) != 1 or tuple(controller.fc_inp.weight.shape) != (50, 3) \
-            or tuple(controller.fc_out.weight.shape) != (1, 50) or controller.fc_inp.bias is None:
-        raise NotImplementedError("closed loop kernel supports FNNModel(3, 50, 1, width_dim=1, bias=True) only")
+    if tuple(controller.fc_inp.weight.shape) != (50, 3) or tuple(controller.fc_out.weight.shape) != (1, 50) \
+            or controller.fc_inp.bias is None:
+        raise NotImplementedError("closed loop kernel supports FNNModel(3, 50, 1, width_dim, bias=True) only")
     f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
-    return f(controller.fc_inp.weight), f(controller.fc_inp.bias), f(controller.fc_out.weight)
+    width = int(getattr(controller, "width_dim", 1))
+    wide = (None, None)
+    if width > 1:
+        if tuple(controller.fc_int.weight.shape) != (50, 50) or controller.fc_int.bias is None:
+            raise NotImplementedError("closed loop kernel supports the 50 x 50 hidden layer fc_int with bias only")
+        wide = (f(controller.fc_int.weight), f(controller.fc_int.bias))
+    return f(controller.fc_inp.weight), f(controller.fc_inp.bias), f(controller.fc_out.weight), wide, width
 
 
 def closed_loop_device(controller, x0, ref, Ts, scale_in, scale_out, substeps=4, steps_per_ref=1,
@@ -81,21 +87,21 @@ def closed_loop_device(controller, x0, ref, Ts, scale_in, scale_out, substeps=4,
     n_ref = ref.shape[0]
     T = n_ref * steps_per_ref
     x0, ref = x0.contiguous(), ref.contiguous()
-    w_in, b_in, w_out = _controller_weights(controller, dev)
+    w_in, b_in, w_out, wide, width = _controller_weights(controller, dev)
     s_in = torch.as_tensor(np.asarray(scale_in, dtype=np.float64), dtype=dt, device=dev)
     s_out = torch.as_tensor(np.asarray(scale_out, dtype=np.float64), dtype=dt, device=dev)
     meas = torch.empty((T + 1, 5, B), dtype=dt, device=dev) if want_meas else None
     u = torch.empty((T, B), dtype=dt, device=dev) if want_u else None
     xf = torch.empty((B, 5), dtype=dt, device=dev)
     L = _native.lib()
-    fn = L.fc_closed_loop_rk4_noise if dt == torch.float32 else L.fc_closed_loop_rk4_f64_noise
     import ctypes
     as5 = lambda v: (ctypes.c_float * 5)(*[float(a) for a in (np.zeros(5) if v is None else np.asarray(v, dtype=np.float64).reshape(5))])
     with torch.cuda.device(dev):
-        rc = fn(_native.ptr(x0), _native.ptr(ref), n_ref, steps_per_ref, B, T, float(Ts), int(substeps),
-                _native.ptr(s_in), _native.ptr(s_out), _native.ptr(w_in), _native.ptr(b_in), _native.ptr(w_out),
-                _native.ptr(meas), _native.ptr(u), _native.ptr(xf), as5(process_std), as5(meas_std),
-                int(noise_seed) & (2 ** 64 - 1), _native.stream_ptr(dev))
+        rc = L.fc_closed_loop_rk4_ex(int(dt == torch.float64), _native.ptr(x0), _native.ptr(ref), n_ref, steps_per_ref, B, T,
+                                     float(Ts), int(substeps), _native.ptr(s_in), _native.ptr(s_out), _native.ptr(w_in),
+                                     _native.ptr(b_in), _native.ptr(w_out), _native.ptr(wide[0]), _native.ptr(wide[1]), width,
+                                     _native.ptr(meas), _native.ptr(u), _native.ptr(xf), as5(process_std), as5(meas_std),
+                                     int(noise_seed) & (2 ** 64 - 1), _native.stream_ptr(dev))
     _native.check(rc, "fc_closed_loop_rk4")
     return meas, u, xf
 

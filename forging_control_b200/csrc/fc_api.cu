@@ -507,7 +507,8 @@ template <typename R>
 static int closed_loop_launch(const R* x0, const R* ref, int n_ref, int steps_per_ref, int B, int T, R ts, int substeps,
                               const R* scale_in, const R* scale_out, const float* inp_w, const float* inp_b,
                               const float* out_w, R* meas, R* u, R* x_final, void* stream,
-                              const float* process_std = nullptr, const float* meas_std = nullptr, unsigned long long seed = 0) {
+                              const float* process_std = nullptr, const float* meas_std = nullptr, unsigned long long seed = 0,
+                              const float* int_w = nullptr, const float* int_b = nullptr, int width_dim = 1) {
   if (B <= 0 || T < 0 || n_ref <= 0 || steps_per_ref <= 0 || substeps <= 0 || !(ts > 0))
     return fail(FC_ERR_BAD_SHAPE, "fc_closed_loop_rk4: bad shape%s B=%lld T=%lld", "", B, T);
   if (!x0 || !ref || !scale_in || !scale_out || !inp_w || !inp_b || !out_w)
@@ -523,8 +524,21 @@ static int closed_loop_launch(const R* x0, const R* ref, int n_ref, int steps_pe
       return fail(FC_ERR_BAD_SHAPE, "fc_closed_loop_rk4: noise standard deviations%s must be >= 0");
     if (nz.process_std[i] > 0.f || nz.meas_std[i] > 0.f) nz.on = 1;
   }
-  closed_loop_kernel<R><<<(B + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-      x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, inp_w, inp_b, out_w, meas, u, x_final, nz);
+  if (width_dim > 1 && (!int_w || !int_b)) return fail(FC_ERR_NULL_POINTER, "fc_closed_loop_rk4: width_dim > 1 needs fc_int%s");
+  if (width_dim > 64) return fail(FC_ERR_UNSUPPORTED, "fc_closed_loop_rk4: width_dim%s=%lld out of range", "", width_dim);
+  ClosedLoopWide wd;
+  wd.int_w = int_w; wd.int_b = int_b; wd.width_dim = width_dim;
+  const dim3 grid((B + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FC_CL_LAUNCH(W, Z)                                                                                              \
+  closed_loop_kernel<R, W, Z><<<grid, threads, 0, st>>>(x0, ref, n_ref, steps_per_ref, B, T, ts, substeps, scale_in, scale_out, \
+                                                        inp_w, inp_b, out_w, meas, u, x_final, nz, wd)
+  const bool wide = width_dim > 1, noisy = nz.on != 0;
+  if (wide && noisy) FC_CL_LAUNCH(true, true);
+  else if (wide) FC_CL_LAUNCH(true, false);
+  else if (noisy) FC_CL_LAUNCH(false, true);
+  else FC_CL_LAUNCH(false, false);
+#undef FC_CL_LAUNCH
   FC_CUDA(cudaGetLastError(), "closed_loop_kernel launch");
   return FC_OK;
 }
@@ -780,6 +794,22 @@ int fc_build_windows(const float* Xtab, const float* ytab, const float* Ztab, lo
                                                                                  (unsigned long long)B, X, y, Z);
   FC_CUDA(cudaGetLastError(), "build_windows_kernel launch");
   return FC_OK;
+}
+
+int fc_closed_loop_rk4_ex(int f64, const void* x0, const void* ref, int n_ref, int steps_per_ref, int B, int T, double ts,
+                          int substeps, const void* scale_in, const void* scale_out, const float* fnn_inp_w,
+                          const float* fnn_inp_b, const float* fnn_out_w, const float* fnn_int_w, const float* fnn_int_b,
+                          int width_dim, void* meas, void* u, void* x_final, const float* process_std, const float* meas_std,
+                          unsigned long long seed, void* stream) {
+  if (f64)
+    return closed_loop_launch<double>((const double*)x0, (const double*)ref, n_ref, steps_per_ref, B, T, ts, substeps,
+                                      (const double*)scale_in, (const double*)scale_out, fnn_inp_w, fnn_inp_b, fnn_out_w,
+                                      (double*)meas, (double*)u, (double*)x_final, stream, process_std, meas_std, seed, fnn_int_w,
+                                      fnn_int_b, width_dim);
+  return closed_loop_launch<float>((const float*)x0, (const float*)ref, n_ref, steps_per_ref, B, T, (float)ts, substeps,
+                                   (const float*)scale_in, (const float*)scale_out, fnn_inp_w, fnn_inp_b, fnn_out_w,
+                                   (float*)meas, (float*)u, (float*)x_final, stream, process_std, meas_std, seed, fnn_int_w,
+                                   fnn_int_b, width_dim);
 }
 
 int fc_fp32_peak(int iters, double* flops_host, void* stream) {

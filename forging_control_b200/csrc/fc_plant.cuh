@@ -105,6 +105,14 @@ __device__ __forceinline__ void rk4_substep(R (&x)[5], R u, R h) {            //
 // (UL/Functions.py:1176-1183): x_next = integrate(x, u) + w0, y = measurement(x_next) + v0, w0 ~ N(0, process_std),
 // v0 ~ N(0, meas_std) per state; the controller reads the noisy measurement.  Normals: philox_normal4 with counter
 // (trajectory, 3*step + k).  std all zero = off.
+// hidden-layer repeats of the controller (FNNModel.forward, UL/Functions.py:261-289): width_dim - 1 applications of the
+// weight-shared fc_int + ReLU
+struct ClosedLoopWide {
+  const float* int_w;   // [50][50]
+  const float* int_b;   // [50]
+  int width_dim;        // <= 1: none
+};
+
 struct ClosedLoopNoise {
   float process_std[5];
   float meas_std[5];
@@ -113,15 +121,22 @@ struct ClosedLoopNoise {
 };
 
 // closed loop: scaler -> FNN (float32) -> saturation -> inverse scaler -> RK4 plant step
-template <typename R>
+// WIDE / NOISE are compile-time switches: the plain variant (reference configuration: width_dim = 1, zero noise)
+// keeps its register and shared-memory footprint (the generic one measured 35 % slower).
+template <typename R, bool WIDE, bool NOISE>
 __global__ void __launch_bounds__(128) closed_loop_kernel(
     const R* __restrict__ x0, const R* __restrict__ ref, int n_ref, int steps_per_ref, int B, int T, R ts,
     int substeps, const R* __restrict__ scale_in, const R* __restrict__ scale_out,
     const float* __restrict__ inp_w, const float* __restrict__ inp_b, const float* __restrict__ out_w,
-    R* __restrict__ meas, R* __restrict__ ucmd, R* __restrict__ x_final, ClosedLoopNoise nz) {
+    R* __restrict__ meas, R* __restrict__ ucmd, R* __restrict__ x_final, ClosedLoopNoise nz, ClosedLoopWide wd) {
   __shared__ float s_w[50 * 3], s_b[50], s_o[50];
+  __shared__ float s_iw[WIDE ? 50 * 50 : 1], s_ib[WIDE ? 50 : 1];
   for (int i = threadIdx.x; i < 150; i += blockDim.x) s_w[i] = inp_w[i];
   for (int i = threadIdx.x; i < 50; i += blockDim.x) { s_b[i] = inp_b[i]; s_o[i] = out_w[i]; }
+  if (WIDE) {
+    for (int i = threadIdx.x; i < 2500; i += blockDim.x) s_iw[i] = wd.int_w[i];
+    for (int i = threadIdx.x; i < 50; i += blockDim.x) s_ib[i] = wd.int_b[i];
+  }
   __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -142,17 +157,32 @@ __global__ void __launch_bounds__(128) closed_loop_kernel(
     // NN_make_step, Functions.py:1596-1604: MaxAbs scale, reference scaled by the y_dot scaler
     const float f0 = (float)(ym1 / si0), f1 = (float)(ym4 / si1), f2 = (float)(r / si0);
     float vv = 0.f;
+    if (!WIDE) {
 #pragma unroll 10
-    for (int k = 0; k < 50; ++k) {
-      float pre = fmaf(s_w[k * 3 + 2], f2, fmaf(s_w[k * 3 + 1], f1, fmaf(s_w[k * 3], f0, s_b[k])));
-      vv = fmaf(s_o[k], fmaxf(pre, 0.f), vv);
+      for (int k = 0; k < 50; ++k) {
+        float pre = fmaf(s_w[k * 3 + 2], f2, fmaf(s_w[k * 3 + 1], f1, fmaf(s_w[k * 3], f0, s_b[k])));
+        vv = fmaf(s_o[k], fmaxf(pre, 0.f), vv);
+      }
+    } else {
+      float a[50], a2[50];
+      for (int k = 0; k < 50; ++k)
+        a[k] = fmaxf(fmaf(s_w[k * 3 + 2], f2, fmaf(s_w[k * 3 + 1], f1, fmaf(s_w[k * 3], f0, s_b[k]))), 0.f);
+      for (int r = 1; r < wd.width_dim; ++r) {
+        for (int i = 0; i < 50; ++i) {
+          float pre = s_ib[i];
+          for (int k = 0; k < 50; ++k) pre = fmaf(s_iw[i * 50 + k], a[k], pre);
+          a2[i] = fmaxf(pre, 0.f);
+        }
+        for (int i = 0; i < 50; ++i) a[i] = a2[i];
+      }
+      for (int k = 0; k < 50; ++k) vv = fmaf(s_o[k], a[k], vv);
     }
     const float us = fminf(fmaxf(vv, -1.f), 1.f);                          // nn.Hardtanh
     const R u = (R)us * so;
     if (ucmd) ucmd[(size_t)t * B + b] = u;
     for (int s = 0; s < substeps; ++s) rk4_substep(x, u, h);
     R y[5] = {x[0], x[1], smooth_floor(x[2]), smooth_floor(x[3]), x[4]};     // template_model.py:154-155
-    if (nz.on) {
+    if (NOISE) {
       float e[12];
       philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t, e);
       philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t + 1u, e + 4);

@@ -141,6 +141,14 @@ int fc_closed_loop_rk4_f64_noise(const double* x0, const double* ref, int n_ref,
                                  const float* fnn_inp_w, const float* fnn_inp_b, const float* fnn_out_w, double* meas,
                                  double* u, double* x_final, const float* process_std, const float* meas_std,
                                  unsigned long long seed, void* stream);
+/* General form: f64 = 0 / 1 selects the plant precision (x0, ref, scale_in, scale_out, meas, u, x_final are float or
+ * double arrays accordingly); fnn_int_w [50][50], fnn_int_b [50], width_dim: hidden-layer repeats of FNNModel
+ * (UL/Functions.py:261-289; width_dim <= 1: none, pointers may be NULL); noise as above.                      */
+int fc_closed_loop_rk4_ex(int f64, const void* x0, const void* ref, int n_ref, int steps_per_ref, int B, int T, double ts,
+                          int substeps, const void* scale_in, const void* scale_out, const float* fnn_inp_w,
+                          const float* fnn_inp_b, const float* fnn_out_w, const float* fnn_int_w, const float* fnn_int_b,
+                          int width_dim, void* meas, void* u, void* x_final, const float* process_std,
+                          const float* meas_std, unsigned long long seed, void* stream);
 
 /* ---- measurement helper: register-resident FFMA loop used by bench.py to measure the FP32
  * roofline denominator on the device it runs on; writes achieved FLOP/s to *flops_host.           */

@@ -139,6 +139,8 @@ def controller_step(fnn, scale_in, scale_out, y_dot, z, ref):
     f32 = np.float32
     xin = np.stack((y_dot / scale_in[0], z / scale_in[1], ref / scale_in[0]), axis=-1).astype(f32)
     hid = np.maximum(xin @ fnn["inp_w"].astype(f32).T + fnn["inp_b"].astype(f32), f32(0))
+    for _ in range(int(fnn.get("width_dim", 1)) - 1):           # FNNModel.forward, UL/Functions.py:277-283: weight-shared repeats
+        hid = np.maximum(hid @ fnn["int_w"].astype(f32).T + fnn["int_b"].astype(f32), f32(0))
     v = hid @ fnn["out_w"].astype(f32).T
     u_s = np.clip(v[..., 0], f32(-1), f32(1))
     return u_s.astype(np.float64) * scale_out[0]

@@ -155,3 +155,29 @@ def test_process_and_measurement_noise_match_oracle_with_the_same_normals(golden
     assert diff[:, 1:].max() > 1e-5                        # the noise is there
     # measurement-noise statistics of the logged y_dot against the noiseless measurement of the same noisy state
     assert np.abs(u.t().cpu().numpy() - u_ref).max() < 5e-3
+
+
+def test_closed_loop_with_wide_controller_matches_oracle(golden_weights):
+    """FNNModel(width_dim=2) in the closed loop (FNNModel.forward, UL/Functions.py:261-289 inside NN_make_step, :1596-1604)."""
+    _, fnn_sd = state_dicts(golden_weights, "w2")
+    ctl = fb.FNNModel(3, 50, 1, 2)
+    ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn_sd.items()})
+    fnn = {"inp_w": fnn_sd["fc_inp.weight"], "inp_b": fnn_sd["fc_inp.bias"], "out_w": fnn_sd["fc_out.weight"],
+           "int_w": fnn_sd["fc_int.weight"], "int_b": fnn_sd["fc_int.bias"], "width_dim": 2}
+    si, so = golden_weights["scale/scaler_input"], golden_weights["scale/scaler_output"]
+    dev = torch.device("cuda:0")
+    B, T = 96, 60
+    x0, seg = _inputs(B, T, seed=8)
+    ref = np.repeat(seg, 150, axis=1)[:, :T]
+    meas, u, _ = fb.closed_loop_device(ctl, torch.tensor(x0, dtype=torch.float64).to(dev), torch.tensor(ref.T.copy(), dtype=torch.float64).to(dev),
+                                       1e-3, si, so, 4, 1)
+    m_ref, u_ref = P.closed_loop(fnn, si, so, x0, ref, 1e-3, 4, np.float64)
+    err = np.abs(meas.permute(2, 0, 1).cpu().numpy() - m_ref) / P.STATE_SCALE
+    assert err[:, 1].max() < 1e-6 and np.median(err) < 1e-6 and np.percentile(err, 99) < 1e-4
+    assert np.abs(u.t().cpu().numpy()[:, 0] - u_ref[:, 0]).max() < 1e-6 * max(1.0, np.abs(u_ref).max())
+    # differs from the width_dim = 1 controller with the same fc_inp / fc_out
+    ctl1 = fb.FNNModel(3, 50, 1, 1)
+    ctl1.load_state_dict({k: torch.tensor(v) for k, v in fnn_sd.items()})
+    _, u1, _ = fb.closed_loop_device(ctl1, torch.tensor(x0, dtype=torch.float64).to(dev), torch.tensor(ref.T.copy(), dtype=torch.float64).to(dev),
+                                     1e-3, si, so, 4, 1)
+    assert (u1 - u).abs().max().item() > 1e-6
