@@ -480,17 +480,23 @@ struct MpcPlan {
   size_t bytes;
 };
 // Automatic choice (measured on B200, profiles/r01_bench_configs_three_kernels.jsonl): while every 128-trajectory tile
-// can have an SM of its own (B <= 128 * #SMs) the one-tile tcgen05 kernel is fastest (B=15: 2.2 ms per step against
-// 7.6 ms for the FFMA kernel; B=4096: 0.94 ms against 1.6 ms for the pair kernel, which would leave SMs idle); beyond
-// that the pair kernel, which keeps two tiles per CTA in flight, wins (B=524288: 80 M against 73 M trajectory-steps/s;
-// the FFMA kernel reaches 23 M).  All three stay selectable (fc_mpc_select_kernel / FC_MPC_KERNEL).
+// can have an SM of its own (128 < B <= 128 * #SMs) the one-tile tcgen05 kernel is fastest (B=4096: 0.96 ms against
+// 1.54 ms for the pair kernel, which would leave SMs idle); beyond that the pair kernel, which keeps two tiles per CTA
+// in flight, wins (B=524288: 84 M against 74 M trajectory-steps/s; the FFMA kernel reaches 23 M), and for a single tile
+// too (B=15: 2.11 ms, one-tile kernel 2.23 ms, FFMA kernel 7.6 ms).  All three stay selectable
+// (fc_mpc_select_kernel / FC_MPC_KERNEL).
 static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
   pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
-  if (mode == 0 && (B + tc::kTileTC - 1) / tc::kTileTC > sms) pl->kind = 2;
+  {
+    const int t128 = (B + tc::kTileTC - 1) / tc::kTileTC;
+    // more tiles than SMs: two tiles per CTA overlap tensor and cell-update work; a single tile: the pair kernel's
+    // dedicated issuer warp alone is worth 5 % (B=15: 2.11 ms against 2.23 ms)
+    if (mode == 0 && (t128 > sms || t128 == 1)) pl->kind = 2;
+  }
   if (width_dim > 1) pl->kind = 1;        // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
   const int tile = pl->kind ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
