@@ -303,6 +303,9 @@ class MPCLoss(nn.Module):
         noise_std, noise_seed = 0.0, 0
         if enable_noise:
             noise_std, noise_seed = self.NOISE_STD, int(torch.randint(0, 2 ** 62, (1,)).item())
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                # the generator's counter is the LOCAL trajectory index: de-correlate the shards of a sharded batch
+                noise_seed = (noise_seed + torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
         loss, cost, command, error, pred = _FusedMPCLoss.apply(
             u0, *params, X, Z, wpack, int(self.N), float(self.alpha), bool(with_grad), self.global_batch,
             float(noise_std), noise_seed, wide[0], wide[1], width_dim)
