@@ -458,6 +458,9 @@ static int sm_count(int* out) {
   return FC_OK;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices have been prepared (several GPUs in one process)
+static int ensure_smem_attributes();
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel
@@ -546,6 +549,21 @@ static int closed_loop_launch(const R* x0, const R* ref, int n_ref, int steps_pe
   else FC_CL_LAUNCH(false, false);
 #undef FC_CL_LAUNCH
   FC_CUDA(cudaGetLastError(), "closed_loop_kernel launch");
+  return FC_OK;
+}
+
+static int ensure_smem_attributes() {
+  int dev = 0;
+  FC_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+  static bool done[64] = {false};
+  if (dev >= 0 && dev < 64 && done[dev]) return FC_OK;
+  FC_CUDA(cudaFuncSetAttribute(mpc_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes),
+          "cudaFuncSetAttribute(smem)");
+  FC_CUDA(cudaFuncSetAttribute(mpc_loss_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmBytesWide),
+          "cudaFuncSetAttribute(smem, tc)");
+  FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
+          "cudaFuncSetAttribute(smem, pair)");
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return FC_OK;
 }
 
@@ -648,16 +666,8 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   if (workspace_bytes < pl.bytes)
     return fail(FC_ERR_WORKSPACE, "fc_mpc_loss: workspace too small%s: have %lld need %lld bytes", "", (long long)workspace_bytes,
                 (long long)pl.bytes);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FC_CUDA(cudaFuncSetAttribute(mpc_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes),
-            "cudaFuncSetAttribute(smem)");
-    FC_CUDA(cudaFuncSetAttribute(mpc_loss_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmBytesWide),
-            "cudaFuncSetAttribute(smem, tc)");
-    FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
-            "cudaFuncSetAttribute(smem, pair)");
-    attr_set = true;
-  }
+  rc = ensure_smem_attributes();
+  if (rc) return rc;
   MpcParams p;
   memset(&p, 0, sizeof(p));
   p.X = X; p.u0 = u0; p.Z = Z;
@@ -721,12 +731,8 @@ int fc_lstm_shadow_rollout(const float* row0, const float* u, const float* ratio
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
-            "cudaFuncSetAttribute(smem, pair)");
-    attr_set = true;
-  }
+  rc = ensure_smem_attributes();
+  if (rc) return rc;
   const int tiles = (B + pr::kTileP - 1) / pr::kTileP, pairs = (tiles + pr::kTiles - 1) / pr::kTiles;
   const int grid = pairs < sms ? pairs : sms;
   MpcParams p;
