@@ -11,7 +11,7 @@ from .distributed import allreduce_loss_and_grads, shard_bounds, sharded_trainin
 __all__ = ["FNNModel", "LSTMModel", "MPCLoss", "NeuralNetwork", "FeasibilityRecovery", "Data",
            "mpc_loss_native", "pack_weights", "closed_loop_device", "closed_loop_rollout",
            "tvp_reference_table", "shard_bounds", "allreduce_loss_and_grads", "sharded_training_step",
-           "install"]
+           "lstm_shadow_native", "DeviceSequenceLoader", "build_windows", "install"]
 
 
 def install(reference_functions_module) -> None:
@@ -25,5 +25,6 @@ def install(reference_functions_module) -> None:
     ref.LSTMModel = LSTMModel
     ref.MPCLoss = MPCLoss
     ref.NeuralNetwork.train_model = staticmethod(NeuralNetwork.train_model)
+    ref.NeuralNetwork.validate_model = staticmethod(NeuralNetwork.validate_model)
     ref.NeuralNetwork.loop = staticmethod(NeuralNetwork.loop)
     ref.FeasibilityRecovery.NN_make_step = staticmethod(FeasibilityRecovery.NN_make_step)
