@@ -367,7 +367,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_port_throughput(3, 1)
+            r = cpu_port_throughput(16, 2)
             line["cpu_baseline"] = {"value": r["value"], "unit": "trajectory-steps/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
