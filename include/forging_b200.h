@@ -5,8 +5,9 @@
  * Python host side (forging_control_b200/Functions.py) binds these with ctypes, see INTEGRATION.md.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer unless the name ends in _host; the library borrows it for
- *     the duration of the call and never frees or retains caller memory;
+ *   - every pointer is a DEVICE pointer unless the name ends in _host or its comment says HOST (the few
+ *     5-/4-float parameter vectors: noise standard deviations, scaler ratios); the library borrows it
+ *     for the duration of the call and never frees or retains caller memory;
  *   - all calls are enqueue-only on `stream` (a cudaStream_t passed as void*), no hidden
  *     synchronisation, re-entrant per device;
  *   - every function returns 0 on success or a negative fc_status; fc_last_error() returns a
