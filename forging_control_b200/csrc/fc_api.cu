@@ -249,6 +249,7 @@ struct DevCtxTC : DevCtx {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   static __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+  __device__ __forceinline__ void tmem_fence() const { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
   static __device__ __forceinline__ void sts2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
   // D[128 x n] (+)= A[128 x 16*ksteps] * B[n x 16*ksteps]^T with BOTH operands in shared memory:
   // A image = [k/8][128][8 halves], B image = [k/8][n_img][8 halves]

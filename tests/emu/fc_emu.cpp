@@ -122,6 +122,7 @@ struct EmuCtxTC : EmuCtx {
   static void report_pair(int, const long long*) {}
   void bar_arrive(int bar) const { tb->bars[bar].fetch_add(1); }
   void operand_fence() const {}
+  void tmem_fence() const {}
   static void sts2(float* p, float a, float b) { p[0] = a; p[1] = b; }
   static void red_add(float* p, float v) { *p += v; }
   void mma_ss(int d_col, int n, const float* a_img, const float* b_img, int n_img, int ksteps, bool accumulate) const {
