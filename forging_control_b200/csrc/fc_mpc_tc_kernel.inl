@@ -82,11 +82,10 @@ struct MpcTileTC {
   FC_HD_CTX static float tanh_from_(float x, float rd) {
     const float big = fmaf(-2.f, rd, 1.f);
     const float x2 = x * x;
-    float pl = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);
-    pl = fmaf(x2, pl, 0.13333333333333333f);
+    float pl = fmaf(x2, -0.053968253968253971f, 0.13333333333333333f);
     pl = fmaf(x2, pl, -0.33333333333333331f);
     pl = fmaf(x2 * x, pl, x);
-    return fabsf(x) < 0.3f ? pl : big;
+    return fabsf(x) < 0.2f ? pl : big;
   }
   // tanh of NU values with one reciprocal per four
   template <int NU>
