@@ -325,7 +325,7 @@ struct MpcPair {
       float gi, gf, go, rg;
       quad_rcp(di, df, dq, dg, gi, gf, go, rg);
       const float gg = tanh_from_(xg, rg);
-      const float cp = first ? 0.f : c[j0 + i];
+      const float cp = c[j0 + i];                            // zeroed by the caller at t = 0
       cn[i] = fmaf(gf, cp, gi * gg);
       c[j0 + i] = cn[i];
       rv[i * 5 + 0] = gi; rv[i * 5 + 1] = gf; rv[i * 5 + 2] = gg; rv[i * 5 + 3] = go; rv[i * 5 + 4] = cp;
@@ -465,6 +465,10 @@ struct MpcPair {
     lap(1);
     if (l > 0 && t + 1 < kLook) copy_input(X, t + 1);        // input block of step t+1: lands during the cell update
     if (l == 0 && scalar && t + 1 < kLook) store_features(X, xin);
+    if (t == 0) {
+#pragma unroll
+      for (int j = 0; j < kMaxOwn; ++j) c[j] = 0.f;          // LSTMModel.initialize_hidden_states: zero state, :331-351
+    }
     fwd_pointwise(X, t == 0, corr, h, rec_out);
     if (l + 1 < kLayers || t + 1 < kLook) {
       F4 hi4[3], lo4[3];
@@ -714,13 +718,14 @@ struct MpcPair {
     for (int i = 0; i < NU; ++i) {
       const int j = j0 + i;
       const float gi = rv[i * 5 + 0], gf = rv[i * 5 + 1], gg = rv[i * 5 + 2], go = rv[i * 5 + 3], cp = rv[i * 5 + 4];
-      const float A = go * (1.f - tch[i] * tch[i]);
+      // s(1-s) and 1-t^2 as single fused operations: fmaf(-s, s, s), fmaf(-t, t, 1)
+      const float A = go * fmaf(-tch[i], tch[i], 1.f);
       const float dct = fmaf(dh[j], A, c[j]);
       c[j] = dct * gf;
-      dg[i * 4 + 0] = dct * (gg * gi * (1.f - gi));
-      dg[i * 4 + 1] = dct * (cp * gf * (1.f - gf));
-      dg[i * 4 + 2] = dct * (gi * (1.f - gg * gg));
-      dg[i * 4 + 3] = dh[j] * (tch[i] * go * (1.f - go));
+      dg[i * 4 + 0] = dct * (gg * fmaf(-gi, gi, gi));
+      dg[i * 4 + 1] = dct * (cp * fmaf(-gf, gf, gf));
+      dg[i * 4 + 2] = dct * (gi * fmaf(-gg, gg, 1.f));
+      dg[i * 4 + 3] = dh[j] * (tch[i] * fmaf(-go, go, go));
     }
   }
 
