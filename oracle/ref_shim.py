@@ -101,6 +101,27 @@ def load_reference_functions():
     return mod
 
 
+def load_reference_surrogate_functions():
+    """Return the reference ``Model_NN/Functions.py`` module (surrogate training variant), imported by path."""
+    if "mnn" in _CACHE:
+        return _CACHE["mnn"]
+    if not os.path.isfile(os.path.join(MNN_DIR, "Functions.py")):
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
+    _install_stubs()
+    cwd = os.getcwd()
+    os.makedirs("/tmp/forging_ref_import", exist_ok=True)
+    os.chdir("/tmp/forging_ref_import")
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "forging_reference_MNN_Functions", os.path.join(MNN_DIR, "Functions.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        os.chdir(cwd)
+    _CACHE["mnn"] = mod
+    return mod
+
+
 class _Dummy:
     """Stand-in for every non-numpy class found in the do-mpc result pickles."""
 
