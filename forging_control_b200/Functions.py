@@ -74,8 +74,10 @@ class FNNModel(nn.Module):
 # ----------------------------------------------------------------------------------------------
 class LSTMModel(nn.Module):
     """LSTM press surrogate, Functions.py:295-379.  ``state_dict`` keys ``lstm.weight_ih_l{k}``,
-    ``lstm.weight_hh_l{k}``, ``fc.weight``, ``fc.bias``.  Stand-alone ``forward`` (used by the
-    reference for the shadow prediction, Functions.py:999) runs the stock ``nn.LSTM``; inside
+    ``lstm.weight_hh_l{k}``, ``fc.weight``, ``fc.bias``.  Stand-alone ``forward`` (the surrogate-training step,
+    Model_NN/Functions.py:551, and the shadow prediction, Functions.py:999) runs the windowed-LSTM kernels of
+    ``surrogate.lstm_window`` for CUDA inputs of the reference configuration (differentiable w.r.t. the weights) and the
+    stock ``nn.LSTM`` module otherwise (CPU tensors, other shapes -- the ``.cpu()`` evaluation of Main.py:347-361); inside
     ``MPCLoss`` the weights are consumed by the fused kernel instead."""
 
     def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, layer_dim: int, bias=False,
@@ -92,6 +94,10 @@ class LSTMModel(nn.Module):
                 torch.zeros(shape, device=device).requires_grad_())
 
     def forward(self, x: torch.Tensor, device: torch.device):
+        from . import surrogate
+        if surrogate.supported(self, x) and not x.requires_grad and x.size(0) > 0:
+            # reference configuration on a CUDA device: forward / reverse-sweep kernels (fc_lstm_window_fwd / _bwd)
+            return surrogate.lstm_window(self, x)
         h0, c0 = self.initialize_hidden_states(x.size(0), device)
         out, _ = self.lstm(x, (h0.detach(), c0.detach()))
         return self.fc(out[:, -1, :])

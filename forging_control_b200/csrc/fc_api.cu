@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(kThreads, 1) mpc_loss_kernel(const MpcParams p
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+}  // namespace fc
+#include "fc_lstm_train.cuh"
+namespace fc {
+
 template <int N> struct TmemIO;
 template <> struct TmemIO<1> {
   static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
@@ -564,6 +568,10 @@ static int ensure_smem_attributes() {
           "cudaFuncSetAttribute(smem, tc)");
   FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
           "cudaFuncSetAttribute(smem, pair)");
+  FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd),
+          "cudaFuncSetAttribute(smem, lstm fwd)");
+  FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemBwd),
+          "cudaFuncSetAttribute(smem, lstm bwd)");
   if (dev >= 0 && dev < 64) done[dev] = true;
   return FC_OK;
 }
@@ -853,6 +861,126 @@ int fc_fp32_peak(int iters, double* flops_host, void* stream) {
   cudaFree(sink);
   const double flop = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
   *flops_host = flop / (best * 1e-3);
+  return FC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// surrogate training path + optimizer update (fc_lstm_train.cuh)
+// ---------------------------------------------------------------------------------------------------
+size_t fc_lstm_train_pack_floats(void) { return (size_t)lt::kPackFloatsL; }
+
+int fc_lstm_train_pack(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1, const float* w_ih2,
+                       const float* w_hh2, float* pack, void* stream) {
+  if (!w_ih0 || !w_hh0 || !w_ih1 || !w_hh1 || !w_ih2 || !w_hh2 || !pack)
+    return fail(FC_ERR_NULL_POINTER, "fc_lstm_train_pack: null pointer%s");
+  if (!aligned16(pack)) return fail(FC_ERR_MISALIGNED, "fc_lstm_train_pack: pack must be 16-byte aligned%s");
+  lt::LstmRaw w;
+  w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
+  w.fc_w = nullptr; w.fc_b = nullptr;
+  lt::pack_lstm_train_kernel<<<(lt::kPackFloatsL + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, pack);
+  FC_CUDA(cudaGetLastError(), "pack_lstm_train_kernel launch");
+  return FC_OK;
+}
+
+struct LstmTrainPlan {
+  int tiles, grid;
+  size_t rec, hseq, dseq, partial, floats;     // offsets in floats
+};
+static int lstm_train_plan(int B, int save, LstmTrainPlan* pl) {
+  if (B <= 0) return fail(FC_ERR_BAD_SHAPE, "fc_lstm_window: B must be positive%s (B=%lld)", "", B);
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  pl->tiles = (B + lt::kTT - 1) / lt::kTT;
+  pl->grid = pl->tiles < sms ? pl->tiles : sms;
+  size_t o = 0;
+  pl->rec = o;  o += save ? (size_t)pl->tiles * lt::kRecFloatsTile : 0;
+  pl->hseq = o; o += save ? (size_t)pl->tiles * lt::kHseqFloatsTile : 0;
+  pl->dseq = o; o += save ? (size_t)pl->grid * lt::kDseqFloatsCta : 0;
+  pl->partial = o; o += save ? (size_t)pl->grid * lt::kPartialFloats : 0;
+  pl->floats = o + 4;
+  return FC_OK;
+}
+
+size_t fc_lstm_window_workspace_bytes(int B, int save) {
+  LstmTrainPlan pl;
+  if (lstm_train_plan(B, save, &pl)) return 0;
+  return pl.floats * sizeof(float);
+}
+
+int fc_lstm_window_fwd(const float* X, const float* pack, const float* fc_w, const float* fc_b, int B, int save, float* out,
+                       void* work, size_t work_bytes, void* stream) {
+  if (!X || !pack || !fc_w || !fc_b || !out || (save && !work)) return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_fwd: null pointer%s");
+  LstmTrainPlan pl;
+  int rc = lstm_train_plan(B, save, &pl);
+  if (rc) return rc;
+  if (save && work_bytes < pl.floats * sizeof(float))
+    return fail(FC_ERR_WORKSPACE, "fc_lstm_window_fwd: workspace too small%s (%lld < %lld bytes)", "", (long long)work_bytes,
+                (long long)(pl.floats * sizeof(float)));
+  if (!aligned16(pack) || (save && !aligned16(work))) return fail(FC_ERR_MISALIGNED, "fc_lstm_window_fwd: pack / work must be 16-byte aligned%s");
+  rc = ensure_smem_attributes();
+  if (rc) return rc;
+  lt::LstmFwdParams p;
+  p.X = X; p.pack = pack; p.fc_w = fc_w; p.fc_b = fc_b; p.out = out; p.B = B; p.save = save;
+  p.rec = save ? (float*)work + pl.rec : nullptr;
+  p.hseq = save ? (float*)work + pl.hseq : nullptr;
+  lt::lstm_window_fwd_kernel<<<pl.grid, lt::kThreadsL, lt::kSmemFwd, (cudaStream_t)stream>>>(p);
+  FC_CUDA(cudaGetLastError(), "lstm_window_fwd_kernel launch");
+  return FC_OK;
+}
+
+int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, const float* fc_w, int B, void* work,
+                       size_t work_bytes, float* g_ih0, float* g_hh0, float* g_ih1, float* g_hh1, float* g_ih2, float* g_hh2,
+                       float* g_fc_w, float* g_fc_b, void* stream) {
+  if (!X || !d_out || !pack || !fc_w || !work || !g_ih0 || !g_hh0 || !g_ih1 || !g_hh1 || !g_ih2 || !g_hh2 || !g_fc_w || !g_fc_b)
+    return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_bwd: null pointer%s");
+  LstmTrainPlan pl;
+  int rc = lstm_train_plan(B, 1, &pl);
+  if (rc) return rc;
+  if (work_bytes < pl.floats * sizeof(float))
+    return fail(FC_ERR_WORKSPACE, "fc_lstm_window_bwd: workspace too small%s (%lld < %lld bytes)", "", (long long)work_bytes,
+                (long long)(pl.floats * sizeof(float)));
+  if (!aligned16(pack) || !aligned16(work)) return fail(FC_ERR_MISALIGNED, "fc_lstm_window_bwd: pack / work must be 16-byte aligned%s");
+  rc = ensure_smem_attributes();
+  if (rc) return rc;
+  lt::LstmBwdParams p;
+  p.X = X; p.d_out = d_out; p.pack = pack; p.fc_w = fc_w; p.B = B;
+  p.rec = (const float*)work + pl.rec;
+  p.hseq = (const float*)work + pl.hseq;
+  p.dseq = (float*)work + pl.dseq;
+  p.partial = (float*)work + pl.partial;
+  lt::lstm_window_bwd_kernel<<<pl.grid, lt::kThreadsL, lt::kSmemBwd, (cudaStream_t)stream>>>(p);
+  FC_CUDA(cudaGetLastError(), "lstm_window_bwd_kernel launch");
+  lt::LstmGradOut g;
+  g.g_ih[0] = g_ih0; g.g_hh[0] = g_hh0; g.g_ih[1] = g_ih1; g.g_hh[1] = g_hh1; g.g_ih[2] = g_ih2; g.g_hh[2] = g_hh2;
+  g.g_fc_w = g_fc_w; g.g_fc_b = g_fc_b;
+  lt::lstm_grad_reduce_kernel<<<296, 1024, 0, (cudaStream_t)stream>>>(p.partial, pl.grid, g);
+  FC_CUDA(cudaGetLastError(), "lstm_grad_reduce_kernel launch");
+  return FC_OK;
+}
+
+int fc_adamw_step(int count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                  const int* numel, int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float grad_scale, void* stream) {
+  if (count <= 0 || count > 8) return fail(FC_ERR_BAD_SHAPE, "fc_adamw_step: 1..8 tensors per call%s (count=%lld)", "", count);
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel) return fail(FC_ERR_NULL_POINTER, "fc_adamw_step: null pointer%s");
+  if (step < 1) return fail(FC_ERR_BAD_SHAPE, "fc_adamw_step: step counts from 1%s (step=%lld)", "", step);
+  lt::AdamWParams a;
+  int most = 0;
+  for (int k = 0; k < count; ++k) {
+    if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || numel[k] <= 0)
+      return fail(FC_ERR_NULL_POINTER, "fc_adamw_step: null pointer or empty tensor%s at index %lld", "", k);
+    a.p[k] = params[k]; a.g[k] = grads[k]; a.m[k] = exp_avg[k]; a.v[k] = exp_avg_sq[k]; a.n[k] = numel[k];
+    if (numel[k] > most) most = numel[k];
+  }
+  a.count = count;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.sqrt_bc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  int blocks = (most + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  lt::adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  FC_CUDA(cudaGetLastError(), "adamw_kernel launch");
   return FC_OK;
 }
 

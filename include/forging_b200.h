@@ -151,6 +151,35 @@ int fc_closed_loop_rk4_ex(int f64, const void* x0, const void* ref, int n_ref, i
                           int width_dim, void* meas, void* u, void* x_final, const float* process_std,
                           const float* meas_std, unsigned long long seed, void* stream);
 
+/* ---- surrogate training path: replaces, inside NeuralNetwork.train_model of the surrogate
+ * (UL/Model_NN/Functions.py:520-569), `output = model(X, device)` (:551, LSTMModel.forward :313-340) and what
+ * `loss.backward()` (:560) leaves in .grad of the eight surrogate parameters.  nn.MSELoss (UL/Model_NN/Main.py:227)
+ * stays the caller's: the backward call takes d loss/d output.
+ *   fc_lstm_train_pack        raw nn.LSTM weights (state_dict layout, float32) -> kernel images (fc_lstm_train_pack_floats()
+ *                             floats); call after every optimizer step.
+ *   fc_lstm_window_fwd        X [B,10,5] -> out [B,4]; save != 0 records the cell activations and hidden sequences
+ *                             in `workspace` (fc_lstm_window_workspace_bytes(B, 1) bytes) for the backward call;
+ *                             save == 0 needs no workspace (inference).
+ *   fc_lstm_window_bwd        d_out [B,4] + the workspace of the matching forward call -> the eight gradient tensors
+ *                             (overwritten, state_dict shapes: g_ih0 [200,5], g_hh* / g_ih1 / g_ih2 [200,50],
+ *                             g_fc_w [4,50], g_fc_b [4]).                                                          */
+size_t fc_lstm_train_pack_floats(void);
+int fc_lstm_train_pack(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1, const float* w_ih2,
+                       const float* w_hh2, float* pack, void* stream);
+size_t fc_lstm_window_workspace_bytes(int B, int save);
+int fc_lstm_window_fwd(const float* X, const float* pack, const float* fc_w, const float* fc_b, int B, int save, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, const float* fc_w, int B, void* workspace,
+                       size_t workspace_bytes, float* g_ih0, float* g_hh0, float* g_ih1, float* g_hh1, float* g_ih2,
+                       float* g_hh2, float* g_fc_w, float* g_fc_b, void* stream);
+
+/* ---- optimizer update: torch.optim.AdamW.step (UL/Main.py:195, UL/Model_NN/Main.py:230; not amsgrad,
+ * not maximize) for `count` <= 8 tensors in ONE launch.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays
+ * of `count` device pointers / element counts; `step` counts from 1; the gradient is read as grad * grad_scale.      */
+int fc_adamw_step(int count, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                  const int* numel, int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float grad_scale, void* stream);
+
 /* ---- measurement helper: register-resident FFMA loop used by bench.py to measure the FP32
  * roofline denominator on the device it runs on; writes achieved FLOP/s to *flops_host.           */
 int fc_fp32_peak(int iters, double* flops_host, void* stream);

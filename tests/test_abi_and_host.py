@@ -115,3 +115,23 @@ def test_install_swaps_hot_path_into_a_reference_like_module():
     fb.install(ref)
     assert ref.MPCLoss is fb.MPCLoss and ref.FNNModel is fb.FNNModel and ref.LSTMModel is fb.LSTMModel
     assert ref.NeuralNetwork.loop is fb.NeuralNetwork.loop
+
+
+def test_lstm_model_on_cpu_is_the_stock_module_and_device_adamw_refuses_cpu():
+    """The surrogate kernels serve CUDA tensors only: CPU evaluation (Main.py:347-361 after ``.cpu()``) stays stock
+    ``nn.LSTM``; the device optimizer has no CPU path."""
+    import torch
+    import forging_control_b200 as fb
+    from forging_control_b200 import surrogate as S
+    m = fb.LSTMModel(5, 50, 4, 3)
+    x = torch.zeros(2, 10, 5)
+    assert not S.supported(m, x)
+    assert m(x, "cpu").shape == (2, 4)
+    with pytest.raises(NotImplementedError):
+        S.lstm_window(m, x)
+    opt = S.DeviceAdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
+    m(x, "cpu").sum().backward()
+    with pytest.raises(RuntimeError):
+        opt.step()
+    with pytest.raises(NotImplementedError):
+        S.DeviceAdamW(m.parameters(), amsgrad=True)
