@@ -15,8 +15,9 @@
 //
 // Tile = 40 samples, 250 compute threads of 256: thread (ug = tid/10, tg = tid%10) owns hidden units 2ug, 2ug+1 (all four
 // gates) of samples 4tg..4tg+3, so cell state, d(cell) and the recurrent d(h) stay in registers; the same thread grid
-// owns an 8-row x 10-column block of the 200 x 100 weight-gradient matrix [W_ih | W_hh] of the current layer, held in
-// 80 registers over the 10 time steps.  All shared-memory operands are [row][40 samples] and are read as float4.
+// owns 8 rows x 10 columns of the 200 x 100 weight-gradient matrix [W_ih | W_hh] of the current layer, held in
+// 80 registers over the 10 time steps (rows ug + 25 r, columns tg + 10 j).  All shared-memory operands are [row][samples]
+// and are read as float4.
 #pragma once
 
 namespace fc {
@@ -35,7 +36,9 @@ constexpr size_t kHseqFloatsTile = (size_t)30 * kH * kTT;
 constexpr size_t kDseqFloatsCta = (size_t)kL * 2 * kThreadsL * 4;
 constexpr int kPartialFloats = 3 * kG * 100 + 200 + 4;       // per CTA: dW_l [200][100] x 3, d fc.weight, d fc.bias
 constexpr int kSmemFwd = (100 * kG + kL * kH * kTT + kL * 5 * kTT) * 4;                 // 168 000 B
-constexpr int kSmemBwd = (kG * 100 + kG * kTT + 2 * 100 * kTT + 4 * kTT) * 4;           // 144 640 B
+constexpr int kSB = 44;                 // row stride (floats) of the backward shared-memory operands: 44 mod 32 = 12 puts the rows
+                                        // of threads that differ in ug or tg by one into different 16-byte bank groups
+constexpr int kSmemBwd = (kG * 100 + kG * kSB + 100 * kSB + 4 * kTT) * 4;               // 133 440 B
 
 __host__ __device__ inline int wf_offset(int l) { return l == 0 ? 0 : (l == 1 ? 55 * kG : 155 * kG); }
 
@@ -220,9 +223,9 @@ struct LstmBwdParams {
 
 __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const LstmBwdParams p) {
   float* WB = fc_dyn_smem;                       // [200][25][4]
-  float* dG = WB + kG * 100;                     // [200][40]
-  float* act = dG + kG * kTT;                    // [2][100][40]: rows 0..49 layer input at t, 50..99 own h at t-1
-  float* dout = act + 2 * 100 * kTT;             // [4][40]
+  float* dG = WB + kG * 100;                     // [200][kSB]
+  float* act = dG + kG * kSB;                    // [100][kSB]: rows 0..49 layer input at t, 50..99 own h at t-1
+  float* dout = act + 100 * kSB;                 // [4][40]
   const int tid = threadIdx.x;
   const bool active = tid < kActive;
   const int ug = active ? tid / 10 : 0, tg = active ? tid % 10 : 0;
@@ -275,23 +278,25 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
         }
       }
       for (int t = kL - 1; t >= 0; --t) {
-        float* ab = act + (t & 1) * 100 * kTT;
+        float* ab = act;
         // stage the operands of the weight-gradient product
         if (l > 0) {
           const float* src = hs_tile + (size_t)((l - 1) * kL + t) * kH * kTT;
-          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4) st4(ab + i, __ldcg(reinterpret_cast<const float4*>(src + i)));
+          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
+            st4(ab + (i / kTT) * kSB + i % kTT, __ldcg(reinterpret_cast<const float4*>(src + i)));
         } else {
           for (int i = tid; i < kH * kTT; i += kThreadsL) {
             const int b = i % kTT, k = i / kTT;
-            ab[i] = (k < 5 && b0 + b < p.B) ? __ldg(p.X + (size_t)(b0 + b) * 50 + t * 5 + k) : 0.f;
+            ab[k * kSB + b] = (k < 5 && b0 + b < p.B) ? __ldg(p.X + (size_t)(b0 + b) * 50 + t * 5 + k) : 0.f;
           }
         }
         if (t > 0) {
           const float* src = hs_tile + (size_t)(l * kL + t - 1) * kH * kTT;
           for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
-            st4(ab + kH * kTT + i, __ldcg(reinterpret_cast<const float4*>(src + i)));
+            st4(ab + (kH + i / kTT) * kSB + i % kTT, __ldcg(reinterpret_cast<const float4*>(src + i)));
         } else {
-          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4) st4(ab + kH * kTT + i, make_float4(0.f, 0.f, 0.f, 0.f));
+          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
+            st4(ab + (kH + i / kTT) * kSB + i % kTT, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         if (active) {
           // gradient arriving from above: fc (top layer, last step) or the layer above's d(input)
@@ -316,6 +321,11 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
             }
           }
           const float* r = rec_tile + (size_t)(l * kL + t) * kRecSlots * kThreadsL * 4;
+          if (t > 0 && (tid & 7) == 0) {                           // records of the next step (t-1): one 128-byte line per 8 lanes
+            const float* rn = r - (size_t)kRecSlots * kThreadsL * 4;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + sl * kThreadsL * 4));
+          }
           float cprev[8];
           if (t > 0) {
             const float* rp = r - (size_t)kRecSlots * kThreadsL * 4;
@@ -351,10 +361,10 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
               cnext[e] = cprev[e];
             }
             const int u = 2 * ug + uu;
-            st4(dG + (0 * kH + u) * kTT + tg * 4, make_float4(di[0], di[1], di[2], di[3]));
-            st4(dG + (1 * kH + u) * kTT + tg * 4, make_float4(df[0], df[1], df[2], df[3]));
-            st4(dG + (2 * kH + u) * kTT + tg * 4, make_float4(dg[0], dg[1], dg[2], dg[3]));
-            st4(dG + (3 * kH + u) * kTT + tg * 4, make_float4(dov[0], dov[1], dov[2], dov[3]));
+            st4(dG + (0 * kH + u) * kSB + tg * 4, make_float4(di[0], di[1], di[2], di[3]));
+            st4(dG + (1 * kH + u) * kSB + tg * 4, make_float4(df[0], df[1], df[2], df[3]));
+            st4(dG + (2 * kH + u) * kSB + tg * 4, make_float4(dg[0], dg[1], dg[2], dg[3]));
+            st4(dG + (3 * kH + u) * kSB + tg * 4, make_float4(dov[0], dov[1], dov[2], dov[3]));
           }
         }
         __syncthreads();                                           // dG, act (and WB on the first step) are visible
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
           const float* dp = dG + tg * 4;
 #pragma unroll 8
           for (int row = 0; row < kG; ++row) {
-            const float4 w = ld4(wb + row * 100), d = ld4(dp + row * kTT);
+            const float4 w = ld4(wb + row * 100), d = ld4(dp + row * kSB);
             const float wv[4] = {w.x, w.y, w.z, w.w}, dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -386,17 +396,18 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
           for (int uu = 0; uu < 2; ++uu)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dhrec[uu * 4 + j] = da[2 + uu][j];
-          // weight gradients: rows 8ug..8ug+7 x columns 10tg..10tg+9 of [dW_ih | dW_hh], reduction over the 40 samples
-          const float* gp = dG + (ug * 8) * kTT;
-          const float* cp = ab + (tg * 10) * kTT;
+          // weight gradients: rows ug + 25 r8 (r8 < 8) x columns tg + 10 j (j < 10) of [dW_ih | dW_hh], reduction over
+          // the 40 samples (interleaved ownership: conflict-free float4 reads with the 44-float row stride)
+          const float* gp = dG + ug * kSB;
+          const float* cp = ab + tg * kSB;
 #pragma unroll 1
           for (int bq = 0; bq < kTT; bq += 4) {
             float4 d4[8];
 #pragma unroll
-            for (int r8 = 0; r8 < 8; ++r8) d4[r8] = ld4(gp + r8 * kTT + bq);
+            for (int r8 = 0; r8 < 8; ++r8) d4[r8] = ld4(gp + r8 * 25 * kSB + bq);
 #pragma unroll
             for (int j = 0; j < 10; ++j) {
-              const float4 a = ld4(cp + j * kTT + bq);
+              const float4 a = ld4(cp + j * 10 * kSB + bq);
 #pragma unroll
               for (int r8 = 0; r8 < 8; ++r8) {
                 float s = wacc[r8][j];
@@ -409,15 +420,15 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
             }
           }
         }
-        __syncthreads();                                           // dG and act[t&1] may be overwritten
+        __syncthreads();                                           // dG and act may be overwritten
       }
       if (active) {
-        float* dst = part + (size_t)l * kG * 100 + (size_t)(ug * 8) * 100 + tg * 10;
+        float* dst = part + (size_t)l * kG * 100 + (size_t)ug * 100 + tg;
 #pragma unroll
         for (int r8 = 0; r8 < 8; ++r8)
 #pragma unroll
           for (int j = 0; j < 10; ++j) {
-            float* q = dst + r8 * 100 + j;
+            float* q = dst + r8 * 2500 + j * 10;
             *q = first ? wacc[r8][j] : *q + wacc[r8][j];
           }
       }
