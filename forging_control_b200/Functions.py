@@ -90,8 +90,9 @@ class LSTMModel(nn.Module):
 
     def initialize_hidden_states(self, batch_size: int, device: torch.device):
         shape = (self.layer_dim, batch_size, self.hidden_dim)
-        return (torch.zeros(shape, device=device).requires_grad_(),
-                torch.zeros(shape, device=device).requires_grad_())
+        dt = self.lstm.weight_ih_l0.dtype       # the reference uses the default dtype; follow the weights (.double() models)
+        return (torch.zeros(shape, device=device, dtype=dt).requires_grad_(),
+                torch.zeros(shape, device=device, dtype=dt).requires_grad_())
 
     def forward(self, x: torch.Tensor, device: torch.device):
         from . import surrogate

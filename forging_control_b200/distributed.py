@@ -51,3 +51,15 @@ def sharded_training_step(loss_function, simulator, controller, X, Z, device, gl
     loss.backward()
     params = [controller.fc_inp.weight, controller.fc_inp.bias, controller.fc_out.weight]
     return allreduce_loss_and_grads(loss, params, group)
+
+
+def sharded_surrogate_step(model, loss_function, X, y, device, global_batch: int, group=None):
+    """One data-parallel surrogate-training step on this rank's shard (X [b,10,5], y [b,1,4] on
+    ``device``): body of the surrogate ``train_model`` (Model_NN/Functions.py:548-560) with the batch mean of
+    ``loss_function`` (``nn.MSELoss``) re-weighted by ``b / global_batch`` and ONE all-reduce(sum) over the flat
+    ``[51 204 gradients | loss]`` buffer.  Leaves the global gradients in ``model.parameters()``, returns the global loss."""
+    for p in model.parameters():
+        p.grad = None
+    loss = loss_function(model(X, device), y.squeeze(1)) * (X.shape[0] / float(global_batch))
+    loss.backward()
+    return allreduce_loss_and_grads(loss, list(model.parameters()), group)

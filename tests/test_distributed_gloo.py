@@ -78,3 +78,41 @@ def test_two_rank_allreduce_equals_single_process():
     for a, b in zip(grads, (g["inp_w"], g["inp_b"], g["out_w"])):
         assert np.abs(a - b).max() / np.abs(b).max() < 1e-12
     assert abs(loss - float(C[f"{name}/f64/loss"])) / abs(loss) < 1e-12      # == the reference on the full batch
+
+
+def _surrogate_worker(rank, world, port, q):
+    import sys
+    for p in (REPO, os.path.join(REPO, "oracle")):
+        sys.path.insert(0, p)
+    import forging_control_b200 as fb
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C = np.load(os.path.join(GOLDEN, "surrogate_train_cases.npz"))
+    W = np.load(os.path.join(GOLDEN, "weights.npz"))
+    m = fb.LSTMModel(5, 50, 4, 3).double()            # CPU tensors: the stock nn.LSTM path carries the host-side logic
+    m.load_state_dict({k[5:]: torch.tensor(W[k]).double() for k in W.files if k.startswith("lstm/")})
+    X, y = torch.tensor(C["shipped_b37/X"]).double(), torch.tensor(C["shipped_b37/y"]).double()
+    lo, hi = fb.shard_bounds(len(X), world, rank)
+    total = fb.sharded_surrogate_step(m, torch.nn.MSELoss(), X[lo:hi], y[lo:hi], "cpu", global_batch=len(X))
+    if rank == 0:
+        q.put((total.item(), {k: p.grad.numpy().copy() for k, p in m.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_surrogate_step_equals_the_reference_full_batch_step():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_surrogate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    loss, grads = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    C = np.load(os.path.join(GOLDEN, "surrogate_train_cases.npz"))
+    assert abs(loss - float(C["shipped_b37/f64/avg_loss"])) <= 1e-12 * abs(loss)
+    for k, g in grads.items():
+        ref = C[f"shipped_b37/f64/grad/{k}"]
+        assert np.abs(g - ref).max() <= 1e-11 * np.abs(ref).max(), k
