@@ -33,7 +33,7 @@ def install(reference_functions_module) -> None:
 
 
 def install_surrogate(reference_model_nn_functions_module) -> None:
-    """The same for the surrogate-training script (``Model_NN/Main.py:19`` imports ``Model_NN/Functions.py``):
+    """The same for the surrogate-training script (``Model_NN/Main.py:26`` imports ``Model_NN/Functions.py``):
 
         import Functions, forging_control_b200 as fb; fb.install_surrogate(Functions)
     """

@@ -3,7 +3,7 @@
 Generates ``tests/golden/surrogate_train_cases.npz`` by RUNNING THE UNMODIFIED REFERENCE surrogate-training step
 (``UL/Model_NN/Functions.py`` imported by path through ``oracle/ref_shim.py``) in the build container:
 ``NeuralNetwork.train_model`` (:520-569) with ``LSTMModel(5, 50, 4, 3)`` (:255-340), ``nn.MSELoss()`` and
-``torch.optim.AdamW(lr=1e-3, weight_decay=0.0)`` (UL/Model_NN/Main.py:221-230), in fp32 and fp64.  Run from the
+``torch.optim.AdamW(lr=1e-3, weight_decay=0.0)`` (UL/Model_NN/Main.py:224-230), in fp32 and fp64.  Run from the
 repo root:
 
     python oracle/make_golden_surrogate.py
