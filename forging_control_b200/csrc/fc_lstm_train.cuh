@@ -38,7 +38,7 @@ constexpr int kPartialFloats = 3 * kG * 100 + 200 + 4;       // per CTA: dW_l [2
 constexpr int kSmemFwd = (100 * kG + kL * kH * kTT + kL * 5 * kTT) * 4;                 // 168 000 B
 constexpr int kSB = 44;                 // row stride (floats) of the backward shared-memory operands: 44 mod 32 = 12 puts the rows
                                         // of threads that differ in ug or tg by one into different 16-byte bank groups
-constexpr int kSmemBwd = (kG * 100 + kG * kSB + 100 * kSB + 4 * kTT) * 4;               // 133 440 B
+constexpr int kSmemBwd = (kG * 100 + kG * kSB + 2 * 100 * kSB + 4 * kTT) * 4;           // 151 040 B
 
 __host__ __device__ inline int wf_offset(int l) { return l == 0 ? 0 : (l == 1 ? 55 * kG : 155 * kG); }
 
@@ -224,8 +224,8 @@ struct LstmBwdParams {
 __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const LstmBwdParams p) {
   float* WB = fc_dyn_smem;                       // [200][25][4]
   float* dG = WB + kG * 100;                     // [200][kSB]
-  float* act = dG + kG * kSB;                    // [100][kSB]: rows 0..49 layer input at t, 50..99 own h at t-1
-  float* dout = act + 100 * kSB;                 // [4][40]
+  float* act = dG + kG * kSB;                    // [2][100][kSB]: rows 0..49 layer input at t, 50..99 own h at t-1
+  float* dout = act + 2 * 100 * kSB;             // [4][40]
   const int tid = threadIdx.x;
   const bool active = tid < kActive;
   const int ug = active ? tid / 10 : 0, tg = active ? tid % 10 : 0;
@@ -277,27 +277,32 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
           cnext[uu * 4 + 0] = v.x; cnext[uu * 4 + 1] = v.y; cnext[uu * 4 + 2] = v.z; cnext[uu * 4 + 3] = v.w;
         }
       }
-      for (int t = kL - 1; t >= 0; --t) {
-        float* ab = act;
-        // stage the operands of the weight-gradient product
+      // operands of the weight-gradient product for step tt -> act[tt & 1], one step ahead of their use (cp.async;
+      // the buffer written is not the one the current step's products read)
+      auto stage = [&](int tt) {
+        float* dstb = act + (tt & 1) * 100 * kSB;
         if (l > 0) {
-          const float* src = hs_tile + (size_t)((l - 1) * kL + t) * kH * kTT;
-          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
-            st4(ab + (i / kTT) * kSB + i % kTT, __ldcg(reinterpret_cast<const float4*>(src + i)));
+          const float* src = hs_tile + (size_t)((l - 1) * kL + tt) * kH * kTT;
+          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4) DevCtx::cp_async16(dstb + (i / kTT) * kSB + i % kTT, src + i);
         } else {
           for (int i = tid; i < kH * kTT; i += kThreadsL) {
             const int b = i % kTT, k = i / kTT;
-            ab[k * kSB + b] = (k < 5 && b0 + b < p.B) ? __ldg(p.X + (size_t)(b0 + b) * 50 + t * 5 + k) : 0.f;
+            dstb[k * kSB + b] = (k < 5 && b0 + b < p.B) ? __ldg(p.X + (size_t)(b0 + b) * 50 + tt * 5 + k) : 0.f;
           }
         }
-        if (t > 0) {
-          const float* src = hs_tile + (size_t)(l * kL + t - 1) * kH * kTT;
+        if (tt > 0) {
+          const float* src = hs_tile + (size_t)(l * kL + tt - 1) * kH * kTT;
           for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
-            st4(ab + (kH + i / kTT) * kSB + i % kTT, __ldcg(reinterpret_cast<const float4*>(src + i)));
+            DevCtx::cp_async16(dstb + (kH + i / kTT) * kSB + i % kTT, src + i);
         } else {
           for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
-            st4(ab + (kH + i / kTT) * kSB + i % kTT, make_float4(0.f, 0.f, 0.f, 0.f));
+            st4(dstb + (kH + i / kTT) * kSB + i % kTT, make_float4(0.f, 0.f, 0.f, 0.f));
         }
+        DevCtx::cp_commit();
+      };
+      stage(kL - 1);
+      for (int t = kL - 1; t >= 0; --t) {
+        float* ab = act + (t & 1) * 100 * kSB;
         if (active) {
           // gradient arriving from above: fc (top layer, last step) or the layer above's d(input)
           float dh[8];
@@ -367,7 +372,9 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
             st4(dG + (3 * kH + u) * kSB + tg * 4, make_float4(dov[0], dov[1], dov[2], dov[3]));
           }
         }
+        DevCtx::cp_wait<0>();
         __syncthreads();                                           // dG, act (and WB on the first step) are visible
+        if (t > 0) stage(t - 1);
         if (active) {
           // data gradients: d(input units 2ug, 2ug+1) and d(h_{t-1} units 2ug, 2ug+1) of samples 4tg..4tg+3
           float da[4][4];

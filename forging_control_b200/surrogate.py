@@ -51,19 +51,23 @@ def supported(model, x) -> bool:
 
 
 def _pack(ws) -> torch.Tensor:
-    """Kernel weight images of the six LSTM matrices, re-packed when a parameter changed (``_version``)."""
+    """Kernel weight images of the six LSTM matrices, re-packed when a parameter changed (``_version``).  A re-pack
+    always writes a FRESH buffer: an autograd graph that still holds the previous images for its backward keeps them."""
     dev = ws[0].device
+    ident = (dev.index, id(ws[0]))
     key = tuple((w.data_ptr(), w._version) for w in ws[:6])
-    slot = _PACK_CACHE.get(dev.index)
+    slot = _PACK_CACHE.get(ident)
     if slot is not None and slot[0] == key and all(r() is w for r, w in zip(slot[2], ws[:6])):
         return slot[1]
     L = _native.lib()
-    buf = slot[1] if slot is not None else torch.empty(int(L.fc_lstm_train_pack_floats()), dtype=torch.float32, device=dev)
+    buf = torch.empty(int(L.fc_lstm_train_pack_floats()), dtype=torch.float32, device=dev)
     wc = [w.detach().contiguous() for w in ws[:6]]
     with torch.cuda.device(dev):
         rc = L.fc_lstm_train_pack(*[_native.ptr(w) for w in wc], _native.ptr(buf), _native.stream_ptr(dev))
     _native.check(rc, "fc_lstm_train_pack")
-    _PACK_CACHE[dev.index] = (key, buf, [weakref.ref(w) for w in ws[:6]])
+    for k in [k for k, v in _PACK_CACHE.items() if any(r() is None for r in v[2])]:    # models that are gone
+        del _PACK_CACHE[k]
+    _PACK_CACHE[ident] = (key, buf, [weakref.ref(w) for w in ws[:6]])
     return buf
 
 
@@ -90,7 +94,6 @@ class _LstmWindow(torch.autograd.Function):
         _native.check(rc, "fc_lstm_window_fwd")
         ctx.saved = save
         if save:
-            # the weight images are cloned only if the parameters change before backward (they do not in train_model)
             ctx.save_for_backward(xc, pack, fc_w, work)
             ctx.shapes = [w.shape for w in ws]
         return out
@@ -136,7 +139,7 @@ class DeviceAdamW(torch.optim.AdamW):
     3 live tensors, the surrogate 8).  Constructor, hyper-parameters, ``param_groups`` and ``state_dict`` are torch's
     (state entries ``step`` / ``exp_avg`` / ``exp_avg_sq``), so checkpoints interchange with the stock optimizer."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, maximize=False, **kw):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, maximize=False):
         if amsgrad or maximize:
             raise NotImplementedError("DeviceAdamW: amsgrad / maximize are not used by the reference and not implemented")
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
