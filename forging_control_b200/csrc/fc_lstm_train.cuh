@@ -388,8 +388,14 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
           for (int row = 0; row < kG; ++row) {
             const float4 w = ld4(wb + row * 100), d = ld4(dp + row * kSB);
             const float wv[4] = {w.x, w.y, w.z, w.w}, dv[4] = {d.x, d.y, d.z, d.w};
+            if (l > 0) {                                           // the bottom layer's inputs are data: no d(input)
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+              for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) da[q][j] = fmaf(wv[q], dv[j], da[q][j]);
+            }
+#pragma unroll
+            for (int q = 2; q < 4; ++q)
 #pragma unroll
               for (int j = 0; j < 4; ++j) da[q][j] = fmaf(wv[q], dv[j], da[q][j]);
           }
@@ -414,6 +420,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
             for (int r8 = 0; r8 < 8; ++r8) d4[r8] = ld4(gp + r8 * 25 * kSB + bq);
 #pragma unroll
             for (int j = 0; j < 10; ++j) {
+              if (l == 0 && j >= 1 && j <= 4) continue;            // bottom layer: input columns 5..49 do not exist
               const float4 a = ld4(cp + j * 10 * kSB + bq);
 #pragma unroll
               for (int r8 = 0; r8 < 8; ++r8) {

@@ -325,7 +325,7 @@ struct MpcPair {
       float gi, gf, go, rg;
       quad_rcp(di, df, dq, dg, gi, gf, go, rg);
       const float gg = tanh_from_(xg, rg);
-      const float cp = c[j0 + i];                            // zeroed by the caller at t = 0
+      const float cp = first ? 0.f : c[j0 + i];
       cn[i] = fmaf(gf, cp, gi * gg);
       c[j0 + i] = cn[i];
       rv[i * 5 + 0] = gi; rv[i * 5 + 1] = gf; rv[i * 5 + 2] = gg; rv[i * 5 + 3] = go; rv[i * 5 + 4] = cp;
@@ -465,10 +465,6 @@ struct MpcPair {
     lap(1);
     if (l > 0 && t + 1 < kLook) copy_input(X, t + 1);        // input block of step t+1: lands during the cell update
     if (l == 0 && scalar && t + 1 < kLook) store_features(X, xin);
-    if (t == 0) {
-#pragma unroll
-      for (int j = 0; j < kMaxOwn; ++j) c[j] = 0.f;          // LSTMModel.initialize_hidden_states: zero state, :331-351
-    }
     fwd_pointwise(X, t == 0, corr, h, rec_out);
     if (l + 1 < kLayers || t + 1 < kLook) {
       F4 hi4[3], lo4[3];
