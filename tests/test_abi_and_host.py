@@ -135,3 +135,32 @@ def test_lstm_model_on_cpu_is_the_stock_module_and_device_adamw_refuses_cpu():
         opt.step()
     with pytest.raises(NotImplementedError):
         S.DeviceAdamW(m.parameters(), amsgrad=True)
+
+
+def test_install_surrogate_swaps_the_training_step_and_host_loop_matches_the_reference_on_cpu():
+    """``install_surrogate`` on a reference-like module; the mirrored ``train_model`` / ``validate_model`` /
+    ``train_loop`` (Model_NN/Functions.py:520-612, 754-822) reproduce the golden epoch of the unmodified reference when
+    fed CPU tensors (stock ``nn.LSTM`` carries the arithmetic there, so this pins the HOST logic: loop order,
+    ``y.squeeze()``, averaging over batches, optimizer placement)."""
+    import types
+    import torch
+    from forging_control_b200 import surrogate as S
+    ref = types.SimpleNamespace(NeuralNetwork=type("NeuralNetwork", (), {}))
+    fb.install_surrogate(ref)
+    assert ref.LSTMModel is fb.LSTMModel and ref.NeuralNetwork.train_model is S.SurrogateNeuralNetwork.train_model
+    C = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "surrogate_train_cases.npz"))
+    keys = [k.split("/")[-1] for k in C.files if k.startswith("fresh_b256x3/init/")]
+    m = fb.LSTMModel(5, 50, 4, 3)
+    m.load_state_dict({k: torch.tensor(C[f"fresh_b256x3/init/{k}"]) for k in keys}, strict=True)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
+    loader = [(torch.tensor(C[f"fresh_b256x3/X{b}"]), torch.tensor(C[f"fresh_b256x3/y{b}"])) for b in range(3)]
+    avg = ref.NeuralNetwork.train_model(loader, m, torch.nn.MSELoss(), opt, "cpu")
+    assert abs(avg - float(C["fresh_b256x3/f32/avg_loss"])) <= 1e-6 * abs(avg)
+    for k, p in m.named_parameters():
+        init = C[f"fresh_b256x3/init/{k}"]
+        d_ref = C[f"fresh_b256x3/f32/after/{k}"] - init
+        assert np.abs((p.detach().numpy() - init) - d_ref).max() <= 1e-3 * np.abs(d_ref).max(), k
+    v = S.SurrogateNeuralNetwork.validate_model(loader, m, torch.nn.MSELoss(), "cpu")
+    assert np.isfinite(v) and v < avg                     # three AdamW steps later the same batches fit better
+    _, vt, vv, _ = S.SurrogateNeuralNetwork.train_loop(m, loader[:1], loader[1:2], torch.nn.MSELoss(), opt, 2, "cpu")
+    assert len(vt) == 2 and len(vv) == 2 and vt[1] < vt[0]
