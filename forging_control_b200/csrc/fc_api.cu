@@ -954,7 +954,7 @@ int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, co
   lt::LstmGradOut g;
   g.g_ih[0] = g_ih0; g.g_hh[0] = g_hh0; g.g_ih[1] = g_ih1; g.g_hh[1] = g_hh1; g.g_ih[2] = g_ih2; g.g_hh[2] = g_hh2;
   g.g_fc_w = g_fc_w; g.g_fc_b = g_fc_b;
-  lt::lstm_grad_reduce_kernel<<<296, 1024, 0, (cudaStream_t)stream>>>(p.partial, pl.grid, g);
+  lt::lstm_grad_reduce_kernel<<<(51204 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p.partial, pl.grid, g);
   FC_CUDA(cudaGetLastError(), "lstm_grad_reduce_kernel launch");
   return FC_OK;
 }

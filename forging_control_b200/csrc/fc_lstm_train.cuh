@@ -450,35 +450,39 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
   }
 }
 
-// gradient tensors <- sum over CTAs of the partials (one warp per element, fp64 accumulation); scale = upstream factor
-__global__ void __launch_bounds__(1024) lstm_grad_reduce_kernel(const float* __restrict__ partial, int grid, LstmGradOut g) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// gradient tensors <- sum over CTAs of the partials: one thread per element (consecutive elements read consecutive
+// partial entries: coalesced), fp64 accumulation in a fixed order
+__global__ void __launch_bounds__(256) lstm_grad_reduce_kernel(const float* __restrict__ partial, int grid, LstmGradOut g) {
   constexpr int kOut = 200 * 5 + 5 * 200 * 50 + 200 + 4;         // 51 204
-  for (int i = blockIdx.x * 32 + warp; i < kOut; i += gridDim.x * 32) {
-    int src;
-    float* dst;
-    if (i < 1000) {                                               // weight_ih_l0 [200][5]
-      src = (i / 5) * 100 + (i % 5);
-      dst = g.g_ih[0] + i;
-    } else if (i < 51000) {
-      const int r = i - 1000, blk = r / 10000, q = r % 10000;      // hh0, ih1, hh1, ih2, hh2
-      const int l = (blk + 1) >> 1;
-      const bool hh = (blk & 1) == 0;
-      src = l * kG * 100 + (q / 50) * 100 + (hh ? 50 : 0) + (q % 50);
-      dst = (hh ? g.g_hh[l] : g.g_ih[l]) + q;
-    } else if (i < 51200) {
-      src = 3 * kG * 100 + (i - 51000);
-      dst = g.g_fc_w + (i - 51000);
-    } else {
-      src = 3 * kG * 100 + 200 + (i - 51200);
-      dst = g.g_fc_b + (i - 51200);
-    }
-    double a = 0.0;
-    for (int b = lane; b < grid; b += 32) a += (double)partial[(size_t)b * kPartialFloats + src];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) *dst = (float)a;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kOut) return;
+  int src;
+  float* dst;
+  if (i < 1000) {                                                 // weight_ih_l0 [200][5]
+    src = (i / 5) * 100 + (i % 5);
+    dst = g.g_ih[0] + i;
+  } else if (i < 51000) {
+    const int r = i - 1000, blk = r / 10000, q = r % 10000;        // hh0, ih1, hh1, ih2, hh2
+    const int l = (blk + 1) >> 1;
+    const bool hh = (blk & 1) == 0;
+    src = l * kG * 100 + (q / 50) * 100 + (hh ? 50 : 0) + (q % 50);
+    dst = (hh ? g.g_hh[l] : g.g_ih[l]) + q;
+  } else if (i < 51200) {
+    src = 3 * kG * 100 + (i - 51000);
+    dst = g.g_fc_w + (i - 51000);
+  } else {
+    src = 3 * kG * 100 + 200 + (i - 51200);
+    dst = g.g_fc_b + (i - 51200);
   }
+  double a0 = 0.0, a1 = 0.0;
+  const float* pp = partial + src;
+  int b = 0;
+  for (; b + 1 < grid; b += 2) {
+    a0 += (double)__ldcg(pp + (size_t)b * kPartialFloats);
+    a1 += (double)__ldcg(pp + (size_t)(b + 1) * kPartialFloats);
+  }
+  if (b < grid) a0 += (double)__ldcg(pp + (size_t)b * kPartialFloats);
+  *dst = (float)(a0 + a1);
 }
 
 // ---------------------------------------------------------------------------------------------------
