@@ -570,6 +570,8 @@ static int ensure_smem_attributes() {
           "cudaFuncSetAttribute(smem, pair)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd),
           "cudaFuncSetAttribute(smem, lstm fwd)");
+  FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd80),
+          "cudaFuncSetAttribute(smem, lstm fwd80)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemBwd),
           "cudaFuncSetAttribute(smem, lstm bwd)");
   if (dev >= 0 && dev < 64) done[dev] = true;
@@ -876,14 +878,13 @@ int fc_lstm_train_pack(const float* w_ih0, const float* w_hh0, const float* w_ih
   if (!aligned16(pack)) return fail(FC_ERR_MISALIGNED, "fc_lstm_train_pack: pack must be 16-byte aligned%s");
   lt::LstmRaw w;
   w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
-  w.fc_w = nullptr; w.fc_b = nullptr;
   lt::pack_lstm_train_kernel<<<(lt::kPackFloatsL + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, pack);
   FC_CUDA(cudaGetLastError(), "pack_lstm_train_kernel launch");
   return FC_OK;
 }
 
 struct LstmTrainPlan {
-  int tiles, grid;
+  int tiles, pairs, grid, grid_f, wide;        // 40-sample tiles, pairs of them, CTAs (reverse / forward), 80-sample forward
   size_t rec, hseq, dseq, partial, floats;     // offsets in floats
 };
 static int lstm_train_plan(int B, int save, LstmTrainPlan* pl) {
@@ -892,10 +893,13 @@ static int lstm_train_plan(int B, int save, LstmTrainPlan* pl) {
   int rc = sm_count(&sms);
   if (rc) return rc;
   pl->tiles = (B + lt::kTT - 1) / lt::kTT;
+  pl->pairs = (pl->tiles + 1) / 2;
   pl->grid = pl->tiles < sms ? pl->tiles : sms;
+  pl->wide = pl->tiles > sms;                  // more tiles than SMs: throughput matters, use the 80-sample forward
+  pl->grid_f = pl->wide ? (pl->pairs < sms ? pl->pairs : sms) : pl->grid;
   size_t o = 0;
-  pl->rec = o;  o += save ? (size_t)pl->tiles * lt::kRecFloatsTile : 0;
-  pl->hseq = o; o += save ? (size_t)pl->tiles * lt::kHseqFloatsTile : 0;
+  pl->rec = o;  o += save ? (size_t)pl->pairs * lt::kRecFloatsPair : 0;
+  pl->hseq = o; o += save ? (size_t)pl->pairs * lt::kHseqFloatsPair : (pl->wide ? (size_t)pl->grid_f * lt::kHseqFloatsPair : 0);
   pl->dseq = o; o += save ? (size_t)pl->grid * lt::kDseqFloatsCta : 0;
   pl->partial = o; o += save ? (size_t)pl->grid * lt::kPartialFloats : 0;
   pl->floats = o + 4;
@@ -910,21 +914,26 @@ size_t fc_lstm_window_workspace_bytes(int B, int save) {
 
 int fc_lstm_window_fwd(const float* X, const float* pack, const float* fc_w, const float* fc_b, int B, int save, float* out,
                        void* work, size_t work_bytes, void* stream) {
-  if (!X || !pack || !fc_w || !fc_b || !out || (save && !work)) return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_fwd: null pointer%s");
+  if (!X || !pack || !fc_w || !fc_b || !out) return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_fwd: null pointer%s");
   LstmTrainPlan pl;
   int rc = lstm_train_plan(B, save, &pl);
   if (rc) return rc;
-  if (save && work_bytes < pl.floats * sizeof(float))
+  const bool need_work = save || pl.wide;
+  if (need_work && !work) return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_fwd: workspace required%s");
+  if (need_work && work_bytes < pl.floats * sizeof(float))
     return fail(FC_ERR_WORKSPACE, "fc_lstm_window_fwd: workspace too small%s (%lld < %lld bytes)", "", (long long)work_bytes,
                 (long long)(pl.floats * sizeof(float)));
-  if (!aligned16(pack) || (save && !aligned16(work))) return fail(FC_ERR_MISALIGNED, "fc_lstm_window_fwd: pack / work must be 16-byte aligned%s");
+  if (!aligned16(pack) || (need_work && !aligned16(work))) return fail(FC_ERR_MISALIGNED, "fc_lstm_window_fwd: pack / work must be 16-byte aligned%s");
   rc = ensure_smem_attributes();
   if (rc) return rc;
   lt::LstmFwdParams p;
   p.X = X; p.pack = pack; p.fc_w = fc_w; p.fc_b = fc_b; p.out = out; p.B = B; p.save = save;
   p.rec = save ? (float*)work + pl.rec : nullptr;
-  p.hseq = save ? (float*)work + pl.hseq : nullptr;
-  lt::lstm_window_fwd_kernel<<<pl.grid, lt::kThreadsL, lt::kSmemFwd, (cudaStream_t)stream>>>(p);
+  p.hseq = need_work ? (float*)work + pl.hseq : nullptr;
+  if (pl.wide)
+    lt::lstm_window_fwd80_kernel<<<pl.grid_f, lt::kThreadsL, lt::kSmemFwd80, (cudaStream_t)stream>>>(p);
+  else
+    lt::lstm_window_fwd_kernel<<<pl.grid, lt::kThreadsL, lt::kSmemFwd, (cudaStream_t)stream>>>(p);
   FC_CUDA(cudaGetLastError(), "lstm_window_fwd_kernel launch");
   return FC_OK;
 }

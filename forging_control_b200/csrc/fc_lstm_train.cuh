@@ -6,7 +6,7 @@
 //   lstm_window_bwd_kernel   what loss.backward() (Model_NN/Functions.py:560) leaves in .grad of the eight surrogate
 //                            parameters for an upstream gradient d_out [B,4] (nn.MSELoss stays the caller's torch
 //                            op): reverse sweep over layers and time with the WEIGHT gradients, per-CTA partial sums
-//   lstm_grad_reduce_kernel  sum of the per-CTA partials (fp64) into the eight gradient tensors
+//   lstm_grad_reduce_kernel  sum of the per-CTA partials (fp64, fixed order) into the eight gradient tensors
 //   adamw_kernel             torch.optim.AdamW.step (Model_NN/Main.py:230, UL/Main.py:195) for up to 8 tensors, 1 launch
 //
 // FP32 FFMA kernels: the weight-gradient contraction reduces over TRAJECTORIES (K = batch), which the
@@ -31,8 +31,19 @@ constexpr int kWfFloats = 55 * kG + 100 * kG + 100 * kG;     // forward images  
 constexpr int kWbFloats = 3 * kG * 100;                      // backward images WB_l[row][ug][ih0 ih1 hh0 hh1]
 constexpr int kPackFloatsL = kWfFloats + kWbFloats;
 constexpr int kRecSlots = 10;                                // float4 per thread and cell: i,f,g,o,c x 2 units
-constexpr size_t kRecFloatsTile = (size_t)30 * kRecSlots * kThreadsL * 4;
-constexpr size_t kHseqFloatsTile = (size_t)30 * kH * kTT;
+// Workspace layout: the unit is a PAIR of 40-sample tiles (80 samples), so that the 80-sample forward kernel and the
+// 40-sample kernels share it.  records [pair][30 cells][2 halves][10 slots][256 threads] float4 (thread-private,
+// warp-coalesced); hidden sequences [pair][30 cells][50 units][80 samples].
+constexpr int kTF = 80;                 // samples per pair / per tile of the 80-sample forward kernel
+constexpr size_t kRecCell = (size_t)kRecSlots * kThreadsL * 4;              // floats per (cell, half)
+constexpr size_t kRecFloatsPair = (size_t)30 * 2 * kRecCell;
+constexpr size_t kHseqFloatsPair = (size_t)30 * kH * kTF;
+__host__ __device__ inline size_t rec_offset(int tile40, int cell) {          // floats, without the thread's slot offset
+  return (size_t)(tile40 >> 1) * kRecFloatsPair + ((size_t)cell * 2 + (tile40 & 1)) * kRecCell;
+}
+__host__ __device__ inline size_t hseq_offset(int tile40) {                   // row stride kTF
+  return (size_t)(tile40 >> 1) * kHseqFloatsPair + (size_t)(tile40 & 1) * kTT;
+}
 constexpr size_t kDseqFloatsCta = (size_t)kL * 2 * kThreadsL * 4;
 constexpr int kPartialFloats = 3 * kG * 100 + 200 + 4;       // per CTA: dW_l [200][100] x 3, d fc.weight, d fc.bias
 constexpr int kSmemFwd = (100 * kG + kL * kH * kTT + kL * 5 * kTT) * 4;                 // 168 000 B
@@ -45,8 +56,6 @@ __host__ __device__ inline int wf_offset(int l) { return l == 0 ? 0 : (l == 1 ? 
 struct LstmRaw {
   const float* w_ih[3];
   const float* w_hh[3];
-  const float* fc_w;
-  const float* fc_b;
 };
 struct LstmGradOut {
   float* g_ih[3];
@@ -94,7 +103,7 @@ struct LstmFwdParams {
   const float* fc_b;     // [4]
   float* out;            // [B,4]
   float* rec;            // [tiles] records (save != 0)
-  float* hseq;           // [tiles][3][10][50][40] (save != 0)
+  float* hseq;           // hidden sequences (save != 0; the 80-sample kernel also needs it as per-CTA scratch otherwise)
   int B, save;
 };
 
@@ -178,11 +187,11 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_fwd_kernel(const Lst
           for (int uu = 0; uu < 2; ++uu)
             st4(seq + (t * kH + 2 * ug + uu) * kTT + tg * 4, make_float4(hv[uu][0], hv[uu][1], hv[uu][2], hv[uu][3]));
           if (p.save) {
-            float* hs = p.hseq + (size_t)tile * kHseqFloatsTile + (size_t)((l * kL + t) * kH) * kTT;
+            float* hs = p.hseq + hseq_offset(tile) + (size_t)((l * kL + t) * kH) * kTF;
 #pragma unroll
             for (int uu = 0; uu < 2; ++uu)
-              st4(hs + (2 * ug + uu) * kTT + tg * 4, make_float4(hv[uu][0], hv[uu][1], hv[uu][2], hv[uu][3]));
-            float* r = p.rec + (size_t)tile * kRecFloatsTile + (size_t)(l * kL + t) * kRecSlots * kThreadsL * 4 + tid * 4;
+              st4(hs + (2 * ug + uu) * kTF + tg * 4, make_float4(hv[uu][0], hv[uu][1], hv[uu][2], hv[uu][3]));
+            float* r = p.rec + rec_offset(tile, l * kL + t) + tid * 4;
 #pragma unroll
             for (int uu = 0; uu < 2; ++uu) {
               __stcs(reinterpret_cast<float4*>(r + (0 + uu) * kThreadsL * 4), make_float4(gi[uu][0], gi[uu][1], gi[uu][2], gi[uu][3]));
@@ -203,6 +212,139 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_fwd_kernel(const Lst
         float a = __ldg(p.fc_b + o);
         const float* h = seq + 9 * kH * kTT + b;
         for (int u = 0; u < kH; ++u) a = fmaf(__ldg(p.fc_w + o * kH + u), h[u * kTT], a);
+        p.out[(size_t)(b0 + b) * 4 + o] = a;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 80-sample forward (large batches): the same arithmetic with an 8 gate-column x 8 sample register tile (4 LDS.128 per
+// 64 FFMA instead of 3 per 32).  The whole-window hidden sequence of 80 samples does not fit shared memory next to the
+// weights, so the layer below is streamed: it is written to the hidden-sequence workspace anyway (or to a per-CTA
+// scratch of the same shape when nothing is recorded) and comes back one step ahead with cp.async.
+// Shared memory: weights [100][200] | input [2][50][80] | own h [2][50][80] | window [10][5][80] = 160 000 B.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSmemFwd80 = (100 * kG + 2 * kH * kTF + 2 * kH * kTF + kL * 5 * kTF) * 4;
+
+__global__ void __launch_bounds__(kThreadsL, 1) lstm_window_fwd80_kernel(const LstmFwdParams p) {
+  float* Wf = fc_dyn_smem;                       // [K][200]
+  float* inb = Wf + 100 * kG;                    // [2][50][80]  h of the layer below at step t (t & 1)
+  float* hb = inb + 2 * kH * kTF;                // [2][50][80]  own h at step t (t & 1)
+  float* xs = hb + 2 * kH * kTF;                 // [10][5][80]
+  const int tid = threadIdx.x;
+  const bool active = tid < kActive;
+  const int ug = active ? tid / 10 : 0, tg = active ? tid % 10 : 0;
+  const int pairs = (p.B + kTF - 1) / kTF;
+  for (int pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    const int b0 = pair * kTF;
+    float* hs = p.hseq + (size_t)(p.save ? pair : (int)blockIdx.x) * kHseqFloatsPair;
+    __syncthreads();
+    for (int i = tid; i < kL * 5 * kTF; i += kThreadsL) {          // xs[t][k][b] <- X[b0+b][t][k]
+      const int b = i % kTF, tk = i / kTF;
+      xs[i] = (b0 + b < p.B) ? __ldg(p.X + (size_t)(b0 + b) * 50 + tk) : 0.f;
+    }
+    for (int l = 0; l < 3; ++l) {
+      const int kin = l == 0 ? 5 : 50;
+      __syncthreads();                                             // previous layer: Wf / hb reads and hs writes are done
+      {
+        const float* src = p.pack + wf_offset(l);
+        const int n = (kin + kH) * kG;
+        for (int i = tid * 4; i < n; i += kThreadsL * 4) st4(Wf + i, __ldg(reinterpret_cast<const float4*>(src + i)));
+      }
+      auto stage = [&](int tt) {                                   // h of the layer below at step tt -> inb[tt & 1]
+        const float* src = hs + (size_t)((l - 1) * kL + tt) * kH * kTF;
+        float* dst = inb + (tt & 1) * kH * kTF;
+        for (int i = tid * 4; i < kH * kTF; i += kThreadsL * 4) DevCtx::cp_async16(dst + i, src + i);
+        DevCtx::cp_commit();
+      };
+      if (l > 0) stage(0);
+      DevCtx::cp_wait<0>();
+      __syncthreads();
+      float c[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) c[e] = 0.f;
+      for (int t = 0; t < kL; ++t) {
+        if (l > 0 && t + 1 < kL) stage(t + 1);
+        float acc[8][8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[g][j] = 0.f;
+        const float* in = l == 0 ? xs + t * 5 * kTF : inb + (t & 1) * kH * kTF;
+        const float* wp = Wf + ug * 8;
+        const float* ap = in + tg * 4;
+#pragma unroll 2
+        for (int k = 0; k < kin; ++k) {
+          const float4 w0 = ld4(wp + k * kG), w1 = ld4(wp + k * kG + 4);
+          const float4 a0 = ld4(ap + k * kTF), a1 = ld4(ap + k * kTF + 40);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[g][j] = fmaf(wv[g], av[j], acc[g][j]);
+        }
+        if (t > 0) {
+          const float* hp = hb + ((t - 1) & 1) * kH * kTF + tg * 4;
+          const float* wr = wp + kin * kG;
+#pragma unroll 2
+          for (int k = 0; k < kH; ++k) {
+            const float4 w0 = ld4(wr + k * kG), w1 = ld4(wr + k * kG + 4);
+            const float4 a0 = ld4(hp + k * kTF), a1 = ld4(hp + k * kTF + 40);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[g][j] = fmaf(wv[g], av[j], acc[g][j]);
+          }
+        }
+        if (active) {
+          float* hrow = hb + (t & 1) * kH * kTF;
+          float* hsg = hs + (size_t)((l * kL + t) * kH) * kTF;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float* r = p.save ? p.rec + rec_offset(2 * pair + half, l * kL + t) + tid * 4 : nullptr;
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+              float gi[4], gf[4], gg[4], go[4], hv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = uu * 8 + half * 4 + j;
+                gi[j] = sigm(acc[0 + uu][half * 4 + j]);
+                gf[j] = sigm(acc[2 + uu][half * 4 + j]);
+                gg[j] = tanh_(acc[4 + uu][half * 4 + j]);
+                go[j] = sigm(acc[6 + uu][half * 4 + j]);
+                const float cn = fmaf(gf[j], c[e], gi[j] * gg[j]);
+                c[e] = cn;
+                hv[j] = go[j] * tanh_(cn);
+              }
+              const int off = (2 * ug + uu) * kTF + half * 40 + tg * 4;
+              const float4 h4 = make_float4(hv[0], hv[1], hv[2], hv[3]);
+              st4(hrow + off, h4);
+              st4(hsg + off, h4);                                  // the layer above (and the reverse sweep) read it back
+              if (p.save) {
+                const int e0 = uu * 8 + half * 4;
+                __stcs(reinterpret_cast<float4*>(r + (0 + uu) * kThreadsL * 4), make_float4(gi[0], gi[1], gi[2], gi[3]));
+                __stcs(reinterpret_cast<float4*>(r + (2 + uu) * kThreadsL * 4), make_float4(gf[0], gf[1], gf[2], gf[3]));
+                __stcs(reinterpret_cast<float4*>(r + (4 + uu) * kThreadsL * 4), make_float4(gg[0], gg[1], gg[2], gg[3]));
+                __stcs(reinterpret_cast<float4*>(r + (6 + uu) * kThreadsL * 4), make_float4(go[0], go[1], go[2], go[3]));
+                __stcs(reinterpret_cast<float4*>(r + (8 + uu) * kThreadsL * 4), make_float4(c[e0], c[e0 + 1], c[e0 + 2], c[e0 + 3]));
+              }
+            }
+          }
+        }
+        DevCtx::cp_wait<0>();
+        __syncthreads();                                           // h_t and the next input block are visible
+      }
+    }
+    for (int i = tid; i < 4 * kTF; i += kThreadsL) {               // read-out fc on h of the top layer at t = 9
+      const int b = i % kTF, o = i / kTF;
+      if (b0 + b < p.B) {
+        float a = __ldg(p.fc_b + o);
+        const float* h = hb + (9 & 1) * kH * kTF + b;
+        for (int u = 0; u < kH; ++u) a = fmaf(__ldg(p.fc_w + o * kH + u), h[u * kTF], a);
         p.out[(size_t)(b0 + b) * 4 + o] = a;
       }
     }
@@ -235,8 +377,8 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
     const int b0 = tile * kTT;
-    const float* hs_tile = p.hseq + (size_t)tile * kHseqFloatsTile;
-    const float* rec_tile = p.rec + (size_t)tile * kRecFloatsTile + tid * 4;
+    const float* hs_tile = p.hseq + hseq_offset(tile);                // rows of kTF floats, this tile's 40 samples first
+    const float* rec_tile = p.rec + tid * 4;
     __syncthreads();
     if (tid < 4 * kTT) {
       const int b = tid % kTT, o = tid / kTT;
@@ -247,7 +389,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
       float a = 0.f;
       if (tid < 200) {
         const int o = tid / kH, u = tid % kH;
-        const float* h = hs_tile + (size_t)((2 * kL + 9) * kH + u) * kTT;
+        const float* h = hs_tile + (size_t)((2 * kL + 9) * kH + u) * kTF;
         for (int b = 0; b < kTT; ++b) a = fmaf(dout[o * kTT + b], __ldcg(h + b), a);
       } else {
         for (int b = 0; b < kTT; ++b) a += dout[(tid - 200) * kTT + b];
@@ -270,7 +412,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
 #pragma unroll
       for (int e = 0; e < 8; ++e) dc[e] = dhrec[e] = 0.f;
       if (active) {
-        const float* r9 = rec_tile + (size_t)(l * kL + 9) * kRecSlots * kThreadsL * 4;
+        const float* r9 = rec_tile + rec_offset(tile, l * kL + 9);
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) {
           const float4 v = __ldcs(reinterpret_cast<const float4*>(r9 + (8 + uu) * kThreadsL * 4));
@@ -282,8 +424,9 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
       auto stage = [&](int tt) {
         float* dstb = act + (tt & 1) * 100 * kSB;
         if (l > 0) {
-          const float* src = hs_tile + (size_t)((l - 1) * kL + tt) * kH * kTT;
-          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4) DevCtx::cp_async16(dstb + (i / kTT) * kSB + i % kTT, src + i);
+          const float* src = hs_tile + (size_t)((l - 1) * kL + tt) * kH * kTF;
+          for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
+            DevCtx::cp_async16(dstb + (i / kTT) * kSB + i % kTT, src + (i / kTT) * kTF + i % kTT);
         } else {
           for (int i = tid; i < kH * kTT; i += kThreadsL) {
             const int b = i % kTT, k = i / kTT;
@@ -291,9 +434,9 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
           }
         }
         if (tt > 0) {
-          const float* src = hs_tile + (size_t)(l * kL + tt - 1) * kH * kTT;
+          const float* src = hs_tile + (size_t)(l * kL + tt - 1) * kH * kTF;
           for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
-            DevCtx::cp_async16(dstb + (kH + i / kTT) * kSB + i % kTT, src + i);
+            DevCtx::cp_async16(dstb + (kH + i / kTT) * kSB + i % kTT, src + (i / kTT) * kTF + i % kTT);
         } else {
           for (int i = tid * 4; i < kH * kTT; i += kThreadsL * 4)
             st4(dstb + (kH + i / kTT) * kSB + i % kTT, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -325,15 +468,15 @@ __global__ void __launch_bounds__(kThreadsL, 1) lstm_window_bwd_kernel(const Lst
               dh[uu * 4 + 0] = v.x; dh[uu * 4 + 1] = v.y; dh[uu * 4 + 2] = v.z; dh[uu * 4 + 3] = v.w;
             }
           }
-          const float* r = rec_tile + (size_t)(l * kL + t) * kRecSlots * kThreadsL * 4;
+          const float* r = rec_tile + rec_offset(tile, l * kL + t);
           if (t > 0 && (tid & 7) == 0) {                           // records of the next step (t-1): one 128-byte line per 8 lanes
-            const float* rn = r - (size_t)kRecSlots * kThreadsL * 4;
+            const float* rn = r - 2 * kRecCell;
 #pragma unroll
             for (int sl = 0; sl < 8; ++sl) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + sl * kThreadsL * 4));
           }
           float cprev[8];
           if (t > 0) {
-            const float* rp = r - (size_t)kRecSlots * kThreadsL * 4;
+            const float* rp = r - 2 * kRecCell;                        // the previous cell of the same layer and half
 #pragma unroll
             for (int uu = 0; uu < 2; ++uu) {
               const float4 v = __ldcs(reinterpret_cast<const float4*>(rp + (8 + uu) * kThreadsL * 4));

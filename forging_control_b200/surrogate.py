@@ -81,14 +81,12 @@ class _LstmWindow(torch.autograd.Function):
         pack = _pack(ws)
         fc_w, fc_b = ws[6].detach().contiguous(), ws[7].detach().contiguous()
         out = torch.empty(B, 4, dtype=torch.float32, device=dev)
-        work = None
-        nbytes = 0
         with torch.cuda.device(dev):
-            if save:
-                nbytes = int(L.fc_lstm_window_workspace_bytes(B, 1))
-                if nbytes == 0:
-                    raise RuntimeError("fc_lstm_window_workspace_bytes failed: " + L.fc_last_error().decode())
-                work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            # save: records + hidden sequences for the backward call; large batches also need a per-CTA scratch without it
+            nbytes = int(L.fc_lstm_window_workspace_bytes(B, int(save)))
+            if nbytes == 0:
+                raise RuntimeError("fc_lstm_window_workspace_bytes failed: " + L.fc_last_error().decode())
+            work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             rc = L.fc_lstm_window_fwd(_native.ptr(xc), _native.ptr(pack), _native.ptr(fc_w), _native.ptr(fc_b), B, int(save),
                                       _native.ptr(out), _native.ptr(work), nbytes, _native.stream_ptr(dev))
         _native.check(rc, "fc_lstm_window_fwd")

@@ -159,7 +159,8 @@ int fc_closed_loop_rk4_ex(int f64, const void* x0, const void* ref, int n_ref, i
  *                             floats); call after every optimizer step.
  *   fc_lstm_window_fwd        X [B,10,5] -> out [B,4]; save != 0 records the cell activations and hidden sequences
  *                             in `workspace` (fc_lstm_window_workspace_bytes(B, 1) bytes) for the backward call;
- *                             save == 0 needs no workspace (inference).
+ *                             save == 0 (inference) needs only the scratch fc_lstm_window_workspace_bytes(B, 0) reports
+ *                             (a few bytes, or the per-CTA buffers of the 80-sample forward used for large B).
  *   fc_lstm_window_bwd        d_out [B,4] + the workspace of the matching forward call -> the eight gradient tensors
  *                             (overwritten, state_dict shapes: g_ih0 [200,5], g_hh* / g_ih1 / g_ih2 [200,50],
  *                             g_fc_w [4,50], g_fc_b [4]).                                                          */

@@ -84,7 +84,7 @@ def test_three_epoch_steps_with_device_adamw_match_reference(dev, cases):
     assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 3.0
 
 
-@pytest.mark.parametrize("B", [1, 40, 41, 1003])
+@pytest.mark.parametrize("B", [1, 40, 41, 1003, 6007])      # 6007: more 40-sample tiles than SMs -> 80-sample forward
 def test_ragged_batches_match_fp64_oracle_with_an_arbitrary_upstream_gradient(dev, B):
     g = torch.Generator().manual_seed(100 + B)
     torch.manual_seed(5)
@@ -125,6 +125,8 @@ def test_full_size_properties(dev, golden_weights):
     o2, g2 = run(X, d2)
     o3, g3 = run(X, d1 + 2.0 * d2)
     assert torch.equal(o1, o2) and torch.equal(o1, o3) and bool(torch.isfinite(o1).all())
+    with torch.no_grad():                                 # inference mode of the 80-sample forward (per-CTA scratch)
+        assert torch.equal(m(X, dev), o1)
     _, ga = run(X[:30000], d1[:30000])
     _, gb = run(X[30000:], d1[30000:])
     for k in g1:
