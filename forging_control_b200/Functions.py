@@ -62,11 +62,54 @@ class FNNModel(nn.Module):
         nn.init.zeros_(self.fc_inp.bias)
         nn.init.zeros_(self.fc_int.bias)
 
+    def _native_ok(self, x) -> bool:
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0 and not x.requires_grad
+                and self.width_dim == 1 and isinstance(self.activation, nn.ReLU) and isinstance(self.constraint, nn.Hardtanh)
+                and tuple(self.fc_inp.weight.shape) == (50, 3) and self.fc_inp.bias is not None
+                and tuple(self.fc_out.weight.shape) == (1, 50) and self.fc_inp.weight.is_cuda
+                and self.fc_inp.weight.dtype == torch.float32)
+
     def forward(self, x):
+        if self._native_ok(x):
+            # reference configuration on a CUDA device: one kernel forward, one kernel (+ reduce) backward (fc_fnn_*)
+            return _FusedFNN.apply(x, self.fc_inp.weight, self.fc_inp.bias, self.fc_out.weight)
         out = self.activation(self.fc_inp(x))
         for _ in range(self.width_dim - 1):
             out = self.activation(self.fc_int(out))
         return self.constraint(self.fc_out(out))
+
+
+class _FusedFNN(torch.autograd.Function):
+    """``FNNModel.forward`` for the reference configuration (Functions.py:261-289 with ``width_dim = 1``) as one kernel;
+    the backward recomputes the hidden layer and reduces the 250 weight gradients in one kernel + a 1-block reduce."""
+
+    @staticmethod
+    def forward(ctx, x, inp_w, inp_b, out_w):
+        dev = x.device
+        xc = x.detach().contiguous()
+        ws = [w.detach().contiguous() for w in (inp_w, inp_b, out_w)]
+        u = torch.empty(x.shape[0], 1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _native.lib().fc_fnn_forward(_native.ptr(xc), *[_native.ptr(w) for w in ws], x.shape[0], _native.ptr(u),
+                                              _native.stream_ptr(dev))
+        _native.check(rc, "fc_fnn_forward")
+        ctx.save_for_backward(xc, *ws)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        xc, inp_w, inp_b, out_w = ctx.saved_tensors
+        dev = xc.device
+        L = _native.lib()
+        d = du.detach().to(torch.float32).reshape(-1).contiguous()
+        g = torch.empty(250, dtype=torch.float32, device=dev)
+        nbytes = int(L.fc_fnn_backward_workspace_bytes())
+        work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.fc_fnn_backward(_native.ptr(xc), _native.ptr(d), _native.ptr(inp_w), _native.ptr(inp_b), _native.ptr(out_w),
+                                   xc.shape[0], _native.ptr(g), _native.ptr(work), nbytes, _native.stream_ptr(dev))
+        _native.check(rc, "fc_fnn_backward")
+        return None, g[0:150].reshape(50, 3), g[150:200], g[200:250].reshape(1, 50)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.environ.get("FC_LIB_PATH", os.path.join(_PKG_DIR, "libforging_b200.so"))   # override: development builds
 SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in
            ("fc_api.cu", "fc_mpc_kernel.inl", "fc_layout.h", "fc_plant.cuh", "fc_mpc_tc_kernel.inl", "fc_tc_layout.h",
-            "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_lstm_train.cuh")]
+            "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_lstm_train.cuh", "fc_fnn.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -27,7 +27,8 @@ EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
            "fc_mpc_loss_noise", "fc_closed_loop_rk4_noise", "fc_closed_loop_rk4_f64_noise",
            "fc_build_windows", "fc_mpc_loss_wide_workspace_bytes", "fc_mpc_loss_wide",
            "fc_closed_loop_rk4_ex", "fc_lstm_train_pack_floats", "fc_lstm_train_pack", "fc_lstm_window_workspace_bytes",
-           "fc_lstm_window_fwd", "fc_lstm_window_bwd", "fc_adamw_step")
+           "fc_lstm_window_fwd", "fc_lstm_window_bwd", "fc_adamw_step", "fc_fnn_forward", "fc_fnn_backward_workspace_bytes",
+           "fc_fnn_backward")
 
 _c_float_p = ctypes.c_void_p   # raw device pointers are passed as integers
 _lib = None
@@ -114,6 +115,12 @@ def lib() -> ctypes.CDLL:
     L.fc_adamw_step.restype = i32
     L.fc_adamw_step.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                 ctypes.POINTER(i32), i32, f32, f32, f32, f32, f32, f32, vp]
+    L.fc_fnn_forward.restype = i32
+    L.fc_fnn_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.fc_fnn_backward_workspace_bytes.restype = sz
+    L.fc_fnn_backward_workspace_bytes.argtypes = []
+    L.fc_fnn_backward.restype = i32
+    L.fc_fnn_backward.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, sz, vp]
     L.fc_fp32_peak.restype = i32
     L.fc_fp32_peak.argtypes = [i32, ctypes.POINTER(f64), vp]
     _lib = L

@@ -69,6 +69,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 }  // namespace fc
 #include "fc_lstm_train.cuh"
+#include "fc_fnn.cuh"
 namespace fc {
 
 template <int N> struct TmemIO;
@@ -990,6 +991,47 @@ int fc_adamw_step(int count, float* const* params, const float* const* grads, fl
   if (blocks > 1184) blocks = 1184;
   lt::adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
   FC_CUDA(cudaGetLastError(), "adamw_kernel launch");
+  return FC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// controller forward / backward for the u_0 path (fc_fnn.cuh)
+// ---------------------------------------------------------------------------------------------------
+static int fnn_grid(long long B, int per_block, int* grid) {
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  long long blocks = (B + per_block - 1) / per_block;
+  const long long cap = (long long)sms * 4 < fn::kMaxBlocksF ? (long long)sms * 4 : fn::kMaxBlocksF;
+  *grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+  return FC_OK;
+}
+
+int fc_fnn_forward(const float* X, const float* inp_w, const float* inp_b, const float* out_w, long long B, float* u, void* stream) {
+  if (B <= 0) return fail(FC_ERR_BAD_SHAPE, "fc_fnn_forward: B must be positive%s (B=%lld)", "", B);
+  if (!X || !inp_w || !inp_b || !out_w || !u) return fail(FC_ERR_NULL_POINTER, "fc_fnn_forward: null pointer%s");
+  int grid = 0;
+  int rc = fnn_grid(B, fn::kThreadsF, &grid);
+  if (rc) return rc;
+  fn::fnn_forward_kernel<<<grid, fn::kThreadsF, 0, (cudaStream_t)stream>>>(X, inp_w, inp_b, out_w, B, u);
+  FC_CUDA(cudaGetLastError(), "fnn_forward_kernel launch");
+  return FC_OK;
+}
+
+size_t fc_fnn_backward_workspace_bytes(void) { return (size_t)fn::kMaxBlocksF * 250 * sizeof(float); }
+
+int fc_fnn_backward(const float* X, const float* du, const float* inp_w, const float* inp_b, const float* out_w, long long B,
+                    float* g_flat, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return fail(FC_ERR_BAD_SHAPE, "fc_fnn_backward: B must be positive%s (B=%lld)", "", B);
+  if (!X || !du || !inp_w || !inp_b || !out_w || !g_flat || !workspace) return fail(FC_ERR_NULL_POINTER, "fc_fnn_backward: null pointer%s");
+  if (workspace_bytes < fc_fnn_backward_workspace_bytes()) return fail(FC_ERR_WORKSPACE, "fc_fnn_backward: workspace too small%s");
+  int grid = 0;
+  int rc = fnn_grid(B, fn::kThreadsF, &grid);
+  if (rc) return rc;
+  fn::fnn_backward_kernel<<<grid, fn::kThreadsF, 0, (cudaStream_t)stream>>>(X, du, inp_w, inp_b, out_w, B, (float*)workspace);
+  FC_CUDA(cudaGetLastError(), "fnn_backward_kernel launch");
+  fn::fnn_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, grid, g_flat);
+  FC_CUDA(cudaGetLastError(), "fnn_reduce_kernel launch");
   return FC_OK;
 }
 

@@ -181,6 +181,17 @@ int fc_adamw_step(int count, float* const* params, const float* const* grads, fl
                   const int* numel, int step, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, void* stream);
 
+/* ---- controller forward / backward for the u_0 path of a training step: `output = model(X)` (UL/Functions.py:643,
+ * FNNModel.forward :261-289, width_dim = 1, ReLU, Hardtanh) and its part of loss.backward() (:655).
+ *   fc_fnn_forward   X [B,3] -> u [B] (= [B,1]); raw state_dict weights fc_inp.weight [50,3], fc_inp.bias [50],
+ *                    fc_out.weight [1,50]; nothing is saved.
+ *   fc_fnn_backward  du [B] -> g_flat [250] = [d fc_inp.weight 150 | d fc_inp.bias 50 | d fc_out.weight 50] (overwritten);
+ *                    workspace of fc_fnn_backward_workspace_bytes() bytes.                                            */
+int fc_fnn_forward(const float* X, const float* inp_w, const float* inp_b, const float* out_w, long long B, float* u, void* stream);
+size_t fc_fnn_backward_workspace_bytes(void);
+int fc_fnn_backward(const float* X, const float* du, const float* inp_w, const float* inp_b, const float* out_w, long long B,
+                    float* g_flat, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement helper: register-resident FFMA loop used by bench.py to measure the FP32
  * roofline denominator on the device it runs on; writes achieved FLOP/s to *flops_host.           */
 int fc_fp32_peak(int iters, double* flops_host, void* stream);

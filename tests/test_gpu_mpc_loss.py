@@ -349,3 +349,31 @@ def test_wide_controller_matches_oracle(dev, golden_weights, width, B, N):
     for got, key in ((gl[:150].reshape(50, 3), "inp_w"), (gl[150:200], "inp_b"), (gl[200:250], "out_w"),
                      (gw[:2500].reshape(50, 50), "int_w"), (gw[2500:2550], "int_b")):
         assert rel_max(got, np.asarray(gr[key]).reshape(got.shape)) < 5e-5, key
+
+
+def test_fused_controller_forward_backward_matches_oracle(dev, golden_weights):
+    """FNNModel.forward on CUDA = fc_fnn_forward / fc_fnn_backward (Functions.py:261-289, the u_0 path of :643/:655):
+    against the fp64 oracle with an arbitrary upstream gradient, ragged batch, saturated and dead units included."""
+    for tag, B in (("c0", 1), ("init", 1000), ("c3", 20001)):
+        _, fnn = state_dicts(golden_weights, tag)
+        ctl = fb.FNNModel(3, 50, 1, 1)
+        fnn = dict(fnn)
+        if tag != "c0":
+            fnn["fc_out.weight"] = fnn["fc_out.weight"] * 8.0  # make the Hardtanh saturate for part of the batch
+        ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()}, strict=True)
+        ctl = ctl.to(dev)
+        g = torch.Generator().manual_seed(B)
+        X = (torch.rand(B, 3, generator=g) * 6 - 3)
+        d = torch.randn(B, 1, generator=g)
+        u = ctl(X.to(dev))
+        assert u.shape == (B, 1) and u.grad_fn is not None and type(u.grad_fn).__name__.startswith("_FusedFNN")
+        u.backward(d.to(dev))
+        w = O.weights_from_state_dicts(state_dicts(golden_weights, tag)[0], fnn, np.float64)
+        u_o, kept = O.fnn_forward(w, X.double().numpy(), 1, keep=True)
+        grads = {k: np.zeros_like(w[k]) for k in ("inp_w", "inp_b", "out_w")}
+        O.fnn_backward(w, kept, d.double().numpy(), grads, 1)
+        assert rel_max(u.detach().cpu().numpy(), np.asarray(u_o).reshape(B, 1)) <= TOL
+        assert B == 1 or 0 < int((u.detach().abs() >= 1).sum()) < B
+        for name, p in (("inp_w", ctl.fc_inp.weight), ("inp_b", ctl.fc_inp.bias), ("out_w", ctl.fc_out.weight)):
+            assert rel_max(p.grad.cpu().numpy(), grads[name].reshape(p.shape)) <= TOL, (tag, name)
+        assert ctl.fc_int.weight.grad is None
