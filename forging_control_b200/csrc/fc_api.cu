@@ -129,6 +129,10 @@ template <> struct TmemIO<32> {
 
 struct DevCtxTC : DevCtx {
   static __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+  // one instruction for a contiguous, 16-byte aligned region (bytes a multiple of 16)
+  static __device__ __forceinline__ void prefetch_l2_bulk(const float* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+  }
   static __device__ __forceinline__ long long clock() { return clock64(); }
   static __device__ void report(const long long* tm) {
     printf("[fc timing, CTA 0 thread 0, cycles] other %lld | fwd: prologue %lld issue+input %lld mma-wait %lld pointwise %lld store+sync %lld glue %lld | bwd: glue %lld prologue %lld finish+sync %lld issue+shadow %lld mma-wait %lld post %lld\n",

@@ -94,6 +94,7 @@ struct EmuCtxTC : EmuCtx {
   static constexpr bool kAccTruncates = false;
   static long long clock() { return 0; }
   static void prefetch_l2(const float*) {}
+  static void prefetch_l2_bulk(const float*, unsigned) {}
   static void report(const long long*) {}
   void mma(int d_col, int n, int a_col, const float* b_img, int n_img, int row0, int ksteps, bool accumulate) const {
     const int K = ksteps * 16;
