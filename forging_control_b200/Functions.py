@@ -40,6 +40,18 @@ logger = logging.getLogger(__name__)
 LOOKBACK = 10  # hard-coded in the reference loss, Functions.py:1434
 
 
+def _maxabs_scale(scaler, what: str) -> np.ndarray:
+    """``scale_`` of a fitted ``MaxAbsScaler`` (the reference's scalers, SL/results/scaler_*.pkl).  The reference calls
+    ``transform`` / ``inverse_transform`` (Functions.py:1596-1604, :1198); the kernels take the per-feature divisor,
+    which is the whole transform only for MaxAbs.  MinMax / Standard / Robust scalers (``Data.get_scaler``) carry an
+    offset and a multiplier instead and are rejected rather than silently mis-scaled."""
+    from sklearn.preprocessing import MaxAbsScaler
+    if not isinstance(scaler, MaxAbsScaler):
+        raise NotImplementedError(f"{what}: only MaxAbsScaler is supported by the CUDA path (got {type(scaler).__name__}); "
+                                  "MinMax / Standard / Robust scalers have an offset the kernels do not apply")
+    return np.asarray(scaler.scale_, dtype=np.float64)
+
+
 # ----------------------------------------------------------------------------------------------
 # controller
 # ----------------------------------------------------------------------------------------------
@@ -63,8 +75,10 @@ class FNNModel(nn.Module):
         nn.init.zeros_(self.fc_int.bias)
 
     def _native_ok(self, x) -> bool:
-        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0 and not x.requires_grad
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0 and x.shape[1] == 3
+                and not x.requires_grad
                 and self.width_dim == 1 and isinstance(self.activation, nn.ReLU) and isinstance(self.constraint, nn.Hardtanh)
+                and (self.constraint.min_val, self.constraint.max_val) == (-1.0, 1.0)
                 and tuple(self.fc_inp.weight.shape) == (50, 3) and self.fc_inp.bias is not None
                 and tuple(self.fc_out.weight.shape) == (1, 50) and self.fc_inp.weight.is_cuda
                 and self.fc_inp.weight.dtype == torch.float32)
@@ -150,8 +164,9 @@ class LSTMModel(nn.Module):
 # ----------------------------------------------------------------------------------------------
 # packed-weight cache (per device, keyed by parameter storage + version)
 # ----------------------------------------------------------------------------------------------
-_PACK_CACHE: dict = {}
-_WORKSPACE: dict = {}
+_PACK_CACHE: dict = {}          # (device, ids of the parameter tensors) -> (versions, packed buffer, weak refs)
+_PACK_CACHE_SLOTS = 16
+_WORKSPACE: dict = {}           # (device, stream) -> scratch buffer
 
 
 def _check_models(simulator: nn.Module, controller: nn.Module):
@@ -171,8 +186,17 @@ def _check_models(simulator: nn.Module, controller: nn.Module):
         raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports FNNModel(3, 50, 1, width_dim, bias=True) only")
     if getattr(controller, "width_dim", 1) > 1 and (tuple(controller.fc_int.weight.shape) != (50, 50) or controller.fc_int.bias is None):
         raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports the 50 x 50 hidden layer fc_int with bias only")
+    check_controller_nonlinearities(controller, "MPCLoss (fused sm_100a kernel)")
+
+
+def check_controller_nonlinearities(controller, what: str):
+    """The kernels hard-code ReLU hidden units and the default ``nn.Hardtanh`` saturation [-1, 1]
+    (FNNModel.__init__, Functions.py:239-259); anything else must not be evaluated silently as if it were that."""
     if not isinstance(getattr(controller, "activation", None), nn.ReLU):
-        raise NotImplementedError("MPCLoss (fused sm_100a kernel) supports the ReLU controller only")
+        raise NotImplementedError(f"{what} supports the ReLU controller only")
+    c = getattr(controller, "constraint", None)
+    if not isinstance(c, nn.Hardtanh) or (c.min_val, c.max_val) != (-1.0, 1.0):
+        raise NotImplementedError(f"{what} supports the default nn.Hardtanh() saturation [-1, 1] only")
 
 
 _NO_CONTROLLER = {}
@@ -193,8 +217,10 @@ def _weight_tensors(simulator, controller):
 
 
 def pack_weights(simulator: nn.Module, controller: nn.Module) -> torch.Tensor:
-    """Device buffer with the tiled weight layouts of the kernels (``fc_pack_weights``); re-packed
-    only when a parameter changed (optimizer steps bump ``_version``)."""
+    """Device buffer with the tiled weight layouts of the kernels (``fc_pack_weights``).  Cached per
+    (device, identity of the eleven parameter tensors); re-packed only when a parameter changed (optimizer steps bump
+    ``_version``) and then into a FRESH buffer, so a buffer handed out earlier (to a caller of this function, or to a
+    kernel still running on another stream) is never overwritten."""
     ws = _weight_tensors(simulator, controller)
     dev = ws[0].device
     if dev.type != "cuda":
@@ -202,29 +228,36 @@ def pack_weights(simulator: nn.Module, controller: nn.Module) -> torch.Tensor:
     for w in ws:
         if w.device != dev or w.dtype != torch.float32:
             raise RuntimeError("MPCLoss: all weights must be float32 tensors on the same CUDA device")
-    # The cache entry is valid only for the very same (still alive) parameter tensors at the same
-    # version: data_ptr alone is not enough, the caching allocator hands freed addresses to new models.
+    # The entry is valid only for the very same (still alive) parameter tensors at the same version: data_ptr alone
+    # is not enough, the caching allocator hands freed addresses to new models.
+    ident = (dev.index,) + tuple(id(w) for w in ws)
     key = tuple((w.data_ptr(), w._version) for w in ws)
-    slot = _PACK_CACHE.get(dev.index)
+    slot = _PACK_CACHE.get(ident)
     if slot is not None and slot[0] == key and all(r() is w for r, w in zip(slot[2], ws)):
         return slot[1]
     L = _native.lib()
-    buf = slot[1] if slot is not None else torch.empty(int(L.fc_pack_floats()), dtype=torch.float32, device=dev)
+    buf = torch.empty(int(L.fc_pack_floats()), dtype=torch.float32, device=dev)
     ws_c = [w.detach().contiguous() for w in ws]
     with torch.cuda.device(dev):
         rc = L.fc_pack_weights(*[_native.ptr(w) for w in ws_c], _native.ptr(buf), _native.stream_ptr(dev))
     _native.check(rc, "fc_pack_weights")
-    _PACK_CACHE[dev.index] = (key, buf, [weakref.ref(w) for w in ws])
+    if len(_PACK_CACHE) >= _PACK_CACHE_SLOTS:          # drop entries of dead models first, then the oldest
+        for k in [k for k, v in _PACK_CACHE.items() if any(r() is None for r in v[2])] or [next(iter(_PACK_CACHE))]:
+            _PACK_CACHE.pop(k, None)
+    _PACK_CACHE.pop(ident, None)
+    _PACK_CACHE[ident] = (key, buf, [weakref.ref(w) for w in ws])
     return buf
 
 
 def _workspace(dev, nbytes: int) -> torch.Tensor:
-    buf = _WORKSPACE.get(dev.index)
+    """Scratch of the fused kernels, one buffer per (device, stream): two streams on one device never share it."""
+    k = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _WORKSPACE.get(k)
     if buf is None or buf.numel() < nbytes:
+        _WORKSPACE.pop(k, None)
         buf = None
-        _WORKSPACE.pop(dev.index, None)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _WORKSPACE[dev.index] = buf
+        _WORKSPACE[k] = buf
     return buf
 
 
@@ -468,9 +501,9 @@ class NeuralNetwork:
         x0 = np.array([[init_state.get(k, 0) for k in ("y", "y_dot", "p1", "p2", "z")]] * N_traj, dtype=np.float64)
         T_ref = Ts * T_traj
         ref = tvp_reference_table(N_traj, T_traj, Ts, T_ref, bias_work, bias_return)      # [N_traj, T_traj]
-        scale_in = np.asarray(scalers["input"].scale_, dtype=np.float64).copy()
-        scale_in[2] = np.asarray(scalers["y_dot"].scale_, dtype=np.float64)[0]            # Functions.py:1597-1598
-        scale_out = np.asarray(scalers["output"].scale_, dtype=np.float64)
+        scale_in = _maxabs_scale(scalers["input"], "NeuralNetwork.loop").copy()
+        scale_in[2] = _maxabs_scale(scalers["y_dot"], "NeuralNetwork.loop")[0]             # Functions.py:1597-1598
+        scale_out = _maxabs_scale(scalers["output"], "NeuralNetwork.loop")
         timer = ClosedLoopTimer()
         timer.tic()
         meas, u = closed_loop_rollout(controller, x0, ref, Ts, scale_in, scale_out, substeps=substeps,
@@ -496,8 +529,8 @@ class NeuralNetwork:
             raise NotImplementedError("LSTM shadow: the kernel is specialised for the reference's look-back of 10")
         B, T1, _ = meas.shape
         T = T1 - 1
-        s_in = np.asarray(model_scalers["input"].scale_, dtype=np.float64)
-        s_out = np.asarray(model_scalers["output"].scale_, dtype=np.float64)
+        s_in = _maxabs_scale(model_scalers["input"], "LSTM shadow")
+        s_out = _maxabs_scale(model_scalers["output"], "LSTM shadow")
         out = np.zeros((B, T + 1, 4))
         out[:, 0] = x0[:, 1:5]
         if T > 0:
@@ -542,11 +575,13 @@ class FeasibilityRecovery:
             raise NotImplementedError("NN_make_step: the IPOPT feasibility-recovery branch is out of scope")
         model.eval()
         with torch.no_grad():
-            X_new = np.asarray(X, dtype=np.float64) / np.asarray(scalers["input"].scale_)
-            X_new[0, -1] = X[0, -1] / np.asarray(scalers["y_dot"].scale_)[0]
+            # the reference's own calls (Functions.py:1596-1604): any fitted sklearn scaler works here
+            X = np.asarray(X, dtype=np.float64)
+            X_new = scalers["input"].transform(X)
+            X_new[0, -1] = scalers["y_dot"].transform(np.array([[X[0, -1]]]))[0, -1]
             dev = next(model.parameters()).device
             y_star = model(torch.as_tensor(X_new).float().to(dev)).double().cpu().numpy()
-            output = y_star * np.asarray(scalers["output"].scale_)
+            output = scalers["output"].inverse_transform(y_star)
         return output, 0.0, warm_start
 
 

@@ -7,13 +7,14 @@ from .Functions import (Data, FNNModel, FeasibilityRecovery, LSTMModel, MPCLoss,
 from .dataset import DeviceSequenceLoader, build_windows
 from .closed_loop import closed_loop_device, closed_loop_rollout, tvp_reference_table
 from .surrogate import DeviceAdamW, SurrogateNeuralNetwork, lstm_window
-from .distributed import allreduce_loss_and_grads, shard_bounds, sharded_surrogate_step, sharded_training_step
+from .distributed import (FlatGradBucket, allreduce_loss_and_grads, shard_bounds, sharded_surrogate_step,
+                          sharded_training_step)
 
 __all__ = ["FNNModel", "LSTMModel", "MPCLoss", "NeuralNetwork", "FeasibilityRecovery", "Data",
            "mpc_loss_native", "pack_weights", "closed_loop_device", "closed_loop_rollout",
            "tvp_reference_table", "shard_bounds", "allreduce_loss_and_grads", "sharded_training_step",
            "lstm_shadow_native", "DeviceSequenceLoader", "build_windows", "install",
-           "sharded_surrogate_step", "DeviceAdamW", "SurrogateNeuralNetwork", "lstm_window", "install_surrogate"]
+           "sharded_surrogate_step", "FlatGradBucket", "DeviceAdamW", "SurrogateNeuralNetwork", "lstm_window", "install_surrogate"]
 
 
 def install(reference_functions_module) -> None:

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 # every symbol include/forging_b200.h declares
 EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
-           "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_closed_loop_rk4",
+           "fc_mpc_loss_workspace_bytes", "fc_mpc_loss", "fc_mpc_select_kernel", "fc_mpc_loss_scratch_traffic_bytes", "fc_closed_loop_rk4",
            "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout",
            "fc_mpc_loss_noise", "fc_closed_loop_rk4_noise", "fc_closed_loop_rk4_f64_noise",
            "fc_build_windows", "fc_mpc_loss_wide_workspace_bytes", "fc_mpc_loss_wide",
@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
     L.fc_pack_weights.argtypes = [vp] * 12 + [vp]
     L.fc_mpc_loss_workspace_bytes.restype = sz
     L.fc_mpc_loss_workspace_bytes.argtypes = [i32, i32, i32]
+    L.fc_mpc_loss_scratch_traffic_bytes.restype = sz
+    L.fc_mpc_loss_scratch_traffic_bytes.argtypes = [i32, i32]
     L.fc_mpc_select_kernel.restype = i32
     L.fc_mpc_select_kernel.argtypes = [i32]
     L.fc_mpc_loss.restype = i32

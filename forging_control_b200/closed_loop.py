@@ -36,19 +36,22 @@ class ClosedLoopTimer:
 def tvp_reference_table(N_traj: int, T_traj: int, Ts: float, T_ref: float, bias_work, bias_return,
                         epsilon: float = 1e-7) -> np.ndarray:
     """``ref[idx, t] = tvp_fun((idx*T_traj + t)*Ts, T_ref, ...)`` exactly as Functions.py:1163-1164
-    evaluates it (Python ``random`` seeded per half-period, Functions.py:953-964)."""
+    evaluates it (Python ``random`` seeded per half-period, Functions.py:953-964).  The phase / period arithmetic is
+    vectorised (the same float64 ``%`` and ``//``); Python's generator is seeded once per DISTINCT (period, half)
+    instead of once per element, so a million-trajectory table costs one ``random.seed`` per half-period."""
+    t_now = (np.arange(N_traj, dtype=np.int64)[:, None] * T_traj + np.arange(T_traj, dtype=np.int64)[None, :]) * Ts
+    phase = np.mod(t_now + epsilon, T_ref)              # == Python float % for positive operands
+    period = np.floor_divide(t_now + epsilon, T_ref)    # == Python float //
+    work = phase < T_ref / 2
     ref = np.empty((N_traj, T_traj))
-    for idx in range(N_traj):
-        for t in range(T_traj):
-            t_now = (idx * T_traj + t) * Ts
-            phase = (t_now + epsilon) % T_ref
-            period = (t_now + epsilon) // T_ref
-            if phase < T_ref / 2:
-                random.seed(period + bias_work)
-                ref[idx, t] = 0.8 * random.random() + 0.1
-            else:
-                random.seed(period + bias_return)
-                ref[idx, t] = -0.8 * random.random() - 0.1
+    for is_work, bias, a, b in ((True, bias_work, 0.8, 0.1), (False, bias_return, -0.8, -0.1)):
+        m = work == is_work
+        vals, inv = np.unique(period[m], return_inverse=True)
+        draws = np.empty(len(vals))
+        for i, pv in enumerate(vals):
+            random.seed(float(pv) + bias)
+            draws[i] = a * random.random() + b
+        ref[m] = draws[inv]
     return ref
 
 
@@ -59,6 +62,8 @@ def _controller_weights(controller, dev):
     if tuple(controller.fc_inp.weight.shape) != (50, 3) or tuple(controller.fc_out.weight.shape) != (1, 50) \
             or controller.fc_inp.bias is None:
         raise NotImplementedError("closed loop kernel supports FNNModel(3, 50, 1, width_dim, bias=True) only")
+    from .Functions import check_controller_nonlinearities
+    check_controller_nonlinearities(controller, "closed loop kernel")
     f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
     width = int(getattr(controller, "width_dim", 1))
     wide = (None, None)
@@ -70,10 +75,10 @@ def _controller_weights(controller, dev):
 
 
 def closed_loop_device(controller, x0, ref, Ts, scale_in, scale_out, substeps=4, steps_per_ref=1,
-                       want_meas=True, want_u=True, process_std=None, meas_std=None, noise_seed=0):
+                       want_meas=True, want_u=True, process_std=None, meas_std=None, noise_seed=0, T=None):
     """Device-resident launch.  ``x0`` [B,5] and ``ref`` [n_ref,B] are CUDA tensors of the same dtype
     (float32 or float64).  Returns (meas [T+1,5,B] or None, u [T,B] or None, x_final [B,5]); the
-    number of steps is ``T = n_ref * steps_per_ref``.  ``process_std`` / ``meas_std`` (5 values each) switch on the
+    number of steps is ``T`` (default ``n_ref * steps_per_ref``; a shorter ``T`` stops inside the last reference segment).  ``process_std`` / ``meas_std`` (5 values each) switch on the
     process / measurement noise of ``NeuralNetwork.loop`` (Functions.py:1176-1183) from the kernel's counter-based
     generator keyed by ``noise_seed``."""
     if x0.device.type != "cuda":
@@ -85,7 +90,9 @@ def closed_loop_device(controller, x0, ref, Ts, scale_in, scale_out, substeps=4,
     if tuple(x0.shape) != (B, 5) or ref.dim() != 2 or ref.shape[1] != B:
         raise ValueError(f"closed loop: expected x0 [B,5], ref [n_ref,B]; got {tuple(x0.shape)}, {tuple(ref.shape)}")
     n_ref = ref.shape[0]
-    T = n_ref * steps_per_ref
+    T = n_ref * steps_per_ref if T is None else int(T)
+    if T < 0 or T > n_ref * steps_per_ref:
+        raise ValueError(f"closed loop: T={T} outside [0, n_ref * steps_per_ref = {n_ref * steps_per_ref}]")
     x0, ref = x0.contiguous(), ref.contiguous()
     w_in, b_in, w_out, wide, width = _controller_weights(controller, dev)
     s_in = torch.as_tensor(np.asarray(scale_in, dtype=np.float64), dtype=dt, device=dev)

@@ -473,8 +473,10 @@ static int ensure_smem_attributes();
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel
-static int g_mpc_mode = -1;
+// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel.
+// Thread-local: fc_mpc_select_kernel affects the calling thread's subsequent fc_mpc_loss* / workspace queries only
+// (no process-global state; the library stays re-entrant across threads and devices).
+static thread_local int g_mpc_mode = -1;
 static int mpc_mode() {
   if (g_mpc_mode < 0) {
     const char* e = getenv("FC_MPC_KERNEL");
@@ -625,6 +627,29 @@ size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad) {
   MpcPlan pl;
   if (mpc_plan(B, N, with_grad, &pl)) return 0;
   return pl.bytes;
+}
+
+// Scratch traffic of one with_grad launch, computed from the workspace layout of the kernel the plan selects: saved
+// activation records (written by the forward, read once by the reverse sweep) + hidden-sequence / d-sequence scratch
+// handed between layers (written and read once each).  An upper bound of the DRAM traffic (the L2 absorbs part of the
+// sequence scratch); the measured figure is the ncu capture in profiles/.
+size_t fc_mpc_loss_scratch_traffic_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  MpcPlan pl;
+  if (mpc_plan(B, N, 1, &pl)) return 0;
+  long kept = 0;                                    // kept (window, step) pairs per layer
+  for (int m = 0; m < N; ++m) kept += steps_kept(m);
+  size_t per_tile = 0;
+  if (pl.kind == 2) {
+    per_tile = (size_t)rec_base(N) * pr::kRecFloatsP * 2                                  // records: write + read
+               + (size_t)N * (kLayers - 1) * kLook * pr::kSlot * 2                        // operand-format hidden sequence
+               + (size_t)kept * (kLayers - 1) * (pr::kUpdWarps * pr::kMaxOwn * 32) * 2;    // d-sequence
+  } else if (pl.kind == 1) {
+    per_tile = (size_t)rec_base(N) * tc::kRecFloatsTC * 2;
+  } else {
+    per_tile = (size_t)rec_base(N) * kRecFloats * 2;
+  }
+  return per_tile * sizeof(float) * (size_t)pl.tiles;
 }
 
 int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,

@@ -1029,7 +1029,7 @@ struct MpcPair {
     if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedP);
     ctx.sync();
 #ifdef FC_TC_TIMING
-    if (p.debug_timing && (tid == 0 || tid == 160) && ctx.bid() == 0) Ctx::report_pair(tid, tm);
+    if (p.debug_timing && (tid == 0 || tid == 160 || tid == 288 || tid == 416) && ctx.bid() == 0) Ctx::report_pair(tid, tm);
 #endif
     ctx.tc_teardown();
   }

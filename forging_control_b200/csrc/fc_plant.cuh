@@ -84,27 +84,31 @@ __device__ __forceinline__ void press_rhs(const R (&x)[5], R u, R (&dx)[5]) {
   dx[4] = (u - z) / R(pc::T1);
 }
 
-template <typename R>
-__device__ __forceinline__ void rk4_substep(R (&x)[5], R u, R h) {            // Functions.py:1767-1775
+// NOISE: the process noise w of do-mpc's model.set_rhs(..., process_noise=True) (template_model.py:145-149) is an
+// ADDITIVE TERM OF THE RIGHT-HAND SIDE, dx/dt = f(x, u) + w, held constant over one simulator step.
+template <typename R, bool NOISE = false>
+__device__ __forceinline__ void rk4_substep(R (&x)[5], R u, R h, const R (&w)[5]) {   // Functions.py:1767-1775
   R k1[5], k2[5], k3[5], k4[5], xt[5];
   press_rhs(x, u, k1);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) xt[i] = x[i] + h / R(2) * k1[i];
+  for (int i = 0; i < 5; ++i) { if (NOISE) k1[i] += w[i]; xt[i] = x[i] + h / R(2) * k1[i]; }
   press_rhs(xt, u, k2);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) xt[i] = x[i] + h / R(2) * k2[i];
+  for (int i = 0; i < 5; ++i) { if (NOISE) k2[i] += w[i]; xt[i] = x[i] + h / R(2) * k2[i]; }
   press_rhs(xt, u, k3);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) xt[i] = x[i] + h * k3[i];
+  for (int i = 0; i < 5; ++i) { if (NOISE) k3[i] += w[i]; xt[i] = x[i] + h * k3[i]; }
   press_rhs(xt, u, k4);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) x[i] = x[i] + h / R(6) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + k4[i]);
+  for (int i = 0; i < 5; ++i) { if (NOISE) k4[i] += w[i]; x[i] = x[i] + h / R(6) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + k4[i]); }
 }
 
 // process / measurement noise of do-mpc's Simulator.make_step(u0, v0, w0) as driven by NeuralNetwork.loop
-// (UL/Functions.py:1176-1183): x_next = integrate(x, u) + w0, y = measurement(x_next) + v0, w0 ~ N(0, process_std),
-// v0 ~ N(0, meas_std) per state; the controller reads the noisy measurement.  Normals: philox_normal4 with counter
-// (trajectory, 3*step + k).  std all zero = off.
+// (UL/Functions.py:1176-1183): every state is declared with process_noise=True (template_model.py:145-149), i.e.
+// x_next = integrate(dx/dt = f(x, u) + w0 over t_step) with ONE draw w0 ~ N(0, process_std) per make_step, held
+// constant over the step (a rate: UL/Main.py:88-96 uses 0.5 m/s on y, 5e7 Pa/s on the pressures);
+// y = measurement(x_next) + v0, v0 ~ N(0, meas_std) per state; the controller reads the noisy measurement.
+// Normals: philox_normal4 with counter (trajectory, 3*step + k).  std all zero = off.
 // hidden-layer repeats of the controller (FNNModel.forward, UL/Functions.py:261-289): width_dim - 1 applications of the
 // weight-shared fc_int + ReLU
 struct ClosedLoopWide {
@@ -180,16 +184,18 @@ __global__ void __launch_bounds__(128) closed_loop_kernel(
     const float us = fminf(fmaxf(vv, -1.f), 1.f);                          // nn.Hardtanh
     const R u = (R)us * so;
     if (ucmd) ucmd[(size_t)t * B + b] = u;
-    for (int s = 0; s < substeps; ++s) rk4_substep(x, u, h);
-    R y[5] = {x[0], x[1], smooth_floor(x[2]), smooth_floor(x[3]), x[4]};     // template_model.py:154-155
+    float e[12];
+    R w[5] = {R(0), R(0), R(0), R(0), R(0)};
     if (NOISE) {
-      float e[12];
       philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t, e);
       philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t + 1u, e + 4);
       philox_normal4(nz.seed, (unsigned)b, 3u * (unsigned)t + 2u, e + 8);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) x[i] += (R)(nz.process_std[i] * e[i]);
-      y[0] = x[0]; y[1] = x[1]; y[2] = smooth_floor(x[2]); y[3] = smooth_floor(x[3]); y[4] = x[4];
+      for (int i = 0; i < 5; ++i) w[i] = (R)(nz.process_std[i] * e[i]);      // one draw per step, a term of the RHS
+    }
+    for (int s = 0; s < substeps; ++s) rk4_substep<R, NOISE>(x, u, h, w);
+    R y[5] = {x[0], x[1], smooth_floor(x[2]), smooth_floor(x[3]), x[4]};     // template_model.py:154-155
+    if (NOISE) {
 #pragma unroll
       for (int i = 0; i < 5; ++i) y[i] += (R)(nz.meas_std[i] * e[5 + i]);
     }

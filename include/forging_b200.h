@@ -64,6 +64,13 @@ size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad);
  * 3 = always the pair kernel.  Also settable with the environment variable FC_MPC_KERNEL=ffma|tc|pair before
  * the first call.  All kernels meet the same parity bar.                                            */
 int fc_mpc_select_kernel(int mode);
+
+/* Scratch traffic (bytes) of one with_grad launch for (B, N), computed from the workspace layout of the kernel the
+ * current selection picks: activation records saved by the forward roll-out and read once by the reverse sweep
+ * (what autograd keeps alive between MPCLoss.forward, Functions.py:1353-1472, and loss.backward(), :655) plus the
+ * hidden-sequence scratch handed between LSTM layers.  Used by bench.py for `roofline.traffic` ("computed"); an
+ * upper bound of the DRAM traffic, the measured value is the ncu capture under profiles/.  0 on error.           */
+size_t fc_mpc_loss_scratch_traffic_bytes(int B, int N);
 int fc_mpc_loss(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N,
                 float alpha, long long B_global, int with_grad, float* cost, float* command,
                 float* error, float* pred, float* du0, float* gl, void* workspace,

@@ -121,14 +121,17 @@ def measurement(x):
     return y
 
 
-def rk4_step(x, u, ts=1e-3, substeps=4):
+def rk4_step(x, u, ts=1e-3, substeps=4, w=None):
+    """``w`` [...,5]: process noise of do-mpc's ``set_rhs(..., process_noise=True)`` (UL/template_model.py:145-149),
+    an additive term of the right-hand side held constant over the step: dx/dt = f(x, u) + w."""
     dt = x.dtype.type
     h = dt(ts / substeps)
+    f = press_rhs if w is None else (lambda xx, uu: press_rhs(xx, uu) + w)
     for _ in range(substeps):
-        k1 = press_rhs(x, u)
-        k2 = press_rhs(x + h / 2 * k1, u)
-        k3 = press_rhs(x + h / 2 * k2, u)
-        k4 = press_rhs(x + h * k3, u)
+        k1 = f(x, u)
+        k2 = f(x + h / 2 * k1, u)
+        k3 = f(x + h / 2 * k2, u)
+        k4 = f(x + h * k3, u)
         x = x + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
     return x
 
@@ -159,8 +162,10 @@ def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np
     """x0 [B,5] raw initial state, ref [B,T] physical reference per step.
     Returns (meas [B,T+1,5], u [B,T]); meas[:,0] = x0 as given (Functions.py:1134-1138).
 
-    Noise (NeuralNetwork.loop, UL/Functions.py:1176-1183 -> do-mpc ``Simulator.make_step(u0, v0, w0)``):
-    ``x_next = integrate(x, u) + w0``, ``y = measurement(x_next) + v0``, the controller reads ``y``.  ``normals``
+    Noise (NeuralNetwork.loop, UL/Functions.py:1176-1183 -> do-mpc ``Simulator.make_step(u0, v0, w0)``): all five
+    states are declared ``process_noise=True`` (UL/template_model.py:145-149), so ``w0`` is a term of the right-hand
+    side, ``x_next = integrate(dx/dt = f(x, u) + w0)`` with one draw per step (a rate: UL/Main.py:88-96 has 0.5 m/s on
+    y and 5e7 Pa/s on the pressures), ``y = measurement(x_next) + v0``, the controller reads ``y``.  ``normals``
     [B, 3T, 4] are the standard normals of the kernels' generator (mpc_loss_oracle.philox_normal4(seed, B, 3T)):
     step k uses the 12 values normals[:, 3k:3k+3].reshape(B,12): w0 = process_std * [0:5], v0 = meas_std * [5:10]."""
     x = np.asarray(x0, dtype=dtype).copy()
@@ -172,12 +177,13 @@ def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np
     for k in range(T):
         u = controller_step(fnn, scale_in, scale_out, y[:, 1].astype(np.float64), y[:, 4].astype(np.float64), ref[:, k])
         us[:, k] = u
-        x = rk4_step(x, u.astype(dtype), ts, substeps)
         if normals is not None:
             e = normals[:, 3 * k:3 * k + 3].reshape(Bn, 12)
-            x = x + (np.asarray(process_std, np.float32)[None, :] * e[:, 0:5].astype(np.float32)).astype(dtype)
+            w = (np.asarray(process_std, np.float32)[None, :] * e[:, 0:5].astype(np.float32)).astype(dtype)
+            x = rk4_step(x, u.astype(dtype), ts, substeps, w=w)
             y = measurement(x) + (np.asarray(meas_std, np.float32)[None, :] * e[:, 5:10].astype(np.float32)).astype(dtype)
         else:
+            x = rk4_step(x, u.astype(dtype), ts, substeps)
             y = measurement(x)
         meas[:, k + 1] = y
     return meas, us

@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 sim = fb.LSTMModel(5, 50, 4, 3); sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()}); sim = sim.to(dev)
 ctl = fb.FNNModel(3, 50, 1, 1); ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()}); ctl = ctl.to(dev)
 wp = fb.pack_weights(sim, ctl)
-B, N = 524288, 10
+B, N = int(os.environ.get('AB_B', 524288)), int(os.environ.get('AB_N', 10))
 g = torch.Generator(device=dev).manual_seed(1234)
 X = torch.rand(B, 3, generator=g, device=dev) * 2 - 1
 Z = torch.rand(B, 10, 5, generator=g, device=dev) * 2 - 1
@@ -21,7 +21,7 @@ u0 = ctl(X).detach().reshape(-1).contiguous()
 for _ in range(3):
     fb.mpc_loss_native(wp, X, u0, Z, N, 20.0, True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-K = 12
+K = int(os.environ.get('AB_K', 12))
 e0.record()
 for _ in range(K):
     r = fb.mpc_loss_native(wp, X, u0, Z, N, 20.0, True)

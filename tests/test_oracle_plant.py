@@ -68,3 +68,25 @@ def test_rhs_branches():
     assert np.all(np.isfinite(d))
     assert d[0, 1] < d[1, 1]                      # forging force only when y>0 and y_dot>=0
     assert abs(P.smooth_floor(np.array([-1e5]))[0]) < 1e-10
+
+
+def test_process_noise_is_a_rate_held_over_the_step(golden_weights):
+    """do-mpc's ``set_rhs(..., process_noise=True)`` (UL/template_model.py:145-149) adds w to the right-hand side:
+    for the linear spool state dz/dt = (u - z)/T1 + w the exact one-step answer is known in closed form, and with the
+    reference's own noise vector (UL/Main.py:88-96) the closed loop stays finite and bounded."""
+    import mpc_loss_oracle as O
+    x = P.INIT_STATE[None].copy()
+    w = np.array([[0.0, 0.0, 0.0, 0.0, 2.0]])
+    ts, u = 1e-3, np.array([0.01])
+    z1 = P.rk4_step(x, u, ts, 4, w=w)[0, 4]
+    a = np.exp(-ts / P.T1)
+    assert abs(z1 - (u[0] + w[0, 4] * P.T1) * (1 - a)) < 1e-9          # z' = (u + w T1 - z)/T1 from z = 0
+    assert abs(P.rk4_step(x, u, ts, 4, w=np.array([[0.5, 0, 0, 0, 0.0]]))[0, 0] - P.rk4_step(x, u, ts, 4)[0, 0] - 0.5e-3) < 1e-6   # dy/dt = v + w
+    si, so = golden_weights["scale/scaler_input"], golden_weights["scale/scaler_output"]
+    B, T = 8, 60
+    pstd = np.array([5e-1, 2e-0, 5e7, 5e7, 2e-0])
+    normals = O.philox_normal4(1234, B, 3 * T)
+    ref = np.full((B, T), 0.4)
+    meas, us = P.closed_loop(_fnn(golden_weights), si, so, np.repeat(P.INIT_STATE[None], B, 0), ref, 1e-3, 4, np.float64,
+                             pstd, np.zeros(5), normals)
+    assert np.isfinite(meas).all() and np.abs(meas[:, :, 0]).max() < 0.1 and meas[:, :, 2:4].max() < 64e6
