@@ -86,7 +86,11 @@ struct MpcPair {
   static constexpr float kExpMax = 30.0f;
   static constexpr float kLog2e = 1.4426950216293335f;            // fp32(log2 e)
   static constexpr float kLog2eLo = 1.92596e-8f;                  // log2 e - fp32(log2 e)
+#ifdef FC_ABL_NO_MUFU         // timing ablation only: no MUFU.EX2 / MUFU.RCP
+  FC_HD_CTX static float denom_(float e2arg) { return 1.f + fminf(e2arg, kExpMax) * fminf(e2arg, kExpMax); }
+#else
   FC_HD_CTX static float denom_(float e2arg) { return 1.f + Ctx::ex2(fminf(e2arg, kExpMax)); }
+#endif
   FC_HD_CTX static void quad_rcp(float a, float b, float c, float d, float& ra, float& rb, float& rc, float& rd) {
     const float ab = a * b, cd = c * d;
     const float r = Ctx::rcp(ab * cd);
@@ -138,6 +142,9 @@ struct MpcPair {
     if (X) phF1 += 1; else phF0 += 1;
   }
   FC_HD_CTX void swap_cells() {                            // cell-update warps only
+#ifdef FC_ABL_NO_SWAP        // timing ablation only
+    return;
+#endif
     if (ntl > 1) {
       float o[kMaxOwn];
       const int col = kColPark + kMaxOwn * th;
@@ -261,9 +268,13 @@ struct MpcPair {
     const float* a_hi = sm + kSmOpP + op_fwd_halves(X) / 2;
     const float* a_lo = a_hi + kOpLoHalves / 2;
     const int d = col_d_fwd(X);
+#ifdef FC_ABL_ONE_TERM       // timing ablation only (results lose the error compensation)
+    ctx.mma_ss(d, kNF, a_hi, b_hi, kNF, ksteps, false);
+#else
     ctx.mma_ss(d, kNF, a_lo, b_hi, kNF, ksteps, false);
     ctx.mma_ss(d, kNF, a_hi, b_lo, kNF, ksteps, true);
     ctx.mma_ss(d, kNF, a_hi, b_hi, kNF, ksteps, true);
+#endif
     ctx.commit(kBarFull + X);
   }
   FC_HD_CTX void issue_bwd(int X, int l) {
@@ -272,15 +283,23 @@ struct MpcPair {
     const float* b_lo = b_hi + bwd_img_halves(l) / 2;
     const int d = col_d_bwd(X);
     if (X == 0) {
+#ifdef FC_ABL_ONE_TERM
+      ctx.mma(d, nb, kColGhi, b_hi, nb, 0, kKB / 16, false);
+#else
       ctx.mma(d, nb, kColGlo, b_hi, nb, 0, kKB / 16, false);
       ctx.mma(d, nb, kColGhi, b_lo, nb, 0, kKB / 16, true);
       ctx.mma(d, nb, kColGhi, b_hi, nb, 0, kKB / 16, true);
+#endif
     } else {
       const float* a_hi = sm + kSmOpP;
       const float* a_lo = a_hi + kOpGLoHalves / 2;
+#ifdef FC_ABL_ONE_TERM
+      ctx.mma_ss(d, nb, a_hi, b_hi, nb, kKB / 16, false);
+#else
       ctx.mma_ss(d, nb, a_lo, b_hi, nb, kKB / 16, false);
       ctx.mma_ss(d, nb, a_hi, b_lo, nb, kKB / 16, true);
       ctx.mma_ss(d, nb, a_hi, b_hi, nb, kKB / 16, true);
+#endif
     }
     ctx.commit(kBarFull + X);
   }
@@ -456,7 +475,11 @@ struct MpcPair {
     if (l == 0 && scalar && t + 1 < kLook) load_features(X, m, t + 1, xin);
     float* rec_out = nullptr;
     if (p.with_grad && t >= tmin)
+#ifdef FC_ABL_NO_REC_TRAFFIC  // timing ablation only: every record lands in the same L2-resident slot
+      rec_out = w_rec(X);
+#else
       rec_out = w_rec(X) + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsP;
+#endif
     const int ksteps = t == 0 ? (l == 0 ? 1 : 4) : kf_of(l) / 16;
     const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
     const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
@@ -834,7 +857,11 @@ struct MpcPair {
     if (t - 1 >= tmin) prefetch_record(rec_l + (size_t)(t - 1 - tmin) * kRecFloatsP);
     else if (l > 0) prefetch_record(w_rec(X) + (size_t)(rec_base(m) + (long)(l - 1) * steps_kept(m) + (kLook - 1 - tmin)) * kRecFloatsP);
     else if (m > 0) prefetch_record(w_rec(X) + (size_t)(rec_base(m - 1) + (long)(kLayers - 1) * steps_kept(m - 1) + (kLook - 1 - t_min_of(m - 1))) * kRecFloatsP);
+#ifdef FC_ABL_NO_REC_TRAFFIC
+    const float* rp = w_rec(X) + ((size_t)uw * kRecF4 * 32 + lane) * 4;
+#else
     const float* rp = rec_l + (size_t)(t - tmin) * kRecFloatsP + ((size_t)uw * kRecF4 * 32 + lane) * 4;
+#endif
     float rv[2][20];
     rec_load<4>(rp, 0, rv[0]);                             // first record group: in flight during the wait
     {

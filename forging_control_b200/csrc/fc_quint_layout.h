@@ -9,10 +9,13 @@
 //   * 10 units per thread are few enough to keep the cell state of BOTH tiles in registers (2 x 10), so the
 //     park-and-swap of the cell state through spare TMEM columns at every item disappears.
 //
-// 800 threads = 25 warps; thread (warp w, lane i) works on TMEM lane / trajectory row r = 32*(w%4)+i of BOTH tiles.
-//   warp 0        MMA issuer (all 32 lanes walk the issue loop, lane 0 issues)
-//   warps 1..3    per-trajectory scalar work (roll-out rows, layer-0 features, read-out, cost terms, controller, row-feature
-//   warp 24       gradients) of the rows of their TMEM quadrant (w%4 = 1, 2, 3, 0)
+// 768 threads = 24 warps (6 per SM sub-partition: 80 registers per thread; a 25th warp would put 7 warps on one
+// sub-partition and cap everybody at 72); thread (warp w, lane i) works on TMEM lane / trajectory row r = 32*(w%4)+i
+// of BOTH tiles.
+//   warps 0..3    per-trajectory scalar work (roll-out rows, layer-0 features, read-out, cost terms, controller, row-feature
+//                 gradients) of the rows of their TMEM quadrant; warp 0 is also the MMA issuer (all 32 lanes walk the
+//                 issue loop, lane 0 issues): it idles two thirds of the time waiting for the cell updates, which is
+//                 where its scalar work goes
 //   warps 4..23   cell update: group g = (w-4)/4 owns the hidden units [10 g, 10 g + 10)
 //
 // Operand K slots.  The K-major operand images are written in 16-byte pieces (8 halves); 10 units per group do not
@@ -24,7 +27,9 @@
 //            A k-index: layers 1,2 (K=112): [0,56) slot of input unit | [56,112) slot of recurrent unit
 //                       layer 0   (K=64) : [0,5) row features | 3 zero | [8,64) slot of recurrent unit
 // backward : D[128 x Nb] = dG[128 x 208] (k = unit*4+gate, natural order: group g = pieces 5g..5g+4; 8 zero) * WB^T
-//            layers 1,2 (Nb=112): group g owns columns [20 g, 20 g + 20): 10 x d(input unit), 10 x d(h_prev unit)
+//            layers 1,2 (Nb=112): group g owns columns [20 g, 20 g + 20), interleaved by pairs of units so that one
+//                                 4-column TMEM load serves a pair: column 20 g + 4 k + q = d(input unit 10g+2k+q) for q < 2,
+//                                 d(h_prev unit 10g+2k+q-2) for q >= 2
 //            layer 0    (Nb=64) : group g owns [10 g, 10 g + 10) d(h_prev unit); [56,61) d(row feature) (scalar warps)
 #pragma once
 #include "fc_layout.h"
@@ -41,10 +46,10 @@ constexpr int kKF0 = 64, kKF = 112;
 constexpr int kRec0 = 8, kRec = 56;      // first recurrent k-index (layer 0 / layers 1,2)
 constexpr int kKB = 208;
 constexpr int kNB0 = 64, kNB = 112;
-constexpr int kWarpsQ = 25;
-constexpr int kThreadsQ = kWarpsQ * 32;  // 800
+constexpr int kWarpsQ = 24;
+constexpr int kThreadsQ = kWarpsQ * 32;  // 768
 constexpr int kUpdWarpsQ = 20;           // cell-update warps (4..23)
-constexpr int kScalarWarpsQ = 4;         // warps 1, 2, 3, 24
+constexpr int kScalarWarpsQ = 3;         // warps 1, 2, 3 arrive on the ready barriers (warp 0 is the one that waits)
 constexpr float kScaleA = 1024.0f, kScaleW = 2048.0f;   // exact power-of-two operand scales (see fc_tc_layout.h)
 
 FC_HD int slot_of(int u) { const int g = u / kOwn, j = u - g * kOwn; return j < 8 ? 8 * g + j : 40 + 2 * g + (j - 8); }
@@ -98,8 +103,9 @@ FC_HD float bwd_weight(const RawWeights& w, int l, int h) {
     return 0.f;
   }
   if (n >= 2 * kHid) return 0.f;
-  const int grp = n / (2 * kOwn), r = n - grp * 2 * kOwn;
-  return r < kOwn ? w.w_ih[l][row * kHid + grp * kOwn + r] : w.w_hh[l][row * kHid + grp * kOwn + (r - kOwn)];
+  const int grp = n / (2 * kOwn), r = n - grp * 2 * kOwn, k = r >> 2, q = r & 3;
+  const int u = grp * kOwn + 2 * k + (q & 1);
+  return q < 2 ? w.w_ih[l][row * kHid + u] : w.w_hh[l][row * kHid + u];
 }
 struct QSlot { int kind; int l; int lo; int h; };   // kind 0 = forward, 1 = backward
 FC_HD QSlot decode_half(long hidx) {                // hidx counts halves from the start of the quint pack buffer
@@ -131,12 +137,13 @@ constexpr int kColGhi = 224, kColGlo = 328;                   // dG operand of t
 //   rows [(N+10)][5][128], cost [3][128],
 //   seq  [10][20 warps][hi8: 32 x float4 | lo8: 32 x float4 | pairs: 32 x float2]   (fp16 pieces in operand format)
 //   dseq [10][20 warps][10][32], grow [N][5][128],
-//   rec  [nrec][20 warps][13][32] float4   (10 units x (i,f,g,o,c_prev) = 50 floats -> 13 float4)
+//   rec  [nrec][20 warps][ 10 x 32 float4 (i,f,g,o of unit j) | 5 x 32 float2 (c_prev of the unit pair k) ]
 constexpr int kSeqWarp = 32 * 4 + 32 * 4 + 32 * 2;           // 320 floats per warp and step
 constexpr int kSeqSlot = kUpdWarpsQ * kSeqWarp;              // 6400 floats per step
 constexpr int kDseqSlot = kUpdWarpsQ * kOwn * 32;            // 6400
-constexpr int kRecF4 = 13;
-constexpr int kRecFloatsQ = kUpdWarpsQ * kRecF4 * 32 * 4;    // 33280
+constexpr int kRecWarp = kOwn * 32 * 4 + (kOwn / 2) * 32 * 2;   // 1600 floats = 6400 B per warp, contiguous
+constexpr int kRecCp = kOwn * 32 * 4;                         // offset of the c_prev pairs inside a warp's block
+constexpr int kRecFloatsQ = kUpdWarpsQ * kRecWarp;            // 32000
 struct WorkLayoutQ {
   size_t rows, cost, seq, dseq, grow, rec, total;
 };

@@ -18,6 +18,9 @@ g = torch.Generator(device=dev).manual_seed(1234)
 X = torch.rand(B, 3, generator=g, device=dev) * 2 - 1
 Z = torch.rand(B, 10, 5, generator=g, device=dev) * 2 - 1
 u0 = ctl(X).detach().reshape(-1).contiguous()
+from forging_control_b200 import _native
+if os.environ.get('AB_MODE'):
+    _native.lib().fc_mpc_select_kernel(int(os.environ['AB_MODE']))
 for _ in range(3):
     fb.mpc_loss_native(wp, X, u0, Z, N, 20.0, True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,4 +30,4 @@ for _ in range(K):
     r = fb.mpc_loss_native(wp, X, u0, Z, N, 20.0, True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print(json.dumps({"lib": os.environ.get("FC_LIB_PATH", "default"), "ms": ms, "Msteps_per_s": B * N / ms / 1e3, "loss": float(r["gl"][250])}))
+print(json.dumps({"lib": os.environ.get("FC_LIB_PATH", "default"), "mode": os.environ.get("AB_MODE", "auto"), "B": B, "N": N, "ms": ms, "Msteps_per_s": B * N / ms / 1e3, "loss": float(r["gl"][250])}))
