@@ -16,7 +16,7 @@ _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.environ.get("FC_LIB_PATH", os.path.join(_PKG_DIR, "libforging_b200.so"))   # override: development builds
 SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in
            ("fc_api.cu", "fc_mpc_kernel.inl", "fc_layout.h", "fc_plant.cuh", "fc_mpc_tc_kernel.inl", "fc_tc_layout.h",
-            "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_mpc_quint_kernel.inl", "fc_quint_layout.h", "fc_lstm_train.cuh", "fc_fnn.cuh")]
+            "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_lstm_train.cuh", "fc_fnn.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

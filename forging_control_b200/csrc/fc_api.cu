@@ -13,7 +13,6 @@
 #include "fc_mpc_kernel.inl"
 #include "fc_mpc_tc_kernel.inl"
 #include "fc_mpc_pair_kernel.inl"
-#include "fc_mpc_quint_kernel.inl"
 #include "fc_plant.cuh"
 
 namespace fc {
@@ -332,29 +331,6 @@ __global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_pair_kernel(const M
   k.run();
 }
 
-__global__ void __launch_bounds__(q5::kThreadsQ, 1) mpc_loss_quint_kernel(const MpcParams p) {
-  DevCtxTC ctx;
-  q5::MpcQuint<DevCtxTC> k(ctx, p);
-  k.run();
-}
-
-// quint-kernel operand images (permuted K slots, see fc_quint_layout.h) behind the three others in the packed buffer
-__global__ void pack_weights_quint_kernel(RawWeights w, float* out) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // half index
-  const long n_halves = 2L * q5::kSmallOff;
-  float* base = out + kPackFloats + tc::kPackFloatsTC + pr::kPackFloatsP;
-  __half* oh = reinterpret_cast<__half*>(base);
-  if (i < n_halves) {
-    const q5::QSlot s = q5::decode_half(i);
-    const float v = (s.kind == 0 ? q5::fwd_weight(w, s.l, s.h) : q5::bwd_weight(w, s.l, s.h)) * q5::kScaleW;
-    const __half hi = __float2half_rn(v);
-    oh[i] = s.lo ? __float2half_rn(v - __half2float(hi)) : hi;
-  } else if (i < n_halves + kSmallFloats) {
-    const int j = (int)(i - n_halves);
-    base[q5::kSmallOff + j] = packed_value(w, kFCW + j);
-  }
-}
-
 // pair-kernel operand images behind the two others in the packed buffer
 __global__ void pack_weights_pair_kernel(RawWeights w, float* out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // half index
@@ -508,8 +484,7 @@ static int ensure_smem_attributes();
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel,
-// 4 = tcgen05 quint kernel (two tiles per CTA, five unit groups, 25 warps).
+// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel.
 // Thread-local: fc_mpc_select_kernel affects the calling thread's subsequent fc_mpc_loss* / workspace queries only
 // (no process-global state; the library stays re-entrant across threads and devices).
 static thread_local int g_mpc_mode = -1;
@@ -520,16 +495,13 @@ static int mpc_mode() {
     if (e && !strcmp(e, "ffma")) g_mpc_mode = 1;
     if (e && !strcmp(e, "tc")) g_mpc_mode = 2;
     if (e && !strcmp(e, "pair")) g_mpc_mode = 3;
-    if (e && !strcmp(e, "quint")) g_mpc_mode = 4;
   }
   return g_mpc_mode;
 }
 
-constexpr int kAutoTwoTileKind = 2;     // MpcPlan::kind of the two-tile kernel the automatic choice takes (2 = pair, 3 = quint)
 struct MpcPlan {
-  int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair, 3 = tcgen05 quint
+  int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair
   int grid, tiles;
-  int tile_rows;        // one-tile tcgen05 kernel: trajectories per tile (32, 64, 96, 128)
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
@@ -544,30 +516,20 @@ static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1)
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
-  pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : (mode == 4 ? 3 : 1));
+  pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
   {
     const int t128 = (B + tc::kTileTC - 1) / tc::kTileTC;
     // more tiles than SMs: two tiles per CTA overlap tensor and cell-update work; a single tile: the two-tile kernels'
     // dedicated issuer warp alone is worth 5 % (B=15: 2.11 ms against 2.23 ms)
-    if (mode == 0 && (t128 > sms || t128 == 1)) pl->kind = kAutoTwoTileKind;
+    if (mode == 0 && (t128 > sms || t128 == 1)) pl->kind = 2;
   }
   if (width_dim > 1) pl->kind = 1;        // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
-  int tile = pl->kind ? tc::kTileTC : kTile;
-  pl->tile_rows = tc::kTileTC;
-  if (pl->kind == 1 && width_dim <= 1) {
-    // mid-size batches: the fewest rows per tile (a whole number of 32-lane TMEM quadrants) that still gives every tile
-    // an SM of its own -- B = 4096 runs as 128 tiles of 32 rows on 128 SMs instead of 32 tiles of 128 rows on 32 SMs;
-    // warps of empty quadrants skip the cell update, so a tile's dependent-step time shrinks as well
-    for (int r = 32; r < tc::kTileTC; r += 32)
-      if ((B + r - 1) / r <= sms) { pl->tile_rows = r; break; }
-    tile = pl->tile_rows;
-  }
+  const int tile = pl->kind ? tc::kTileTC : kTile;
   pl->tiles = (B + tile - 1) / tile;
-  const int units = pl->kind >= 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
+  const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
   pl->grid = units < sms ? units : sms;
-  pl->work_stride = pl->kind == 3 ? q5::kTilesQ * q5::work_layout_q(N, with_grad).total
-                    : pl->kind == 2 ? pr::kTiles * pr::work_layout_p(N, with_grad).total
-                                    : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad, width_dim).total : work_layout(N, with_grad).total);
+  pl->work_stride = pl->kind == 2 ? pr::kTiles * pr::work_layout_p(N, with_grad).total
+                                  : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad, width_dim).total : work_layout(N, with_grad).total);
   pl->bytes = (size_t)pl->grid * kPartialStride * sizeof(double) + (size_t)pl->grid * pl->work_stride * sizeof(float);
   if (width_dim > 1) pl->bytes += (size_t)pl->grid * kWidePartialStride * sizeof(double);
   return FC_OK;
@@ -624,8 +586,6 @@ static int ensure_smem_attributes() {
           "cudaFuncSetAttribute(smem, tc)");
   FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
           "cudaFuncSetAttribute(smem, pair)");
-  FC_CUDA(cudaFuncSetAttribute(mpc_loss_quint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q5::kSmBytesQ),
-          "cudaFuncSetAttribute(smem, quint)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd),
           "cudaFuncSetAttribute(smem, lstm fwd)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd80),
@@ -644,9 +604,7 @@ extern "C" {
 
 const char* fc_last_error(void) { return g_err; }
 int fc_version(void) { return 100; }
-size_t fc_pack_floats(void) {
-  return (size_t)kPackFloats + (size_t)tc::kPackFloatsTC + (size_t)pr::kPackFloatsP + (size_t)q5::kPackFloatsQ;
-}
+size_t fc_pack_floats(void) { return (size_t)kPackFloats + (size_t)tc::kPackFloatsTC + (size_t)pr::kPackFloatsP; }
 
 int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
                     const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
@@ -665,14 +623,12 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
   FC_CUDA(cudaGetLastError(), "pack_weights_tc_kernel launch");
   pack_weights_pair_kernel<<<(2 * pr::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, wpack);
   FC_CUDA(cudaGetLastError(), "pack_weights_pair_kernel launch");
-  pack_weights_quint_kernel<<<(2 * q5::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, wpack);
-  FC_CUDA(cudaGetLastError(), "pack_weights_quint_kernel launch");
   return FC_OK;
 }
 
 int fc_mpc_select_kernel(int mode) {
-  if (mode < 0 || mode > 4)
-    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05), 3 (tcgen05 pair) or 4 (tcgen05 quint)");
+  if (mode < 0 || mode > 3)
+    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05) or 3 (tcgen05 pair)");
   g_mpc_mode = mode;
   return FC_OK;
 }
@@ -695,11 +651,7 @@ size_t fc_mpc_loss_scratch_traffic_bytes(int B, int N) {
   long kept = 0;                                    // kept (window, step) pairs per layer
   for (int m = 0; m < N; ++m) kept += steps_kept(m);
   size_t per_tile = 0;
-  if (pl.kind == 3) {
-    per_tile = (size_t)rec_base(N) * q5::kRecFloatsQ * 2                                  // records: write + read
-               + (size_t)N * (kLayers - 1) * kLook * q5::kSeqSlot * 2                     // operand-format hidden sequence
-               + (size_t)kept * (kLayers - 1) * q5::kDseqSlot * 2;                        // d-sequence
-  } else if (pl.kind == 2) {
+  if (pl.kind == 2) {
     per_tile = (size_t)rec_base(N) * pr::kRecFloatsP * 2                                  // records: write + read
                + (size_t)N * (kLayers - 1) * kLook * pr::kSlot * 2                        // operand-format hidden sequence
                + (size_t)kept * (kLayers - 1) * (pr::kUpdWarps * pr::kMaxOwn * 32) * 2;    // d-sequence
@@ -771,8 +723,7 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   MpcParams p;
   memset(&p, 0, sizeof(p));
   p.X = X; p.u0 = u0; p.Z = Z;
-  p.wpack = pl.kind == 3 ? wpack + kPackFloats + tc::kPackFloatsTC + pr::kPackFloatsP
-            : pl.kind == 2 ? wpack + kPackFloats + tc::kPackFloatsTC : (pl.kind == 1 ? wpack + kPackFloats : wpack);
+  p.wpack = pl.kind == 2 ? wpack + kPackFloats + tc::kPackFloatsTC : (pl.kind == 1 ? wpack + kPackFloats : wpack);
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.partial = reinterpret_cast<double*>(workspace);
   p.width_dim = width_dim; p.int_w = int_w; p.int_b = int_b;
@@ -781,7 +732,6 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   p.work = reinterpret_cast<float*>(after_partial);
   p.work_stride = pl.work_stride;
   p.B = B; p.N = N; p.with_grad = with_grad ? 1 : 0; p.num_tiles = pl.tiles;
-  p.tile_rows = pl.tile_rows;
   p.alpha = alpha;
   p.grad_scale = (float)(1.0 / ((double)N * (double)B_global));
   // 1.0 = the law measured on iid data (scripts/micro/umma_test.cu); real LSTM partial sums are more coherent and
@@ -796,8 +746,7 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   p.debug_timing = getenv("FC_TC_TIMING") ? 1 : 0;
   p.noise_std = noise_std; p.noise_seed = noise_seed;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl.kind == 3) mpc_loss_quint_kernel<<<pl.grid, q5::kThreadsQ, q5::kSmBytesQ, st>>>(p);
-  else if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+  if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
   else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, width_dim > 1 ? tc::kSmBytesWide : tc::kSmBytesTC, st>>>(p);
   else mpc_loss_kernel<<<pl.grid, kThreads, kSmBytes, st>>>(p);
   FC_CUDA(cudaGetLastError(), "mpc_loss kernel launch");

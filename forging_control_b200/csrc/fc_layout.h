@@ -215,10 +215,6 @@ struct MpcParams {
   unsigned long long noise_seed;
   // LSTM shadow roll-out (pair kernel, forward only; Functions.py:969-1011, 1196-1231): N windows, the command of
   // every step is an input, no cost / controller / reverse sweep
-  // one-tile tcgen05 kernel: trajectories per tile (32, 64, 96 or 128; 0 = 128).  Fewer rows per tile spread a mid-size
-  // batch over more SMs; warps whose TMEM quadrant holds no row of the tile skip the cell update (they only keep the
-  // barriers), which also shortens the dependent-step latency of the reference's own batch of 15
-  int tile_rows;
   int shadow;
   const float* sh_row0;  // [B][5]  first window row (scaled), repeated 10 times
   const float* sh_u;     // [B][N]  scaled commands; sh_u[b][m+1] closes the row appended after window m

@@ -23,8 +23,6 @@ struct MpcTileTC {
   const MpcParams& p;
   float* sm;
   int tid, warp, lane, row, quarter, nown, u_first;
-  int trows;             // trajectories per tile (p.tile_rows: 32, 64, 96 or 128)
-  bool live;             // this warp's TMEM quadrant holds rows of the tile; dead warps only keep the barriers
   bool full;             // this quarter owns 13 units (else 12: unit slot 12 is a masked dummy)
   float *rows, *seq, *dseq, *grow, *rec, *actg;
   float c[kMaxOwn];      // forward: cell state, backward: d(cell state)
@@ -44,8 +42,6 @@ struct MpcTileTC {
     nown = units_of(quarter);
     u_first = first_unit(quarter);
     full = nown == kMaxOwn;
-    trows = (p.tile_rows > 0 && p.tile_rows < kTileTC && p.width_dim <= 1) ? p.tile_rows : kTileTC;
-    live = 32 * (warp & 3) < trows;
     WorkLayoutTC wl = work_layout_tc(p.N, p.with_grad, p.width_dim);
     float* base = p.work + (size_t)ctx.bid() * p.work_stride;
     rows = base + wl.rows;
@@ -66,9 +62,6 @@ struct MpcTileTC {
 #else
   FC_HD_CTX void lap(int) {}
 #endif
-
-  // global trajectory index of this thread's row in `tile` (out of range for rows the tile does not hold)
-  FC_HD_CTX int traj(int tile) const { return row < trows ? tile * trows + row : 0x7fffffff; }
 
   // Activations.  MUFU (ex2 / rcp, 16 lanes per clock and SM) bounds the cell update, so reciprocals are shared:
   // 1/a, 1/b, 1/c, 1/d come from ONE rcp of the product (9 extra multiplies on the FMA pipe instead of 3 MUFU
@@ -156,7 +149,7 @@ struct MpcTileTC {
   // tile set-up (quarter-0 thread of each trajectory)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void load_tile(int tile) {
-    const int b = traj(tile);
+    const int b = tile * kTileTC + row;
     const bool ok = b < p.B;
     if (quarter == 0) {
       for (int r = 0; r < kLook; ++r)
@@ -173,12 +166,6 @@ struct MpcTileTC {
       sm[kSmCostTC + kTileTC + row] = 0.f;
       sm[kSmCostTC + 2 * kTileTC + row] = 0.f;
       if (ok) p.pred[(size_t)b * p.N] = p.u0[b];                                     // :1417-1418
-      if (!live) {                                           // rows of a dead quadrant: the glue is skipped, its scratch stays zero
-        sm[kSmDvTC + row] = 0.f;
-        sm[kSmFinTC + row] = 0.f; sm[kSmFinTC + kTileTC + row] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sm[kSmGxTC + q * kTileTC + row] = 0.f;
-      }
     }
   }
 
@@ -284,7 +271,7 @@ struct MpcTileTC {
       const int rec_col = (l == 0 ? kRec0 : kRec) / 2 + block_start(quarter) / 2;   // first recurrent column of this quarter
       float h[kMaxOwn], xin[kMaxOwn];
       // A(0): zero recurrent columns and padding, input of step 0
-      if (live) {
+      {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         ctx.template tmem_st<4>(kColAhi + rec_col, z); ctx.template tmem_st<2>(kColAhi + rec_col + 4, z);
         ctx.template tmem_st<4>(kColAlo + rec_col, z); ctx.template tmem_st<2>(kColAlo + rec_col + 4, z);
@@ -294,11 +281,9 @@ struct MpcTileTC {
           else        { ctx.template tmem_st<4>(kColAhi + 52, z); ctx.template tmem_st<4>(kColAlo + 52, z); }
         }
       }
-      if (live) {
-        load_input(l, m, 0, xin);
-        store_input(l, xin);
-        ctx.tmem_st_wait();
-      }
+      load_input(l, m, 0, xin);
+      store_input(l, xin);
+      ctx.tmem_st_wait();
       wait_bar(kBarWeights);                               // operand image of this layer landed
       ctx.tc_sync();
       lap(9);
@@ -307,7 +292,7 @@ struct MpcTileTC {
         lap(0);
         const int ksteps = t == 0 ? (l == 0 ? 1 : 4) : kf / 16;
         if (tid == 0) issue_mma(kColD, kNF, kColAhi, kColAlo, ksteps, fwd_img_halves(l), kBarChunk0);
-        if (live && t + 1 < kLook) load_input(l, m, t + 1, xin);
+        if (t + 1 < kLook) load_input(l, m, t + 1, xin);
         float* rec_out = nullptr;
         if (p.with_grad && t >= tmin) rec_out = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsTC;
         const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
@@ -320,7 +305,6 @@ struct MpcTileTC {
           else if (p.with_grad) request_weights(true, kLayers - 1);
           else if (more_after) request_weights(false, 0);
         }
-        if (live) {
         if (t + 1 < kLook) store_input(l, xin);            // input columns of step t+1: overlap with the cell update
         fwd_pointwise(t == 0, corr, h, rec_out);
         lap(3);
@@ -350,7 +334,6 @@ struct MpcTileTC {
             for (int q = 0; q < 4; ++q) hrec[q] = xq[q];   // parked until the barrier below
           }
         }
-        }   // live
         ctx.tc_sync();
         lap(4);
       }
@@ -359,7 +342,7 @@ struct MpcTileTC {
     if (p.width_dim > 1) {
       fwd_glue_wide(tile, m);
     } else {
-      if (quarter == 0 && live) fwd_glue(tile, m);
+      if (quarter == 0) fwd_glue(tile, m);
       ctx.sync();
     }
     lap(10);
@@ -377,7 +360,7 @@ struct MpcTileTC {
              sw[(kFCB - kFCW) + q];
     if (p.noise_std > 0.f) {                                                   // enable_noise, :1400-1402 / :1438-1440
       float e[4];
-      philox_normal4(p.noise_seed, (unsigned)(traj(tile)), (unsigned)m, e);
+      philox_normal4(p.noise_seed, (unsigned)(tile * kTileTC + row), (unsigned)m, e);
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
     }
@@ -406,7 +389,7 @@ struct MpcTileTC {
       unext = fminf(fmaxf(v, -1.f), 1.f);                                      // nn.Hardtanh
       sm[kSmUprevTC + row] = ucur;
       sm[kSmUcurTC + row] = unext;
-      int b = traj(tile);
+      int b = tile * kTileTC + row;
       if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;                    // :1455
     }
     rnew[4 * kTileTC] = unext;
@@ -476,7 +459,7 @@ struct MpcTileTC {
                sw[(kFCB - kFCW) + q];
       if (p.noise_std > 0.f) {
         float e[4];
-        philox_normal4(p.noise_seed, (unsigned)(traj(tile)), (unsigned)m, e);
+        philox_normal4(p.noise_seed, (unsigned)(tile * kTileTC + row), (unsigned)m, e);
 #pragma unroll
         for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
       }
@@ -503,7 +486,7 @@ struct MpcTileTC {
         unext = fminf(fmaxf(wide_output(wide_buf(cur)), -1.f), 1.f);           // nn.Hardtanh
         sm[kSmUprevTC + row] = ucur;
         sm[kSmUcurTC + row] = unext;
-        int b = traj(tile);
+        int b = tile * kTileTC + row;
         if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;
       }
     }
@@ -521,7 +504,7 @@ struct MpcTileTC {
     const float* iw = sw + (kINPW - kFCW);
     const float* ow = sw + (kOUTW - kFCW);
     const float* wi = sm + kSmWideW;
-    const bool valid = traj(tile) < p.B;
+    const bool valid = tile * kTileTC + row < p.B;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, gu = 0.f;
     if (quarter == 0) {
       const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;
@@ -752,8 +735,8 @@ struct MpcTileTC {
     const float* iw = sw + (kINPW - kFCW);
     const float* ib = sw + (kINPB - kFCW);
     const float* ow = sw + (kOUTW - kFCW);
-    if (quarter == 0 && live) {
-      const bool valid = traj(tile) < p.B;
+    if (quarter == 0) {
+      const bool valid = tile * kTileTC + row < p.B;
       const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileTC + row;
       float x0 = Ctx::ldcg(rx), x1 = Ctx::ldcg(rx + kTileTC), x2 = Ctx::ldcg(rx + 2 * kTileTC), x3 = Ctx::ldcg(rx + 3 * kTileTC);
       const float ref = sm[kSmRefTC + row];
@@ -847,23 +830,19 @@ struct MpcTileTC {
       Factors fa;
       float extra[kMaxOwn];
       const float* rec_l = rec + (size_t)(rec_base(m) + (long)l * steps_kept(m)) * kRecFloatsTC;
-      if (live) {
-        bwd_factors(rec_l + (size_t)(kLook - 1 - tmin) * kRecFloatsTC, fa);
-        bwd_extra(l, kLook - 1, extra);
-      }
+      bwd_factors(rec_l + (size_t)(kLook - 1 - tmin) * kRecFloatsTC, fa);
+      bwd_extra(l, kLook - 1, extra);
       wait_bar(kBarWeights);
       lap(12);
       for (int t = kLook - 1; t >= tmin; --t) {
         lap(0);
-        if (live) {
-          bwd_finish(fa, extra);
-          ctx.tmem_st_wait();
-        }
+        bwd_finish(fa, extra);
+        ctx.tmem_st_wait();
         ctx.tc_sync();
         lap(5);
         if (tid == 0) issue_mma(kColD, nb, kColGhi, kColGlo, kKB / 16, bwd_img_halves(l), kBarChunk0);
         // in the shadow of the MMA: record and upstream gradient of the next step
-        if (live && t > tmin) {
+        if (t > tmin) {
           // HBM -> L2 for the step after next (or the first step of the next layer / window)
           if (t - 2 >= tmin) prefetch_record(rec_l + (size_t)(t - 2 - tmin) * kRecFloatsTC);
           else if (l > 0) prefetch_record(rec + (size_t)(rec_base(m) + (long)(l - 1) * steps_kept(m) + (kLook - 1 - tmin)) * kRecFloatsTC);
@@ -879,9 +858,7 @@ struct MpcTileTC {
           else if (m > 0) request_weights(true, kLayers - 1);
           else if (more_after) request_weights(false, 0);
         }
-        if (!live) {
-          // dead quadrant: nothing to collect
-        } else if (l > 0) {
+        if (l > 0) {
           float d[32];
           ctx.template tmem_ld_nowait<16>(kColD + 26 * quarter, d);
           ctx.template tmem_ld_nowait<8>(kColD + 26 * quarter + 16, d + 16);
@@ -925,7 +902,7 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void store_costs(int tile) {
     if (quarter == 0) {
-      int b = traj(tile);
+      int b = tile * kTileTC + row;
       if (b < p.B) {
         const float inv = 1.f / (float)p.N;
         float cst = sm[kSmCostTC + row] * inv;                                 // :1458-1460
@@ -947,7 +924,7 @@ struct MpcTileTC {
 
   FC_HD_CTX void store_du0(int tile) {
     if (quarter == 0) {
-      int b = traj(tile);
+      int b = tile * kTileTC + row;
       if (b < p.B) {
         const float s = p.grad_scale;
         float u0 = Ctx::ldcg(rows + (size_t)((kLook - 1) * kFeat + 4) * kTileTC + row);

@@ -18,7 +18,6 @@
 #include "../../forging_control_b200/csrc/fc_mpc_kernel.inl"
 #include "../../forging_control_b200/csrc/fc_mpc_tc_kernel.inl"
 #include "../../forging_control_b200/csrc/fc_mpc_pair_kernel.inl"
-#include "../../forging_control_b200/csrc/fc_mpc_quint_kernel.inl"
 #include <atomic>
 #include <cstdint>
 
@@ -155,7 +154,6 @@ struct EmuCtxTC : EmuCtx {
 
 }  // namespace
 
-static int g_tile_rows = 0;
 static float g_noise_std = 0.f;
 static unsigned long long g_noise_seed = 0ull;
 
@@ -163,9 +161,6 @@ extern "C" {
 
 // enable_noise for the following emulated launches (0 = off)
 void fc_emu_set_noise(float std, unsigned long long seed) { g_noise_std = std; g_noise_seed = seed; }
-
-// rows per tile of the one-tile tcgen05 kernel for the following emulated launches (0 = 128)
-void fc_emu_set_tile_rows(int r) { g_tile_rows = r; }
 
 int fc_emu_pack_floats() { return fc::kPackFloats; }
 
@@ -252,8 +247,7 @@ int fc_emu_mpc_loss_tc(const float* X, const float* u0, const float* Z, const fl
   p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
   p.acc_comp = 1.0f;
   { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
-  p.tile_rows = g_tile_rows;
-  { const int tr = g_tile_rows > 0 ? g_tile_rows : fc::tc::kTileTC; p.num_tiles = (B + tr - 1) / tr; }
+  p.num_tiles = (B + fc::tc::kTileTC - 1) / fc::tc::kTileTC;
   if (grid > p.num_tiles) grid = p.num_tiles;
   fc::tc::WorkLayoutTC wl = fc::tc::work_layout_tc(N, with_grad);
   p.work_stride = wl.total;
@@ -423,90 +417,6 @@ int fc_emu_mpc_loss_tc_wide(const float* X, const float* u0, const float* Z, con
     for (int b = 0; b < grid; ++b) a += partial_wide[(size_t)b * fc::kWidePartialStride + i];
     gl_wide[i] = (float)a;
   }
-  return 0;
-}
-int fc_emu_pack_floats_quint() { return fc::q5::kPackFloatsQ; }
-
-void fc_emu_pack_weights_quint(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
-                               const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
-                               const float* inp_w, const float* inp_b, const float* out_w, float* out) {
-  fc::RawWeights w;
-  w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
-  w.fc_w = fc_w; w.fc_b = fc_b; w.inp_w = inp_w; w.inp_b = inp_b; w.out_w = out_w;
-  uint16_t* oh = reinterpret_cast<uint16_t*>(out);
-  const long n_halves = 2L * fc::q5::kSmallOff;
-  for (long i = 0; i < n_halves; ++i) {
-    const fc::q5::QSlot s = fc::q5::decode_half(i);
-    const float v = (s.kind == 0 ? fc::q5::fwd_weight(w, s.l, s.h) : fc::q5::bwd_weight(w, s.l, s.h)) * fc::q5::kScaleW;
-    const uint16_t hi = EmuCtxTC::h_bits(v);
-    oh[i] = s.lo ? EmuCtxTC::h_bits(v - EmuCtxTC::h_val(hi)) : hi;
-  }
-  for (int j = 0; j < fc::kSmallFloats; ++j) out[fc::q5::kSmallOff + j] = fc::packed_value(w, fc::kFCW + j);
-}
-
-static void emu_run_quint(fc::MpcParams& p, int grid) {
-  for (int b = 0; b < grid; ++b) {
-    EmuBlockTC blk(b, grid, fc::q5::kSmFloatsQ, fc::q5::kThreadsQ);
-    std::vector<std::thread> th;
-    th.reserve(fc::q5::kThreadsQ);
-    for (int t = 0; t < fc::q5::kThreadsQ; ++t)
-      th.emplace_back([&blk, &p, t]() {
-        EmuCtxTC ctx(&blk, t);
-        fc::q5::MpcQuint<EmuCtxTC> k(ctx, p);
-        k.run();
-      });
-    for (auto& x : th) x.join();
-  }
-}
-
-int fc_emu_mpc_loss_quint(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
-                          long long B_global, int with_grad, int grid, float* cost, float* command, float* error,
-                          float* pred, float* du0, float* gl /*[256]*/) {
-  fc::MpcParams p;
-  std::memset(&p, 0, sizeof(p));
-  p.X = X; p.u0 = u0; p.Z = Z; p.wpack = wpack;
-  p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
-  p.B = B; p.N = N; p.with_grad = with_grad; p.alpha = alpha;
-  p.grad_scale = 1.0f / ((float)N * (float)B_global);
-  p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
-  p.acc_comp = 1.0f;
-  { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
-  p.num_tiles = (B + fc::q5::kTileQ - 1) / fc::q5::kTileQ;
-  const int npairs = (p.num_tiles + fc::q5::kTilesQ - 1) / fc::q5::kTilesQ;
-  if (grid > npairs) grid = npairs;
-  p.work_stride = fc::q5::kTilesQ * fc::q5::work_layout_q(N, with_grad).total;
-  std::vector<float> work((size_t)grid * p.work_stride, 0.f);
-  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
-  p.work = work.data();
-  p.partial = partial.data();
-  emu_run_quint(p, grid);
-  for (int i = 0; i < 256; ++i) gl[i] = 0.f;
-  for (int i = 0; i <= fc::kNumFnnGrad; ++i) {
-    double a = 0.0;
-    for (int b = 0; b < grid; ++b) a += partial[(size_t)b * fc::kPartialStride + i];
-    gl[i] = (float)(i == fc::kNumFnnGrad ? a / (double)B_global : a);
-  }
-  return 0;
-}
-
-int fc_emu_lstm_shadow_quint(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, int grid,
-                             float* y /*[B][T][4]*/) {
-  fc::MpcParams p;
-  std::memset(&p, 0, sizeof(p));
-  p.wpack = wpack;
-  p.B = B; p.N = T; p.with_grad = 0;
-  p.acc_comp = 1.0f; p.g_scale = p.g_unscale = 1.0f;
-  p.shadow = 1; p.sh_row0 = row0; p.sh_u = u; p.sh_y = y;
-  for (int q = 0; q < 4; ++q) p.sh_ratio[q] = ratio[q];
-  p.num_tiles = (B + fc::q5::kTileQ - 1) / fc::q5::kTileQ;
-  const int npairs = (p.num_tiles + fc::q5::kTilesQ - 1) / fc::q5::kTilesQ;
-  if (grid > npairs) grid = npairs;
-  p.work_stride = fc::q5::kTilesQ * fc::q5::work_layout_q(T, 0).total;
-  std::vector<float> work((size_t)grid * p.work_stride, 0.f);
-  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
-  p.work = work.data();
-  p.partial = partial.data();
-  emu_run_quint(p, grid);
   return 0;
 }
 }  // extern "C"

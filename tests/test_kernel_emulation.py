@@ -17,7 +17,7 @@ EMU_SRC = os.path.join(REPO, "tests", "emu", "fc_emu.cpp")
 EMU_LIB = os.path.join(REPO, "tests", "emu", "libfc_emu.so")
 DEPS = [EMU_SRC] + [os.path.join(REPO, "forging_control_b200", "csrc", f) for f in
                     ("fc_mpc_kernel.inl", "fc_layout.h", "fc_mpc_tc_kernel.inl", "fc_tc_layout.h",
-                     "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_mpc_quint_kernel.inl", "fc_quint_layout.h")]
+                     "fc_mpc_pair_kernel.inl", "fc_pair_layout.h")]
 FP = ctypes.POINTER(ctypes.c_float)
 
 
@@ -126,8 +126,7 @@ def _check_v(o, out, g, tol=1e-5):
     assert rel_max(o["gl"][200:250], g["out_w"][0]) < tol
 
 
-@pytest.mark.parametrize("variant,name", [("tc", "n1_b3"), ("tc", "n2_b5"), ("pair", "n1_b3"), ("pair", "n2_b5"),
-                                          ("quint", "n1_b3"), ("quint", "n2_b5")])
+@pytest.mark.parametrize("variant,name", [("tc", "n1_b3"), ("tc", "n2_b5"), ("pair", "n1_b3"), ("pair", "n2_b5")])
 def test_emulated_tcgen05_kernels_match_oracle(emu, golden_cases, golden_weights, variant, name):
     C = golden_cases
     N, B, wd = (int(v) for v in C[f"{name}/meta"])
@@ -140,7 +139,7 @@ def test_emulated_tcgen05_kernels_match_oracle(emu, golden_cases, golden_weights
     _check_v(o, out, g)
 
 
-@pytest.mark.parametrize("variant", ["pair", "quint"])
+@pytest.mark.parametrize("variant", ["pair"])
 def test_emulated_pair_kernel_two_tiles_and_odd_tail(emu, golden_cases, golden_weights, variant):
     """B = 300 on one emulated CTA: a pass with two tiles in flight, then a pass with a single (ragged) tile."""
     C, name, rep = golden_cases, "n2_b5", 60
@@ -157,28 +156,7 @@ def test_emulated_pair_kernel_two_tiles_and_odd_tail(emu, golden_cases, golden_w
     _check_v(o, out, g)
 
 
-def test_emulated_one_tile_kernel_with_32_row_tiles(emu, golden_cases, golden_weights):
-    """B = 70 as three tiles of 32 rows (the last one ragged) on one emulated CTA: warps of TMEM quadrants 1..3 hold no
-    rows and skip the cell update (mid-batch / small-batch shape of the one-tile tcgen05 kernel)."""
-    C, name, rep = golden_cases, "n2_b5", 14
-    N = int(C[f"{name}/meta"][0])
-    lstm, fnn = state_dicts(golden_weights, str(C[f"{name}/ctl"]))
-    rng = np.random.default_rng(1)
-    X = np.ascontiguousarray(np.tile(C[f"{name}/X"], (rep, 1)), dtype=np.float32)
-    Z = np.tile(C[f"{name}/Z"], (rep, 1, 1))
-    Z = np.ascontiguousarray(Z * (1 + 0.05 * rng.standard_normal(Z.shape)), dtype=np.float32)
-    u0 = np.ascontiguousarray(np.tile(C[f"{name}/f32/u0"], rep))
-    emu.fc_emu_set_tile_rows(32)
-    try:
-        o = _run_v(emu, "tc", _pack_v(emu, lstm, fnn, "tc"), X, u0, Z, N, 20.0, grid=1)
-    finally:
-        emu.fc_emu_set_tile_rows(0)
-    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
-    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
-    _check_v(o, out, g)
-
-
-@pytest.mark.parametrize("variant", ["pair", "quint"])
+@pytest.mark.parametrize("variant", ["pair"])
 def test_emulated_lstm_shadow_rollout_matches_oracle(emu, golden_weights, variant):
     """Forward-only shadow mode of the two-tile kernels (fc_lstm_shadow_rollout) against the oracle restatement of
     simulator_make_step / loop (UL/Functions.py:969-1011, :1196-1231)."""
@@ -196,7 +174,7 @@ def test_emulated_lstm_shadow_rollout_matches_oracle(emu, golden_weights, varian
     assert rel_max(y, ref) < 1e-5
 
 
-@pytest.mark.parametrize("variant", ["ffma", "pair", "quint"])
+@pytest.mark.parametrize("variant", ["ffma", "pair"])
 def test_emulated_enable_noise_matches_oracle_with_the_same_noise(emu, golden_cases, golden_weights, variant):
     """enable_noise (UL/Functions.py:1400-1402): the kernels' counter-based generator restated in the oracle
     (philox_normal4) gives the same roll-out, costs and gradients."""
