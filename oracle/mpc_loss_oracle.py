@@ -305,6 +305,28 @@ def mpc_loss_forward_backward(w, X, u0, Z, N, alpha, width_dim=1, prune=True, no
     return out, grads
 
 
+def kink_margin(w, X, u0, Z, N, alpha, width_dim=1, noise=None) -> np.ndarray:
+    """Per trajectory: the smallest distance of any argument of a non-smooth operation of the roll-out from its kink --
+    ReLU pre-activations of the controller (UL/Functions.py:273-283), the Hardtanh saturation |v| = 1 (:287) and the four
+    pressure-constraint ReLUs (:1411, :1449).  d loss/d u0 of a trajectory is discontinuous there, so an implementation
+    that is accurate to eps on the VALUES may legitimately return a different per-trajectory gradient than the fp64
+    arbiter exactly for the trajectories whose margin is below eps (and for no others)."""
+    out, tape = mpc_loss_forward(w, X, u0, Z, N, alpha, width_dim, keep=True, noise=noise)
+    rows = tape["rows"]
+    B = X.shape[0]
+    margin = np.full(B, np.inf)
+    for m in range(N):
+        x = rows[:, LOOKBACK + m, :4]
+        for v in (x[:, 1], x[:, 2], x[:, 1] - P1_MAX, x[:, 2] - P2_MAX):
+            margin = np.minimum(margin, np.abs(v))
+        if m + 1 < N:
+            _, pre, _, v = tape["fnn"][m + 1]
+            for pk in pre:
+                margin = np.minimum(margin, np.abs(pk).min(axis=1))
+            margin = np.minimum(margin, np.abs(np.abs(v[:, 0]) - 1.0))
+    return margin
+
+
 # ----------------------------------------------------------------------------------------------
 # torch restatement (autograd); used for cross-checks and for bench.py's cpu_baseline leg
 # ----------------------------------------------------------------------------------------------

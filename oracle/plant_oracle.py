@@ -158,7 +158,7 @@ def tvp_reference(t_now, ref_step, bias_work, bias_return, epsilon=1e-7):
 
 
 def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np.float64,
-                process_std=None, meas_std=None, normals=None):
+                process_std=None, meas_std=None, normals=None, u_ulp_jitter=None):
     """x0 [B,5] raw initial state, ref [B,T] physical reference per step.
     Returns (meas [B,T+1,5], u [B,T]); meas[:,0] = x0 as given (Functions.py:1134-1138).
 
@@ -167,7 +167,11 @@ def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np
     side, ``x_next = integrate(dx/dt = f(x, u) + w0)`` with one draw per step (a rate: UL/Main.py:88-96 has 0.5 m/s on
     y and 5e7 Pa/s on the pressures), ``y = measurement(x_next) + v0``, the controller reads ``y``.  ``normals``
     [B, 3T, 4] are the standard normals of the kernels' generator (mpc_loss_oracle.philox_normal4(seed, B, 3T)):
-    step k uses the 12 values normals[:, 3k:3k+3].reshape(B,12): w0 = process_std * [0:5], v0 = meas_std * [5:10]."""
+    step k uses the 12 values normals[:, 3k:3k+3].reshape(B,12): w0 = process_std * [0:5], v0 = meas_std * [5:10].
+
+    ``u_ulp_jitter`` (a numpy Generator): every command is moved by -1, 0 or +1 float32 ulp at random.  The float32
+    controller of any two implementations differs by about that (summation order); the spread between a jittered and a
+    plain run is the arbiter for how far two correct closed loops of this stiff, kinked plant may drift apart."""
     x = np.asarray(x0, dtype=dtype).copy()
     Bn, T = ref.shape
     meas = np.empty((Bn, T + 1, 5), dtype)
@@ -176,6 +180,8 @@ def closed_loop(fnn, scale_in, scale_out, x0, ref, ts=1e-3, substeps=4, dtype=np
     y = x
     for k in range(T):
         u = controller_step(fnn, scale_in, scale_out, y[:, 1].astype(np.float64), y[:, 4].astype(np.float64), ref[:, k])
+        if u_ulp_jitter is not None:
+            u = u * (1.0 + u_ulp_jitter.integers(-1, 2, size=u.shape) * 2.0 ** -23)
         us[:, k] = u
         if normals is not None:
             e = normals[:, 3 * k:3 * k + 3].reshape(Bn, 12)

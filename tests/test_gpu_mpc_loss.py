@@ -71,6 +71,37 @@ def test_module_api_matches_reference_golden(dev, golden_cases, golden_weights, 
     assert ctl.fc_int.weight.grad is None and sim.lstm.weight_hh_l0.grad is None
 
 
+def _assert_flips_sit_on_kinks(w, X, u0, Z, N, d, width_dim=1, noise=None):
+    """The arbiter's own justification of every per-trajectory outlier: a trajectory may differ in d loss/d u0 only if
+    the fp64 oracle has an argument of a ReLU / Hardtanh / constraint kink within the tolerance of the path (1e-5) of
+    that kink -- there the derivative jumps and a value error <= 1e-5 decides the branch.  Anything else is a bug."""
+    flipped = np.nonzero(d > TOL)[0]
+    if len(flipped):
+        margin = O.kink_margin(w, X[flipped], u0[flipped], Z[flipped], N, ALPHA, width_dim,
+                               None if noise is None else noise[flipped])
+        assert margin.max() < TOL, (flipped, margin, d[flipped])
+
+
+def _kernel_vs_oracle_without_flips(run_kernel, run_oracle, X, Z, make_u0, max_rounds=4):
+    """Batch-summed gradients in max-norm at the tolerance of the path.  A trajectory sitting on a kink (see above) moves
+    the sums by O(1/B) of a per-trajectory gradient, which may exceed 1e-5 of the partly cancelling sums; such
+    trajectories are replaced IN PLACE by a copy of a regular one (indices, and with them the counter-based noise of
+    every other trajectory, stay what they were) and both sides are evaluated again."""
+    X, Z = X.clone(), Z.clone()
+    for _ in range(max_rounds):
+        u0 = make_u0(X)
+        r = run_kernel(X, Z, u0)
+        out, g = run_oracle(X, Z, u0)
+        d = np.abs(r["du0"].cpu().numpy() - g["u0"]) / np.abs(g["u0"]).max()
+        flipped = np.nonzero(d > TOL)[0]
+        if len(flipped) == 0:
+            return r, out, g
+        assert len(flipped) <= max(3, 5e-4 * len(d)), (len(flipped), d.max())
+        safe = int(np.argmin(d))
+        X[flipped], Z[flipped] = X[safe], Z[safe]
+    raise AssertionError("trajectories keep landing on kinks")
+
+
 def _seeded(B, seed):
     g = torch.Generator().manual_seed(seed)
     return torch.rand(B, 3, generator=g) * 2 - 1, torch.rand(B, 10, 5, generator=g) * 2 - 1
@@ -100,6 +131,7 @@ def test_native_call_matches_fp64_oracle(dev, golden_weights, N, B, tag):
     d = np.abs(r["du0"].cpu().numpy() - g["u0"]) / np.abs(g["u0"]).max()
     n_flip = int((d > TOL).sum())
     assert n_flip <= 5e-4 * B, (n_flip, d.max())
+    _assert_flips_sit_on_kinks(w, X.double().numpy(), u0.astype(np.float32).astype(np.float64), Z.double().numpy(), N, d)
     if n_flip:
         # A flipped trajectory moves the batch-summed gradients by O(1/B) of a per-trajectory gradient,
         # which can exceed 1e-5 of the (partly cancelling) sums -- torch float32 vs float64 shows the same
@@ -259,13 +291,24 @@ def test_enable_noise_matches_oracle_with_the_same_noise(dev, golden_weights):
     g = torch.Generator().manual_seed(11)
     X = (torch.rand(B, 3, generator=g) * 2 - 1)
     Z = (torch.rand(B, 10, 5, generator=g) * 2 - 1)
-    Xd, Zd = X.to(dev), Z.to(dev)
-    with torch.no_grad():
-        u0 = ctl(Xd).reshape(-1).contiguous()
-    r = fb.mpc_loss_native(fb.pack_weights(sim, ctl), Xd, u0, Zd, N, ALPHA, True, None, std, seed)
     w = O.weights_from_state_dicts(lstm, fnn, np.float64)
     noise = std * O.philox_normal4(seed, B, N)
-    out, gr = O.mpc_loss_forward_backward(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, ALPHA, noise=noise)
+    wp = fb.pack_weights(sim, ctl)
+
+    def make_u0(Xc):
+        with torch.no_grad():
+            return ctl(Xc.to(dev)).reshape(-1).contiguous()
+
+    def run_kernel(Xc, Zc, u0):
+        return fb.mpc_loss_native(wp, Xc.to(dev), u0, Zc.to(dev), N, ALPHA, True, None, std, seed)
+
+    def run_oracle(Xc, Zc, u0):
+        return O.mpc_loss_forward_backward(w, Xc.double().numpy(), u0.double().cpu().numpy(), Zc.double().numpy(), N, ALPHA, noise=noise)
+
+    # first the batch as given: values at the tolerance, per-trajectory outliers only on kinks of the arbiter
+    u0 = make_u0(X)
+    r = run_kernel(X, Z, u0)
+    out, gr = run_oracle(X, Z, u0)
     clean, _ = O.mpc_loss_forward_backward(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, ALPHA)
     gl = r["gl"].cpu().numpy()
     assert abs(gl[250] - out["loss"]) / abs(out["loss"]) < TOL
@@ -273,8 +316,13 @@ def test_enable_noise_matches_oracle_with_the_same_noise(dev, golden_weights):
     assert rel_max(r["cost"].cpu().numpy(), out["cost"]) < TOL
     assert rel_max(r["pred"].cpu().numpy(), out["prediction"]) < TOL
     d = np.abs(r["du0"].cpu().numpy() - gr["u0"]) / np.abs(gr["u0"]).max()
-    assert (d > TOL).sum() <= 3          # kink flips, see test_native_call_matches_fp64_oracle
-    assert rel_max(gl[:150].reshape(50, 3), gr["inp_w"]) < 5e-5 and rel_max(gl[200:250], gr["out_w"][0]) < 5e-5
+    assert (d > TOL).sum() <= 3
+    _assert_flips_sit_on_kinks(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, d, noise=noise)
+    # then the batch-summed gradients at the tolerance of the path
+    r, out, gr = _kernel_vs_oracle_without_flips(run_kernel, run_oracle, X, Z, make_u0)
+    gl = r["gl"].cpu().numpy()
+    assert rel_max(gl[:150].reshape(50, 3), gr["inp_w"]) < TOL and rel_max(gl[150:200], gr["inp_b"]) < TOL
+    assert rel_max(gl[200:250], gr["out_w"][0]) < TOL
 
 
 def test_enable_noise_module_api_is_seeded_by_torch(dev, golden_weights):
@@ -333,22 +381,35 @@ def test_wide_controller_matches_oracle(dev, golden_weights, width, B, N):
     g = torch.Generator().manual_seed(width * 100 + B)
     X = (torch.rand(B, 3, generator=g) * 2 - 1)
     Z = (torch.rand(B, 10, 5, generator=g) * 2 - 1)
-    Xd, Zd = X.to(dev), Z.to(dev)
-    with torch.no_grad():
-        u0 = ctl(Xd).reshape(-1).contiguous()
-    r = fb.mpc_loss_native(fb.pack_weights(sim, ctl), Xd, u0, Zd, N, ALPHA, True, None, 0.0, 0,
-                           ctl.fc_int.weight.detach().contiguous(), ctl.fc_int.bias.detach().contiguous(), width)
     w = O.weights_from_state_dicts(lstm, fnn, np.float64)
-    out, gr = O.mpc_loss_forward_backward(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, ALPHA, width_dim=width)
-    gl, gw = r["gl"].cpu().numpy(), r["gl_wide"].cpu().numpy()
+    wp = fb.pack_weights(sim, ctl)
+    iw, ib = ctl.fc_int.weight.detach().contiguous(), ctl.fc_int.bias.detach().contiguous()
+
+    def make_u0(Xc):
+        with torch.no_grad():
+            return ctl(Xc.to(dev)).reshape(-1).contiguous()
+
+    def run_kernel(Xc, Zc, u0):
+        return fb.mpc_loss_native(wp, Xc.to(dev), u0, Zc.to(dev), N, ALPHA, True, None, 0.0, 0, iw, ib, width)
+
+    def run_oracle(Xc, Zc, u0):
+        return O.mpc_loss_forward_backward(w, Xc.double().numpy(), u0.double().cpu().numpy(), Zc.double().numpy(), N, ALPHA, width_dim=width)
+
+    u0 = make_u0(X)
+    r = run_kernel(X, Z, u0)
+    out, gr = run_oracle(X, Z, u0)
+    gl = r["gl"].cpu().numpy()
     assert abs(gl[250] - out["loss"]) / abs(out["loss"]) < TOL
     assert rel_max(r["cost"].cpu().numpy(), out["cost"]) < TOL
     assert rel_max(r["pred"].cpu().numpy(), out["prediction"]) < TOL
     d = np.abs(r["du0"].cpu().numpy() - gr["u0"]) / np.abs(gr["u0"]).max()
     assert (d > TOL).sum() <= 3
+    _assert_flips_sit_on_kinks(w, X.double().numpy(), u0.double().cpu().numpy(), Z.double().numpy(), N, d, width_dim=width)
+    r, out, gr = _kernel_vs_oracle_without_flips(run_kernel, run_oracle, X, Z, make_u0)
+    gl, gw = r["gl"].cpu().numpy(), r["gl_wide"].cpu().numpy()
     for got, key in ((gl[:150].reshape(50, 3), "inp_w"), (gl[150:200], "inp_b"), (gl[200:250], "out_w"),
                      (gw[:2500].reshape(50, 50), "int_w"), (gw[2500:2550], "int_b")):
-        assert rel_max(got, np.asarray(gr[key]).reshape(got.shape)) < 5e-5, key
+        assert rel_max(got, np.asarray(gr[key]).reshape(got.shape)) < TOL, key
 
 
 def test_fused_controller_forward_backward_matches_oracle(dev, golden_weights):
