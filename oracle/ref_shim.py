@@ -79,9 +79,10 @@ def _install_stubs():
 _CACHE = {}
 
 
-def load_reference_functions():
-    """Return the reference ``Functions`` module (UL variant), imported by path."""
-    if "ul" in _CACHE:
+def load_reference_functions(fresh: bool = False):
+    """Return the reference ``Functions`` module (UL variant), imported by path.  ``fresh`` imports a private copy of
+    the module object (for tests that patch it, e.g. ``forging_control_b200.install``)."""
+    if "ul" in _CACHE and not fresh:
         return _CACHE["ul"]
     if not reference_available():
         raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
@@ -92,12 +93,13 @@ def load_reference_functions():
     os.chdir("/tmp/forging_ref_import")
     try:
         spec = importlib.util.spec_from_file_location(
-            "forging_reference_UL_Functions", os.path.join(UL_DIR, "Functions.py"))
+            "forging_reference_UL_Functions" + ("_fresh" if fresh else ""), os.path.join(UL_DIR, "Functions.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:
         os.chdir(cwd)
-    _CACHE["ul"] = mod
+    if not fresh:
+        _CACHE["ul"] = mod
     return mod
 
 

@@ -164,3 +164,29 @@ def test_install_surrogate_swaps_the_training_step_and_host_loop_matches_the_ref
     assert np.isfinite(v) and v < avg                     # three AdamW steps later the same batches fit better
     _, vt, vv, _ = S.SurrogateNeuralNetwork.train_loop(m, loader[:1], loader[1:2], torch.nn.MSELoss(), opt, 2, "cpu")
     assert len(vt) == 2 and len(vv) == 2 and vt[1] < vt[0]
+
+
+@pytest.mark.reference
+def test_install_on_the_real_reference_module():
+    """install() on the unmodified reference ``Functions`` module (mount or staged copy): the names Main.py:19 imports
+    resolve to the CUDA-path classes afterwards, the reference's own train_loop / test / Data stay in place."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference not mounted")
+    R = ref_shim.load_reference_functions(fresh=True)
+    before = (R.FNNModel, R.LSTMModel, R.MPCLoss, R.NeuralNetwork.train_loop, R.Data)
+    fb.install(R)
+    assert R.FNNModel is fb.FNNModel and R.LSTMModel is fb.LSTMModel and R.MPCLoss is fb.MPCLoss
+    assert R.FNNModel is not before[0] and R.MPCLoss is not before[2]
+    assert R.NeuralNetwork.train_loop is before[3] and R.Data is before[4]           # untouched
+    assert R.NeuralNetwork.train_model is fb.NeuralNetwork.train_model
+    assert R.FeasibilityRecovery.NN_make_step is fb.FeasibilityRecovery.NN_make_step
+    # the shipped checkpoints load strictly into the swapped classes (Main.py:154-168)
+    import torch
+    sim = R.LSTMModel(5, 50, 4, 3)
+    sim.load_state_dict(torch.load(os.path.join(ref_shim.MNN_DIR, "results", "model_NN.pt"), map_location="cpu"), strict=True)
+    ctl = R.FNNModel(3, 50, 1, 1)
+    ctl.load_state_dict(torch.load(os.path.join(ref_shim.UL_DIR, "results", "NN_controller_N_10_0.pt"), map_location="cpu"), strict=True)
