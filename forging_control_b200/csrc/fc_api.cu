@@ -138,7 +138,17 @@ template <> struct TmemIO<32> {
   }
 };
 
+#ifdef FC_TC_TRACE
+__device__ long long g_trace[3][32768];
+__device__ int g_trace_n[3];
+#endif
+
 struct DevCtxTC : DevCtx {
+#ifdef FC_TC_TRACE
+  static constexpr int kTraceMax = 32768;
+  static __device__ __forceinline__ void trace_put(int slot, int i, long long v) { g_trace[slot][i] = v; }
+  static __device__ __forceinline__ void trace_count(int slot, int n) { g_trace_n[slot] = n; }
+#endif
   static __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
   // one instruction for a contiguous, 16-byte aligned region (bytes a multiple of 16)
   static __device__ __forceinline__ void prefetch_l2_bulk(const float* p, unsigned bytes) {
@@ -1075,4 +1085,13 @@ int fc_fnn_backward(const float* X, const float* du, const float* inp_w, const f
   return FC_OK;
 }
 
+#ifdef FC_TC_TRACE
+// development aid: copies the event trace of the last pair-kernel launch (3 x 32768 events, counts in n[3])
+int fc_debug_trace(long long* events, int* n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(events, fc::g_trace, sizeof(long long) * 3 * 32768);
+  cudaMemcpyFromSymbol(n, fc::g_trace_n, sizeof(int) * 3);
+  return 0;
+}
+#endif
 }  // extern "C"

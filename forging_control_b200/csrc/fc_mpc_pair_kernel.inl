@@ -41,7 +41,18 @@ struct MpcPair {
   // keeping both in registers was measured 12 % slower: spills)
   float c[kMaxOwn];
   unsigned phF0, phF1, phR0, phR1, phW;
-#ifdef FC_TC_TIMING
+#if defined(FC_TC_TRACE)
+#ifndef FC_TRACE_W1
+#define FC_TRACE_W1 5
+#define FC_TRACE_W2 13
+#endif
+  // event trace (development aid, -DFC_TC_TRACE): lane 0 of warps 0 (issuer), 5 (third 0) and 13 (third 2) of CTA 0 log
+  // (clock << 8 | event) at every lap point; read back with fc_debug_trace
+  int trace_slot, trace_n;
+  FC_HD_CTX void lap(int k) {
+    if (trace_slot >= 0 && trace_n < Ctx::kTraceMax) Ctx::trace_put(trace_slot, trace_n++, (Ctx::clock() << 8) | (long long)k);
+  }
+#elif defined(FC_TC_TIMING)
   long long tm[24], tlast;  // cycle breakdown (development aid, -DFC_TC_TIMING): threads 0 and 160 of CTA 0 report
   FC_HD_CTX void lap(int k) { long long t = Ctx::clock(); tm[k] += t - tlast; tlast = t; }
 #else
@@ -66,6 +77,10 @@ struct MpcPair {
     wbase = p.work + (size_t)ctx.bid() * p.work_stride;
     phF0 = phF1 = phR0 = phR1 = phW = 0;
     ntl = 0; tile0 = 0;
+#ifdef FC_TC_TRACE
+    trace_n = 0;
+    trace_slot = (ctx.bid() == 0 && lane == 0) ? (warp == 0 ? 0 : warp == FC_TRACE_W1 ? 1 : warp == FC_TRACE_W2 ? 2 : -1) : -1;
+#endif
 #ifdef FC_TC_TIMING
     for (int i = 0; i < 24; ++i) tm[i] = 0;
     tlast = 0;
@@ -85,7 +100,6 @@ struct MpcPair {
   // ---------------------------------------------------------------------------------------------
   static constexpr float kExpMax = 30.0f;
   static constexpr float kLog2e = 1.4426950216293335f;            // fp32(log2 e)
-  static constexpr float kLog2eLo = 1.92596e-8f;                  // log2 e - fp32(log2 e)
 #ifdef FC_ABL_NO_MUFU         // timing ablation only: no MUFU.EX2 / MUFU.RCP
   FC_HD_CTX static float denom_(float e2arg) { return 1.f + fminf(e2arg, kExpMax) * fminf(e2arg, kExpMax); }
 #else
@@ -97,16 +111,12 @@ struct MpcPair {
     const float rab = r * cd, rcd = r * ab;
     ra = rab * b; rb = rab * a; rc = rcd * d; rd = rcd * c;
   }
-  FC_HD_CTX static float tanh_from_(float x, float rd) {
-    // below |x| = 0.2: odd Taylor polynomial up to x^7 (next term 62/2835 x^9: relative 6e-8 at 0.2); above: 1 - 2 rd
-    // (absolute error ~1e-7, i.e. <= 6e-7 relative from 0.2 on)
-    const float big = fmaf(-2.f, rd, 1.f);
-    const float x2 = x * x;
-    float pl = fmaf(x2, -0.053968253968253971f, 0.13333333333333333f);
-    pl = fmaf(x2, pl, -0.33333333333333331f);
-    pl = fmaf(x2 * x, pl, x);
-    return fabsf(x) < 0.2f ? pl : big;
-  }
+  // tanh(x) = 1 - 2 rd with rd = 1/(1 + e^{2x}): absolute error ~1e-7.  The gate pre-activations and cell states it is
+  // applied to carry an absolute error of that size already (fp16 hi/lo product, fp32 cell recurrence), so the odd
+  // polynomial rounds 1 and 2 used below |x| = 0.2 for RELATIVE accuracy bought nothing measurable: summed gradients
+  // 2e-7..5e-7 of the fp64 oracle without it against 1.4e-7..2.6e-7 with it (profiles/r02b_activation_variants.md),
+  // for 12 of 62 instructions per cell unit
+  FC_HD_CTX static float tanh_from_(float, float rd) { return fmaf(-2.f, rd, 1.f); }
   template <int NU>
   FC_HD_CTX static void tanh_batch(const float* x, float* y) {
     float d[NU], r[NU];
@@ -124,12 +134,14 @@ struct MpcPair {
 #pragma unroll
     for (int i = 0; i < NU; ++i) y[i] = tanh_from_(x[i], r[i]);
   }
-  struct ActK { float khi, klo, us, corr; };
+  // unscale, the accumulator compensation (1 + corr) and -log2(e) folded into ONE multiplier of the raw accumulator
+  // value (rounded once: 6e-8 relative on the exponent argument, i.e. <= 2e-8 on a sigmoid)
+  struct ActK { float k1, k2; };
   FC_HD_CTX static ActK make_actk(float unscale, float corr) {
     ActK k;
-    k.khi = -kLog2e * unscale;                              // exact: unscale is a power of two
-    k.klo = fmaf(k.khi, corr, -kLog2eLo * unscale);
-    k.us = unscale; k.corr = corr;
+    const float khi = -kLog2e * unscale;                    // exact: unscale is a power of two
+    k.k1 = fmaf(khi, corr, khi);                            // sigmoid gates: exponent argument = raw * k1
+    k.k2 = -2.f * k.k1;                                     // tanh gate: 2 log2(e) x
     return k;
   }
 
@@ -334,16 +346,13 @@ struct MpcPair {
     float cn[NU], tch[NU];
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-      const float xi = g[i * 4 + 0], xf = g[i * 4 + 1], xo = g[i * 4 + 3];
-      float xg = g[i * 4 + 2] * ak.us;
-      xg = fmaf(xg, ak.corr, xg);
-      const float di = denom_(fmaf(xi, ak.khi, xi * ak.klo));
-      const float df = denom_(fmaf(xf, ak.khi, xf * ak.klo));
-      const float dq = denom_(fmaf(xo, ak.khi, xo * ak.klo));
-      const float dg = denom_(2.f * kLog2e * xg);
+      const float di = denom_(g[i * 4 + 0] * ak.k1);
+      const float df = denom_(g[i * 4 + 1] * ak.k1);
+      const float dq = denom_(g[i * 4 + 3] * ak.k1);
+      const float dg = denom_(g[i * 4 + 2] * ak.k2);
       float gi, gf, go, rg;
       quad_rcp(di, df, dq, dg, gi, gf, go, rg);
-      const float gg = tanh_from_(xg, rg);
+      const float gg = tanh_from_(0.f, rg);
       const float cp = first ? 0.f : c[j0 + i];
       cn[i] = fmaf(gf, cp, gi * gg);
       c[j0 + i] = cn[i];
@@ -1055,6 +1064,9 @@ struct MpcPair {
       part[i] = (pgd[i] + pgd[kNumFnnGrad + i]) + (pgd[2 * kNumFnnGrad + i] + pgd[3 * kNumFnnGrad + i]);
     if (tid == 0) part[kNumFnnGrad] = *reinterpret_cast<const double*>(sm + kSmRedP);
     ctx.sync();
+#ifdef FC_TC_TRACE
+    if (trace_slot >= 0) Ctx::trace_count(trace_slot, trace_n);
+#endif
 #ifdef FC_TC_TIMING
     if (p.debug_timing && (tid == 0 || tid == 160 || tid == 288 || tid == 416) && ctx.bid() == 0) Ctx::report_pair(tid, tm);
 #endif

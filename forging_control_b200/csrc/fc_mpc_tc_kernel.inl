@@ -68,7 +68,6 @@ struct MpcTileTC {
   // operations).  Every denominator is 1 + 2^e with e clamped to kExpMax, so the product stays below 2^121.
   static constexpr float kExpMax = 30.0f;
   static constexpr float kLog2e = 1.4426950216293335f;            // fp32(log2 e)
-  static constexpr float kLog2eLo = 1.92596e-8f;                  // log2 e - fp32(log2 e)
   FC_HD_CTX static float denom_(float e2arg) { return 1.f + Ctx::ex2(fminf(e2arg, kExpMax)); }
   FC_HD_CTX static void quad_rcp(float a, float b, float c, float d, float& ra, float& rb, float& rc, float& rd) {
     const float ab = a * b, cd = c * d;
@@ -76,17 +75,9 @@ struct MpcTileTC {
     const float rab = r * cd, rcd = r * ab;
     ra = rab * b; rb = rab * a; rc = rcd * d; rd = rcd * c;
   }
-  // tanh(x) from rd = 1/(1 + e^{2x}): 1 - 2 rd has an ABSOLUTE error of ~1e-7 (cancellation against 1), which is
-  // a large relative error for the small gate / cell values that dominate here; below |x| = 0.3 use the odd
-  // Taylor polynomial (relative error < 6e-8) instead.  Branch-free select.
-  FC_HD_CTX static float tanh_from_(float x, float rd) {
-    const float big = fmaf(-2.f, rd, 1.f);
-    const float x2 = x * x;
-    float pl = fmaf(x2, -0.053968253968253971f, 0.13333333333333333f);
-    pl = fmaf(x2, pl, -0.33333333333333331f);
-    pl = fmaf(x2 * x, pl, x);
-    return fabsf(x) < 0.2f ? pl : big;
-  }
+  // tanh(x) = 1 - 2 rd with rd = 1/(1 + e^{2x}) (absolute error ~1e-7, the size of the error its argument already
+  // carries; see fc_mpc_pair_kernel.inl)
+  FC_HD_CTX static float tanh_from_(float, float rd) { return fmaf(-2.f, rd, 1.f); }
   // tanh of NU values with one reciprocal per four
   template <int NU>
   FC_HD_CTX static void tanh_batch(const float* x, float* y) {
@@ -174,12 +165,12 @@ struct MpcTileTC {
   // ---------------------------------------------------------------------------------------------
   // g holds RAW accumulator values (pre-activation * kScaleA * kScaleW, before the truncation compensation);
   // ak folds unscale, compensation and -log2(e) into the exponent argument of the three sigmoid gates
-  struct ActK { float khi, klo, us, corr; };
+  struct ActK { float k1, k2; };
   FC_HD_CTX static ActK make_actk(float unscale, float corr) {
     ActK k;
-    k.khi = -kLog2e * unscale;                              // exact: unscale is a power of two
-    k.klo = fmaf(k.khi, corr, -kLog2eLo * unscale);
-    k.us = unscale; k.corr = corr;
+    const float khi = -kLog2e * unscale;                    // exact: unscale is a power of two
+    k.k1 = fmaf(khi, corr, khi);                            // one multiplier per gate (see fc_mpc_pair_kernel.inl)
+    k.k2 = -2.f * k.k1;
     return k;
   }
   template <int NU>
@@ -188,16 +179,13 @@ struct MpcTileTC {
     float cn[NU], th[NU];
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-      const float xi = g[i * 4 + 0], xf = g[i * 4 + 1], xo = g[i * 4 + 3];
-      float xg = g[i * 4 + 2] * ak.us;
-      xg = fmaf(xg, ak.corr, xg);
-      const float di = denom_(fmaf(xi, ak.khi, xi * ak.klo));
-      const float df = denom_(fmaf(xf, ak.khi, xf * ak.klo));
-      const float dq = denom_(fmaf(xo, ak.khi, xo * ak.klo));
-      const float dg = denom_(2.f * kLog2e * xg);
+      const float di = denom_(g[i * 4 + 0] * ak.k1);
+      const float df = denom_(g[i * 4 + 1] * ak.k1);
+      const float dq = denom_(g[i * 4 + 3] * ak.k1);
+      const float dg = denom_(g[i * 4 + 2] * ak.k2);
       float gi, gf, go, rg;
       quad_rcp(di, df, dq, dg, gi, gf, go, rg);
-      const float gg = tanh_from_(xg, rg);
+      const float gg = tanh_from_(0.f, rg);
       const float cp = first ? 0.f : c[j0 + i];
       cn[i] = fmaf(gf, cp, gi * gg);
       c[j0 + i] = cn[i];
