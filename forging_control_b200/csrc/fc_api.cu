@@ -54,6 +54,10 @@ struct DevCtx {
     unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
   }
+  static __device__ __forceinline__ void cp_async8(float* dst, const float* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  }
   static __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
@@ -341,6 +345,14 @@ __global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_pair_kernel(const M
   k.run();
 }
 
+// replica mode of the same source: one 32-trajectory tile per CTA, the 50 hidden units of a trajectory split over
+// twelve threads (small / mid-size batches, fc_mpc_pair_kernel.inl)
+__global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_replica_kernel(const MpcParams p) {
+  DevCtxTC ctx;
+  pr::MpcPair<DevCtxTC, 4> k(ctx, p);
+  k.run();
+}
+
 // pair-kernel operand images behind the two others in the packed buffer
 __global__ void pack_weights_pair_kernel(RawWeights w, float* out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // half index
@@ -494,7 +506,8 @@ static int ensure_smem_attributes();
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel.
+// kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel,
+// 4 = replica mode of the pair kernel (32-trajectory tiles).
 // Thread-local: fc_mpc_select_kernel affects the calling thread's subsequent fc_mpc_loss* / workspace queries only
 // (no process-global state; the library stays re-entrant across threads and devices).
 static thread_local int g_mpc_mode = -1;
@@ -505,41 +518,45 @@ static int mpc_mode() {
     if (e && !strcmp(e, "ffma")) g_mpc_mode = 1;
     if (e && !strcmp(e, "tc")) g_mpc_mode = 2;
     if (e && !strcmp(e, "pair")) g_mpc_mode = 3;
+    if (e && !strcmp(e, "replica")) g_mpc_mode = 4;
   }
   return g_mpc_mode;
 }
 
 struct MpcPlan {
-  int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair
+  int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair, 3 = replica mode of the pair kernel
   int grid, tiles;
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
-// Automatic choice (measured on B200, profiles/r01_bench_configs_three_kernels.jsonl): while every 128-trajectory tile
-// can have an SM of its own (128 < B <= 128 * #SMs) the one-tile tcgen05 kernel is fastest (B=4096: 0.96 ms against
-// 1.54 ms for the pair kernel, which would leave SMs idle); beyond that the pair kernel, which keeps two tiles per CTA
-// in flight, wins (B=524288: 84 M against 74 M trajectory-steps/s; the FFMA kernel reaches 23 M), and for a single tile
-// too (B=15: 2.11 ms, one-tile kernel 2.23 ms, FFMA kernel 7.6 ms).  All three stay selectable
-// (fc_mpc_select_kernel / FC_MPC_KERNEL).
+// Automatic choice (measured on B200, profiles/r02b_midbatch.jsonl, profiles/r01_bench_configs_three_kernels.jsonl):
+//   B <= 32 * #SMs   replica mode of the pair kernel: 32-trajectory tiles, one per SM, the hidden units of a trajectory
+//                    split over twelve threads (B = 15: 1.33 ms against 1.97 ms, N = 5 / B = 4096: 0.61 ms against 0.90 ms)
+//   .. <= 128 * #SMs the one-tile tcgen05 kernel: every 128-trajectory tile has an SM of its own
+//   beyond           the pair kernel, which keeps two tiles per CTA in flight (B = 524288: 89 M against 77 M
+//                    trajectory-steps/s; the FFMA kernel reaches 22 M).
+// All four stay selectable (fc_mpc_select_kernel / FC_MPC_KERNEL).
 static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
-  pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : 1);
+  pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : (mode == 4 ? 3 : 1));
   {
     const int t128 = (B + tc::kTileTC - 1) / tc::kTileTC;
     // more tiles than SMs: two tiles per CTA overlap tensor and cell-update work; a single tile: the two-tile kernels'
     // dedicated issuer warp alone is worth 5 % (B=15: 2.11 ms against 2.23 ms)
     if (mode == 0 && (t128 > sms || t128 == 1)) pl->kind = 2;
+    if (mode == 0 && B <= (pr::kTileP / 4) * sms) pl->kind = 3;
   }
   if (width_dim > 1) pl->kind = 1;        // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
-  const int tile = pl->kind ? tc::kTileTC : kTile;
+  const int tile = pl->kind == 3 ? pr::kTileP / 4 : (pl->kind ? tc::kTileTC : kTile);
   pl->tiles = (B + tile - 1) / tile;
   const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
   pl->grid = units < sms ? units : sms;
   pl->work_stride = pl->kind == 2 ? pr::kTiles * pr::work_layout_p(N, with_grad).total
-                                  : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad, width_dim).total : work_layout(N, with_grad).total);
+                    : pl->kind == 3 ? pr::work_layout_p(N, with_grad).total
+                    : (pl->kind == 1 ? tc::work_layout_tc(N, with_grad, width_dim).total : work_layout(N, with_grad).total);
   pl->bytes = (size_t)pl->grid * kPartialStride * sizeof(double) + (size_t)pl->grid * pl->work_stride * sizeof(float);
   if (width_dim > 1) pl->bytes += (size_t)pl->grid * kWidePartialStride * sizeof(double);
   return FC_OK;
@@ -596,6 +613,8 @@ static int ensure_smem_attributes() {
           "cudaFuncSetAttribute(smem, tc)");
   FC_CUDA(cudaFuncSetAttribute(mpc_loss_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
           "cudaFuncSetAttribute(smem, pair)");
+  FC_CUDA(cudaFuncSetAttribute(mpc_loss_replica_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
+          "cudaFuncSetAttribute(smem, replica)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd),
           "cudaFuncSetAttribute(smem, lstm fwd)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd80),
@@ -637,8 +656,8 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
 }
 
 int fc_mpc_select_kernel(int mode) {
-  if (mode < 0 || mode > 3)
-    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05) or 3 (tcgen05 pair)");
+  if (mode < 0 || mode > 4)
+    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05), 3 (tcgen05 pair) or 4 (replica)");
   g_mpc_mode = mode;
   return FC_OK;
 }
@@ -665,6 +684,12 @@ size_t fc_mpc_loss_scratch_traffic_bytes(int B, int N) {
     per_tile = (size_t)rec_base(N) * pr::kRecFloatsP * 2                                  // records: write + read
                + (size_t)N * (kLayers - 1) * kLook * pr::kSlot * 2                        // operand-format hidden sequence
                + (size_t)kept * (kLayers - 1) * (pr::kUpdWarps * pr::kMaxOwn * 32) * 2;    // d-sequence
+  } else if (pl.kind == 3) {
+    // 32-trajectory tiles: eleven threads of a trajectory write 5 record float4 per step, the last one 8; one hidden-sequence
+    // float4 per thread (+2); d-sequence 4 (6) floats
+    per_tile = (size_t)rec_base(N) * (11 * 5 + 8) * 32 * 4 * 2
+               + (size_t)N * (kLayers - 1) * kLook * (12 + 2) * 32 * 4 * 2
+               + (size_t)kept * (kLayers - 1) * (11 * 4 + 6) * 32 * 2;
   } else if (pl.kind == 1) {
     per_tile = (size_t)rec_base(N) * tc::kRecFloatsTC * 2;
   } else {
@@ -733,7 +758,7 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   MpcParams p;
   memset(&p, 0, sizeof(p));
   p.X = X; p.u0 = u0; p.Z = Z;
-  p.wpack = pl.kind == 2 ? wpack + kPackFloats + tc::kPackFloatsTC : (pl.kind == 1 ? wpack + kPackFloats : wpack);
+  p.wpack = pl.kind >= 2 ? wpack + kPackFloats + tc::kPackFloatsTC : (pl.kind == 1 ? wpack + kPackFloats : wpack);
   p.cost = cost; p.command = command; p.error = error; p.pred = pred; p.du0 = du0;
   p.partial = reinterpret_cast<double*>(workspace);
   p.width_dim = width_dim; p.int_w = int_w; p.int_b = int_b;
@@ -756,7 +781,8 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   p.debug_timing = getenv("FC_TC_TIMING") ? 1 : 0;
   p.noise_std = noise_std; p.noise_seed = noise_seed;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+  if (pl.kind == 3) mpc_loss_replica_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+  else if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
   else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, width_dim > 1 ? tc::kSmBytesWide : tc::kSmBytesTC, st>>>(p);
   else mpc_loss_kernel<<<pl.grid, kThreads, kSmBytes, st>>>(p);
   FC_CUDA(cudaGetLastError(), "mpc_loss kernel launch");
@@ -769,12 +795,26 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   return FC_OK;
 }
 
+// shadow roll-out: 32-trajectory tiles (replica mode) while every tile can have an SM of its own, else tile pairs
+static void shadow_plan(int B, int sms, bool* replica, int* tiles, int* grid) {
+  const int mode = mpc_mode();
+  *replica = mode == 4 || (mode != 3 && B <= (pr::kTileP / 4) * sms);
+  if (*replica) {
+    *tiles = (B + pr::kTileP / 4 - 1) / (pr::kTileP / 4);
+    *grid = *tiles < sms ? *tiles : sms;
+  } else {
+    *tiles = (B + pr::kTileP - 1) / pr::kTileP;
+    const int pairs = (*tiles + pr::kTiles - 1) / pr::kTiles;
+    *grid = pairs < sms ? pairs : sms;
+  }
+}
+
 size_t fc_lstm_shadow_workspace_bytes(int B, int T) {
   if (B <= 0 || T <= 0) return 0;
   int sms = 0;
   if (sm_count(&sms)) return 0;
-  const int tiles = (B + pr::kTileP - 1) / pr::kTileP, pairs = (tiles + pr::kTiles - 1) / pr::kTiles;
-  const int grid = pairs < sms ? pairs : sms;
+  bool replica; int tiles, grid;
+  shadow_plan(B, sms, &replica, &tiles, &grid);
   return (size_t)grid * kPartialStride * sizeof(double) + (size_t)grid * pr::kTiles * pr::work_layout_p(T, 0).total * sizeof(float);
 }
 
@@ -795,8 +835,8 @@ int fc_lstm_shadow_rollout(const float* row0, const float* u, const float* ratio
   if (rc) return rc;
   rc = ensure_smem_attributes();
   if (rc) return rc;
-  const int tiles = (B + pr::kTileP - 1) / pr::kTileP, pairs = (tiles + pr::kTiles - 1) / pr::kTiles;
-  const int grid = pairs < sms ? pairs : sms;
+  bool replica; int tiles, grid;
+  shadow_plan(B, sms, &replica, &tiles, &grid);
   MpcParams p;
   memset(&p, 0, sizeof(p));
   p.wpack = wpack + kPackFloats + tc::kPackFloatsTC;
@@ -809,7 +849,8 @@ int fc_lstm_shadow_rollout(const float* row0, const float* u, const float* ratio
   p.shadow = 1; p.sh_row0 = row0; p.sh_u = u; p.sh_y = y;
   // ratio is a HOST array of 4 floats
   for (int q = 0; q < 4; ++q) p.sh_ratio[q] = ratio[q];
-  mpc_loss_pair_kernel<<<grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
+  if (replica) mpc_loss_replica_kernel<<<grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
+  else mpc_loss_pair_kernel<<<grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
   FC_CUDA(cudaGetLastError(), "mpc_loss_pair_kernel (shadow) launch");
   return FC_OK;
 }

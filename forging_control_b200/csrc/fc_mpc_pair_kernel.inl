@@ -22,12 +22,22 @@
 namespace fc {
 namespace pr {
 
-template <class Ctx>
+// R = 1: two 128-trajectory tiles per CTA (the schedule described above).
+// R = 4 ("replica" mode, small and mid-size batches): ONE tile of 32 trajectories per CTA, replicated into the four
+// 32-row groups of the M = 128 operand images, so that every TMEM quadrant holds the gate pre-activations of the same 32
+// trajectories and the twelve cell-update warps split the 50 hidden units of a trajectory twelve ways (4 units per thread,
+// 6 for the last one) instead of three ways: the dependent chain of a step shrinks from ~5 000 to ~1 200 cycles, which is
+// what a latency-bound batch (B = 15 .. 4 736) needs.  Both operands come from shared memory in both directions (SS-mode
+// MMA); the per-trajectory scalar work runs on warp 1; read-out partial sums are exchanged through shared memory.
+template <class Ctx, int R = 1>
 struct MpcPair {
+  static_assert(R == 1 || R == 4, "replica factor");
+  static constexpr int kRowsT = kTileP / R;          // distinct trajectories per tile
+  static constexpr int kOwn = R == 1 ? kMaxOwn : 6;  // register slots for the units a thread owns
   Ctx& ctx;
   const MpcParams& p;
   float* sm;
-  int tid, warp, lane, row, th, nown, u_first, uw;
+  int tid, warp, lane, row, traj, quad, th, nown, u_first, uw;
   bool service;          // warps 0..3: thread 0 issues the MMAs, the rest only joins the CTA-wide barriers
   bool owner;            // third 0 of the cell-update warps: also collects the row-feature gradients of its row
   bool scalar;           // does the per-trajectory scalar work of its row: warps 1..3, and warp 4 for the rows of warp 0
@@ -39,7 +49,7 @@ struct MpcPair {
   // forward: cell state, backward: d(cell state) of the tile of the CURRENT item; the state of the other tile is
   // parked in spare TMEM columns of the own lane and exchanged at the start of every item (items alternate strictly;
   // keeping both in registers was measured 12 % slower: spills)
-  float c[kMaxOwn];
+  float c[kOwn];
   unsigned phF0, phF1, phR0, phR1, phW;
 #if defined(FC_TC_TRACE)
 #ifndef FC_TRACE_W1
@@ -65,13 +75,24 @@ struct MpcPair {
     warp = tid >> 5;
     lane = tid & 31;
     row = 32 * (warp & 3) + lane;
+    quad = warp & 3;
+    traj = R == 1 ? row : lane;
     service = warp < 4;
     th = service ? 0 : (warp >> 2) - 1;
-    nown = units_of(th);
-    u_first = first_unit(th);
-    last = th == 2;
-    owner = !service && th == 0;
-    scalar = (service && warp != 0) || warp == 4;
+    if (R == 1) {
+      nown = units_of(th);
+      u_first = first_unit(th);
+      last = th == 2;
+      owner = !service && th == 0;
+      scalar = (service && warp != 0) || warp == 4;
+    } else {
+      // units [16 th + 4 quad, + 4); the last thread of a trajectory also takes units 48, 49 (44..49)
+      u_first = 16 * th + 4 * quad;
+      last = !service && th == 2 && quad == 3;
+      nown = last ? 6 : 4;
+      owner = !service && th == 0 && quad == 0;
+      scalar = warp == 1;
+    }
     uw = service ? 0 : warp - 4;                             // index among the cell-update warps
     tstride = work_layout_p(p.N, p.with_grad).total;
     wbase = p.work + (size_t)ctx.bid() * p.work_stride;
@@ -149,7 +170,7 @@ struct MpcPair {
   // hand-shakes
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void wait_full(int X) {
-    if (service && warp != 0) ctx.bar_wait_relaxed(kBarFull + X, X ? phF1 : phF0);  // warps 1..3: off the critical path
+    if (R == 1 && service && warp != 0) ctx.bar_wait_relaxed(kBarFull + X, X ? phF1 : phF0);  // warps 1..3: off the critical path
     else ctx.bar_wait(kBarFull + X, X ? phF1 : phF0);
     if (X) phF1 += 1; else phF0 += 1;
   }
@@ -157,7 +178,7 @@ struct MpcPair {
 #ifdef FC_ABL_NO_SWAP        // timing ablation only
     return;
 #endif
-    if (ntl > 1) {
+    if constexpr (R == 1) if (ntl > 1) {
       float o[kMaxOwn];
       const int col = kColPark + kMaxOwn * th;
       ctx.template tmem_ld_nowait<16>(col, o);
@@ -192,6 +213,38 @@ struct MpcPair {
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX float* op_ptr(int halves_off, int k) const {       // k multiple of 2
     return sm + kSmOpP + ((halves_off + (k >> 3) * (kTileP * 8) + row * 8 + (k & 7)) >> 1);
+  }
+  // R == 4: copy g (0..3) of this lane's trajectory, i.e. image row 32 g + lane
+  FC_HD_CTX float* op_ptr_rep(int halves_off, int k, int g) const {
+    return sm + kSmOpP + ((halves_off + (k >> 3) * (kTileP * 8) + (32 * g + lane) * 8 + (k & 7)) >> 1);
+  }
+  // R == 4: fp16 hi/lo words of the 4 (6) owned units: w = {hi01, hi23, lo01, lo23, hi45, lo45}
+  FC_HD_CTX void split_units_r(const float* v, float scale, float* w) const {
+    Ctx::split_h2(v[0] * scale, v[1] * scale, w[0], w[2]);
+    Ctx::split_h2(v[2] * scale, v[3] * scale, w[1], w[3]);
+    if (last) Ctx::split_h2(v[kOwn - 2] * scale, v[kOwn - 1] * scale, w[4], w[5]);
+    else { w[4] = 0.f; w[5] = 0.f; }
+  }
+  // ... into halves [kbase + u_first, ...) of the hi and lo images, all four copies: 8 bytes (half a piece) per image,
+  // the last thread also the whole piece of units 48..55 (48, 49 and the zero padding)
+  FC_HD_CTX void st_pieces_r(int img_hi, int img_lo, int kbase, const float* w) {
+    const int k0 = kbase + u_first;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      Ctx::sts2(op_ptr_rep(img_hi, k0, g), w[0], w[1]);
+      Ctx::sts2(op_ptr_rep(img_lo, k0, g), w[2], w[3]);
+      if (last) {
+        Ctx::sts4(op_ptr_rep(img_hi, k0 + 4, g), F4{w[4], 0.f, 0.f, 0.f});
+        Ctx::sts4(op_ptr_rep(img_lo, k0 + 4, g), F4{w[5], 0.f, 0.f, 0.f});
+      }
+    }
+  }
+  // ... and into the thread-private slots of the hidden-sequence scratch: slot 0 = {hi01, hi23, lo01, lo23}, the last
+  // thread: slot 1 = {hi45, 0, 0, 0}, slot 2 = {lo45, 0, 0, 0}
+  FC_HD_CTX void stg_pieces_r(int X, int t, const float* w) {
+    float* sq = seq_ptr(X, t);
+    Ctx::stg4(sq, F4{w[0], w[1], w[2], w[3]});
+    if (last) { Ctx::stg4(sq + 128, F4{w[4], 0.f, 0.f, 0.f}); Ctx::stg4(sq + 256, F4{w[5], 0.f, 0.f, 0.f}); }
   }
   // the owned units' values v[0..nown) (scaled here) as fp16 hi/lo pieces of 8 halves (third 2: the third piece
   // holds units 48,49 and the zero padding up to slot 56)
@@ -229,6 +282,19 @@ struct MpcPair {
   FC_HD_CTX void copy_input(int X, int t) {
     const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
     const float* sq = seq_ptr(X, t);
+    if constexpr (R == 4) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        Ctx::cp_async8(op_ptr_rep(img_hi, u_first, g), sq);
+        Ctx::cp_async8(op_ptr_rep(img_lo, u_first, g), sq + 2);
+        if (last) {
+          Ctx::cp_async16(op_ptr_rep(img_hi, u_first + 4, g), sq + 128);
+          Ctx::cp_async16(op_ptr_rep(img_lo, u_first + 4, g), sq + 256);
+        }
+      }
+      Ctx::cp_commit();
+      return;
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
       if (ch < 2 || last) {
@@ -240,6 +306,11 @@ struct MpcPair {
   FC_HD_CTX void st_units_zero(int img_hi, int img_lo, int kbase) {
     const int k0 = kbase + u_first;
     const F4 z = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (R == 4) {
+      const float w[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st_pieces_r(img_hi, img_lo, kbase, w);
+      return;
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
       if (ch < 2 || last) { Ctx::sts4(op_ptr(img_hi, k0 + ch * 8), z); Ctx::sts4(op_ptr(img_lo, k0 + ch * 8), z); }
@@ -266,8 +337,16 @@ struct MpcPair {
       for (int i = 0; i < 4; ++i) {
         Ctx::split_h2(v[ch * 8 + 2 * i], v[ch * 8 + 2 * i + 1], hi[i], lo[i]);
       }
-      Ctx::sts4(op_ptr(0, k0 + ch * 8), F4{hi[0], hi[1], hi[2], hi[3]});
-      Ctx::sts4(op_ptr(kOpGLoHalves, k0 + ch * 8), F4{lo[0], lo[1], lo[2], lo[3]});
+      if constexpr (R == 1) {
+        Ctx::sts4(op_ptr(0, k0 + ch * 8), F4{hi[0], hi[1], hi[2], hi[3]});
+        Ctx::sts4(op_ptr(kOpGLoHalves, k0 + ch * 8), F4{lo[0], lo[1], lo[2], lo[3]});
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          Ctx::sts4(op_ptr_rep(0, k0 + ch * 8, g), F4{hi[0], hi[1], hi[2], hi[3]});
+          Ctx::sts4(op_ptr_rep(kOpGLoHalves, k0 + ch * 8, g), F4{lo[0], lo[1], lo[2], lo[3]});
+        }
+      }
     }
   }
 
@@ -294,7 +373,7 @@ struct MpcPair {
     const float* b_hi = sm + kSmWP;
     const float* b_lo = b_hi + bwd_img_halves(l) / 2;
     const int d = col_d_bwd(X);
-    if (X == 0) {
+    if (R == 1 && X == 0) {
 #ifdef FC_ABL_ONE_TERM
       ctx.mma(d, nb, kColGhi, b_hi, nb, 0, kKB / 16, false);
 #else
@@ -320,9 +399,10 @@ struct MpcPair {
   // tile set-up (scalar-work thread of each trajectory)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void load_tile(int X) {
-    const int b = (tile0 + X) * kTileP + row;
+    const int b = (tile0 + X) * kRowsT + traj;
     const bool ok = b < p.B;
     float* rows = w_rows(X);
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     for (int r = 0; r < kLook; ++r)
 #pragma unroll
       for (int f = 0; f < kFeat; ++f) {
@@ -377,6 +457,15 @@ struct MpcPair {
     const ActK ak = make_actk(1.0f / (kScaleA * kScaleW), corr);
     float* rp = rec_out ? rec_out + ((size_t)uw * kRecF4 * 32 + lane) * 4 : nullptr;
     const int col0 = col_d_fwd(X) + 4 * u_first;
+    if constexpr (R == 4) {
+      float g4[24];
+      ctx.template tmem_ld_nowait<16>(col0, g4);
+      if (last) ctx.template tmem_ld_nowait<8>(col0 + 16, g4 + 16);
+      ctx.tmem_ld_wait();
+      fwd_units<4>(0, g4, ak, first, h, rp, 0);
+      if (last) fwd_units<2>(4, g4 + 16, ak, first, h, rp, 5);   // units 48, 49: record float4 5..7
+      return;
+    }
     float g[2][16];
     ctx.template tmem_ld_nowait<16>(col0, g[0]);
 #pragma unroll
@@ -395,7 +484,7 @@ struct MpcPair {
 
   // layer 0: the 5 row features of step t (scalar-work thread of the row): k = 0..7, 3 zero
   FC_HD_CTX void load_features(int X, int m, int t, float* xin) {
-    const float* rp = w_rows(X) + (size_t)(m + t) * kFeat * kTileP + row;
+    const float* rp = w_rows(X) + (size_t)(m + t) * kFeat * kTileP + traj;
 #pragma unroll
     for (int f = 0; f < kFeat; ++f) xin[f] = Ctx::ldcg(rp + f * kTileP);
   }
@@ -405,8 +494,16 @@ struct MpcPair {
     Ctx::split_h2(xin[0] * kScaleA, xin[1] * kScaleA, hi[0], lo[0]);
     Ctx::split_h2(xin[2] * kScaleA, xin[3] * kScaleA, hi[1], lo[1]);
     Ctx::split_h2(xin[4] * kScaleA, 0.f, hi[2], lo[2]);
-    Ctx::sts4(op_ptr(img_hi, 0), F4{hi[0], hi[1], hi[2], 0.f});
-    Ctx::sts4(op_ptr(img_lo, 0), F4{lo[0], lo[1], lo[2], 0.f});
+    if constexpr (R == 1) {
+      Ctx::sts4(op_ptr(img_hi, 0), F4{hi[0], hi[1], hi[2], 0.f});
+      Ctx::sts4(op_ptr(img_lo, 0), F4{lo[0], lo[1], lo[2], 0.f});
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        Ctx::sts4(op_ptr_rep(img_hi, 0, g), F4{hi[0], hi[1], hi[2], 0.f});
+        Ctx::sts4(op_ptr_rep(img_lo, 0, g), F4{lo[0], lo[1], lo[2], 0.f});
+      }
+    }
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -477,7 +574,7 @@ struct MpcPair {
 
   FC_HD_CTX void fwd_item(int X, int l, int m, int t) {
     const int tmin = t_min_of(m);
-    float h[kMaxOwn], xin[kFeat];
+    float h[kOwn], xin[kFeat];
     lap(16);
     swap_cells();
     lap(11);
@@ -498,12 +595,21 @@ struct MpcPair {
     if (l > 0 && t + 1 < kLook) copy_input(X, t + 1);        // input block of step t+1: lands during the cell update
     if (l == 0 && scalar && t + 1 < kLook) store_features(X, xin);
     fwd_pointwise(X, t == 0, corr, h, rec_out);
+    lap(24);
     if (l + 1 < kLayers || t + 1 < kLook) {
-      F4 hi4[3], lo4[3];
-      split_units(h, kScaleA, hi4, lo4);
-      if (l + 1 < kLayers) stg_pieces(X, t, hi4, lo4);       // input of the layer above, already in operand format
-      if (t + 1 < kLook) st_pieces(img_hi, img_lo, l == 0 ? kRec0 : kRec, hi4, lo4);
+      if constexpr (R == 1) {
+        F4 hi4[3], lo4[3];
+        split_units(h, kScaleA, hi4, lo4);
+        if (l + 1 < kLayers) stg_pieces(X, t, hi4, lo4);     // input of the layer above, already in operand format
+        if (t + 1 < kLook) st_pieces(img_hi, img_lo, l == 0 ? kRec0 : kRec, hi4, lo4);
+      } else {
+        float w[6];
+        split_units_r(h, kScaleA, w);
+        if (l + 1 < kLayers) stg_pieces_r(X, t, w);
+        if (t + 1 < kLook) st_pieces_r(img_hi, img_lo, l == 0 ? kRec0 : kRec, w);
+      }
     }
+    lap(25);
     if (t + 1 < kLook) {
       if (l > 0) Ctx::template cp_wait<0>();
       lap(2);
@@ -515,13 +621,19 @@ struct MpcPair {
       const float* fw = sm + kSmSmallP;
       float xq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < kMaxOwn; ++j)
+      for (int j = 0; j < kOwn; ++j)
         if (j < nown) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) xq[q] = fmaf(fw[q * kHid + u_first + j], h[j], xq[q]);
         }
-      ctx.template tmem_st<4>(kColFcp + 12 * X + 4 * th, xq);
-      ctx.tmem_st_wait();
+      if constexpr (R == 1) {
+        ctx.template tmem_st<4>(kColFcp + 12 * X + 4 * th, xq);
+        ctx.tmem_st_wait();
+      } else {
+        // twelve partial sums per trajectory, exchanged through the free tail of the operand region
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sm[kSmExP + (uw * 4 + q) * 32 + lane] = xq[q];
+      }
     }
     if (t + 1 == kLook) lap(13);
   }
@@ -551,7 +663,8 @@ struct MpcPair {
   // window m the surrogate output is logged and [output * scale_out / scale_in, u_{m+1}] becomes the newest row
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void load_tile_shadow(int X) {
-    const int b = (tile0 + X) * kTileP + row;
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
+    const int b = (tile0 + X) * kRowsT + traj;
     const bool ok = b < p.B;
     float* rows = w_rows(X);
 #pragma unroll
@@ -560,13 +673,29 @@ struct MpcPair {
       for (int r = 0; r < kLook; ++r) rows[(size_t)(r * kFeat + f) * kTileP + row] = v;
     }
   }
+  // read-out partial sums of the trajectory as three values per output (R == 4: the twelve partial sums of the
+  // exchange buffer folded four at a time, fixed order)
+  FC_HD_CTX void readout_partials(int X, float* fp) {
+    if constexpr (R == 1) {
+      ctx.template tmem_ld_nowait<8>(kColFcp + 12 * X, fp);
+      ctx.template tmem_ld_nowait<4>(kColFcp + 12 * X + 8, fp + 8);
+      ctx.tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* e = sm + kSmExP + ((t3 * 4) * 4 + q) * 32 + lane;
+          fp[t3 * 4 + q] = ((e[0] + e[4 * 32]) + e[8 * 32]) + e[12 * 32];
+        }
+    }
+  }
   FC_HD_CTX void shadow_glue(int X, int m) {
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     const float* sw = sm + kSmSmallP;
     float fp[12];
-    ctx.template tmem_ld_nowait<8>(kColFcp + 12 * X, fp);
-    ctx.template tmem_ld_nowait<4>(kColFcp + 12 * X + 8, fp + 8);
-    ctx.tmem_ld_wait();
-    const int b = (tile0 + X) * kTileP + row;
+    readout_partials(X, fp);
+    const int b = (tile0 + X) * kRowsT + traj;
     const bool ok = b < p.B;
     float* rnew = w_rows(X) + (size_t)(kLook + m) * kFeat * kTileP + row;
 #pragma unroll
@@ -582,17 +711,16 @@ struct MpcPair {
   // after window m (scalar-work thread of each trajectory): read-out, cost terms, next command
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void fwd_glue(int X, int m) {
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     const float* sw = sm + kSmSmallP;
     float fp[12];
-    ctx.template tmem_ld_nowait<8>(kColFcp + 12 * X, fp);
-    ctx.template tmem_ld_nowait<4>(kColFcp + 12 * X + 8, fp + 8);
-    ctx.tmem_ld_wait();
+    readout_partials(X, fp);
     float x[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) x[q] = ((fp[q] + fp[4 + q]) + fp[8 + q]) + sw[(kFCB - kFCW) + q];
     if (p.noise_std > 0.f) {                                                   // enable_noise, :1400-1402 / :1438-1440
       float e[4];
-      philox_normal4(p.noise_seed, (unsigned)((tile0 + X) * kTileP + row), (unsigned)m, e);
+      philox_normal4(p.noise_seed, (unsigned)((tile0 + X) * kRowsT + traj), (unsigned)m, e);
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = fmaf(p.noise_std, e[q], x[q]);
     }
@@ -622,7 +750,7 @@ struct MpcPair {
         v = fmaf(ow[u], fmaxf(pre, 0.f), v);
       }
       unext = fminf(fmaxf(v, -1.f), 1.f);                                      // nn.Hardtanh
-      int b = (tile0 + X) * kTileP + row;
+      int b = (tile0 + X) * kRowsT + traj;
       if (b < p.B) p.pred[(size_t)b * p.N + m + 1] = unext;                    // :1455
     }
     rnew[4 * kTileP] = unext;
@@ -632,6 +760,7 @@ struct MpcPair {
   // before the reverse sweep of window m (scalar-work thread per trajectory, then 200 accumulation threads)
   // ---------------------------------------------------------------------------------------------
   FC_HD_CTX void bwd_glue_tile(int X, int m) {
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     const int k = m + 1;
     const float s = p.grad_scale;
     const bool has_u = k <= p.N - 1;
@@ -639,7 +768,7 @@ struct MpcPair {
     const float* iw = sw + (kINPW - kFCW);
     const float* ib = sw + (kINPB - kFCW);
     const float* ow = sw + (kOUTW - kFCW);
-    const bool valid = (tile0 + X) * kTileP + row < p.B;
+    const bool valid = (tile0 + X) * kRowsT + traj < p.B;
     const float* rows = w_rows(X);
     const float* rx = rows + (size_t)(kLook + m) * kFeat * kTileP + row;
     float x0 = Ctx::ldcg(rx), x1 = Ctx::ldcg(rx + kTileP), x2 = Ctx::ldcg(rx + 2 * kTileP), x3 = Ctx::ldcg(rx + 3 * kTileP);
@@ -700,7 +829,7 @@ struct MpcPair {
       double a_ow = 0.0, a_b = 0.0, a_w0 = 0.0, a_w1 = 0.0, a_w2 = 0.0;   // batch sums cancel heavily: fp64
       const float w0 = iw[u * 3 + 0], w1 = iw[u * 3 + 1], w2 = iw[u * 3 + 2], bb = ib[u], owu = ow[u];
       for (int X = 0; X < ntl; ++X)
-        for (int tr = part * 32; tr < part * 32 + 32; ++tr) {
+        for (int tr = part * 32; tr < part * 32 + 32 && tr < kRowsT; ++tr) {
           float dv = sm[kSmDvP + X * kTileP + tr];
           float x0 = sm[kSmFinP + (X * 2) * kTileP + tr], x3 = sm[kSmFinP + (X * 2 + 1) * kTileP + tr];
           float ref = sm[kSmRefP + X * kTileP + tr];
@@ -759,7 +888,7 @@ struct MpcPair {
 
   FC_HD_CTX void prefetch_record(const float* rec_in) {
     // the warp's record slots are contiguous (nf4 x 512 B): one bulk prefetch from lane 0 instead of nf4 per-lane ones
-    const int nf4 = last ? 23 : 20;
+    const int nf4 = R == 1 ? (last ? 23 : 20) : (last ? 8 : 5);
     if (lane == 0) Ctx::prefetch_l2_bulk(rec_in + (size_t)uw * kRecF4 * 32 * 4, (unsigned)nf4 * 512u);
   }
 
@@ -770,21 +899,21 @@ struct MpcPair {
       if (t == kLook - 1) {
         float gxv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + row] * p.g_scale;   // into the scaled domain
+        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + traj] * p.g_scale;   // into the scaled domain
 #pragma unroll
-        for (int j = 0; j < kMaxOwn; ++j) {
+        for (int j = 0; j < kOwn; ++j) {
           const int u = u_first + j < kHid ? u_first + j : kHid - 1;
           const float* fw = sm + kSmSmallP + u;
           extra[j] = fw[0] * gxv[0] + fw[kHid] * gxv[1] + fw[2 * kHid] * gxv[2] + fw[3 * kHid] * gxv[3];
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < kMaxOwn; ++j) extra[j] = 0.f;
+        for (int j = 0; j < kOwn; ++j) extra[j] = 0.f;
       }
     } else {
       const float* dsq = w_dseq(X) + (size_t)t * kSlot + (size_t)uw * kMaxOwn * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < kMaxOwn; ++j) extra[j] = j < nown ? Ctx::ldcg(dsq + j * 32) : 0.f;
+      for (int j = 0; j < kOwn; ++j) extra[j] = j < nown ? Ctx::ldcg(dsq + j * 32) : 0.f;
     }
   }
 
@@ -795,6 +924,30 @@ struct MpcPair {
     // the gate gradients then need no multiplication before their fp16 split; only the weight scale is removed here
     const float unscale_b = 1.0f / kScaleW;
     const int dcol = col_d_bwd(X);
+    if constexpr (R == 4) {
+      // third th owns columns [36 th, 36 th + 36) (layer 0: [18 th, 18 th + 18)): 18 slots d(input unit), 18 slots
+      // d(h_prev unit); this thread's units are slots 4 quad .. 4 quad + 3 (+ 2 for the last thread)
+      float di[kOwn], dr[kOwn];
+      const int cr = l > 0 ? dcol + 36 * th + 18 + 4 * quad : dcol + 18 * th + 4 * quad;
+      if (l > 0) {
+        ctx.template tmem_ld_nowait<4>(dcol + 36 * th + 4 * quad, di);
+        if (last) ctx.template tmem_ld_nowait<2>(dcol + 36 * th + 4 * quad + 4, di + 4);
+      }
+      ctx.template tmem_ld_nowait<4>(cr, dr);
+      if (last) ctx.template tmem_ld_nowait<2>(cr + 4, dr + 4);
+      ctx.tmem_ld_wait();
+      float* dq = w_dseq(X) + (size_t)t * kSlot + (size_t)uw * kMaxOwn * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kOwn; ++j)
+        if (j < nown) {
+          if (l > 0) { const float v = di[j] * unscale_b; dq[j * 32] = fmaf(v, corr_b, v); }
+          const float v = dr[j] * unscale_b;
+          dh[j] = fmaf(v, corr_b, v);
+        } else {
+          dh[j] = 0.f;
+        }
+      return;
+    }
     if (l > 0) {
       float d[36];
       ctx.template tmem_ld_nowait<32>(dcol + 36 * th, d);
@@ -819,6 +972,7 @@ struct MpcPair {
   }
   // layer 0: gradient of the row features of step t (owner thread of the row)
   FC_HD_CTX void bwd_collect_features(int X, int m, int t) {
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     const float corr_b = Ctx::kAccTruncates ? acc_correction(kKB / 16, p.acc_comp) : 0.0f;
     const float unscale_b = p.g_unscale / kScaleW;
     const int kr = m + t - (kLook - 1);                    // gradient of row rho_{9+kr}
@@ -857,7 +1011,7 @@ struct MpcPair {
 
   FC_HD_CTX void bwd_item(int X, int l, int m, int t) {
     const int tmin = t_min_of(m);
-    float dh[kMaxOwn];
+    float dh[kOwn];
     lap(20);
     swap_cells();
     lap(11);
@@ -873,12 +1027,13 @@ struct MpcPair {
 #endif
     float rv[2][20];
     rec_load<4>(rp, 0, rv[0]);                             // first record group: in flight during the wait
+    if constexpr (R == 4) { if (last) rec_load<2>(rp, 5, rv[1]); }
     {
-      float extra[kMaxOwn];
+      float extra[kOwn];
       bwd_extra(X, l, t, extra);
       if (t == kLook - 1) {
 #pragma unroll
-        for (int j = 0; j < kMaxOwn; ++j) { dh[j] = extra[j]; c[j] = 0.f; }
+        for (int j = 0; j < kOwn; ++j) { dh[j] = extra[j]; c[j] = 0.f; }
       } else {
         lap(12);
         wait_full(X);                                      // MMA(X, l, t+1) complete
@@ -886,8 +1041,21 @@ struct MpcPair {
         bwd_collect(X, l, t + 1, dh);
         if (l == 0 && owner) bwd_collect_features(X, m, t + 1);
 #pragma unroll
-        for (int j = 0; j < kMaxOwn; ++j) dh[j] += extra[j];
+        for (int j = 0; j < kOwn; ++j) dh[j] += extra[j];
       }
+    }
+    if constexpr (R == 4) {
+      float dg[24];
+      bwd_units<4>(0, rv[0], dh, dg);
+      st_pairs_smem<8>(4 * u_first, dg);
+      if (last) {
+        bwd_units<2>(4, rv[1], dh, dg + 16);
+        st_pairs_smem<4>(4 * u_first + 16, dg + 16);
+      }
+      lap(7);
+      arrive_ready(X, true);
+      lap(8);
+      return;
     }
 #pragma unroll
     for (int gi = 0; gi < 4; ++gi) {
@@ -925,7 +1093,7 @@ struct MpcPair {
     }
     if (!service) {
       if (l > 0) {
-        float dh[kMaxOwn];
+        float dh[kOwn];
         bwd_collect(X, l, tmin, dh);                       // d(h) before the first kept step is not needed
       } else if (owner) {
         bwd_collect_features(X, m, tmin);
@@ -959,16 +1127,20 @@ struct MpcPair {
     if (scalar) {
       for (int X = 0; X < kTiles; ++X) {
         float mine = 0.f;
-        int b = (tile0 + X) * kTileP + row;
+        int b = (tile0 + X) * kRowsT + traj;
         if (X < ntl && b < p.B) {
           const float inv = 1.f / (float)p.N;
           const float* cg = w_cost(X);
-          mine = Ctx::ldcg(cg + row) * inv;                                    // :1458-1460
+          mine = Ctx::ldcg(cg + traj) * inv;                                   // :1458-1460
           p.cost[b] = mine;
-          p.command[b] = Ctx::ldcg(cg + kTileP + row) * inv;
-          p.error[b] = Ctx::ldcg(cg + 2 * kTileP + row) * inv;
+          p.command[b] = Ctx::ldcg(cg + kTileP + traj) * inv;
+          p.error[b] = Ctx::ldcg(cg + 2 * kTileP + traj) * inv;
         }
-        sm[kSmGxP + X * kTileP + row] = mine;              // gx area is free between the sweeps
+        sm[kSmGxP + X * kTileP + traj] = mine;             // gx area is free between the sweeps
+        if constexpr (R == 4) {                            // the rows that do not exist contribute nothing to the sum below
+#pragma unroll
+          for (int g = 1; g < 4; ++g) sm[kSmGxP + X * kTileP + 32 * g + lane] = 0.f;
+        }
       }
     }
     ctx.sync();
@@ -981,9 +1153,10 @@ struct MpcPair {
   }
 
   FC_HD_CTX void store_du0() {
+    const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     if (scalar)
       for (int X = 0; X < ntl; ++X) {
-        int b = (tile0 + X) * kTileP + row;
+        int b = (tile0 + X) * kRowsT + traj;
         if (b < p.B) {
           const float s = p.grad_scale;
           const float* rows = w_rows(X);
@@ -1002,13 +1175,21 @@ struct MpcPair {
   // zero padding of the dG operands (k = 200..207): TMEM columns 100..103 of tile 0, the last 16-byte piece of tile 1
   FC_HD_CTX void zero_dg_padding() {
     if (scalar) {
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
-      ctx.template tmem_st<4>(kColGhi + 100, z);
-      ctx.template tmem_st<4>(kColGlo + 100, z);
-      ctx.tmem_st_wait();
       const F4 z4 = {0.f, 0.f, 0.f, 0.f};
-      Ctx::sts4(op_ptr(0, kGates), z4);
-      Ctx::sts4(op_ptr(kOpGLoHalves, kGates), z4);
+      if constexpr (R == 1) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        ctx.template tmem_st<4>(kColGhi + 100, z);
+        ctx.template tmem_st<4>(kColGlo + 100, z);
+        ctx.tmem_st_wait();
+        Ctx::sts4(op_ptr(0, kGates), z4);
+        Ctx::sts4(op_ptr(kOpGLoHalves, kGates), z4);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          Ctx::sts4(op_ptr_rep(0, kGates, g), z4);
+          Ctx::sts4(op_ptr_rep(kOpGLoHalves, kGates, g), z4);
+        }
+      }
     }
   }
 
@@ -1021,20 +1202,21 @@ struct MpcPair {
     tlast = Ctx::clock();
 #endif
     if (tid == 0) {
-      ctx.bar_init(kBarReady, kUpdWarps + 3);                // cell-update warps + warps 1..3
-      ctx.bar_init(kBarReady + 1, kUpdWarps + 3);
+      ctx.bar_init(kBarReady, kUpdWarps + (R == 1 ? 3 : 1));   // cell-update warps + warps 1..3 (R == 4: + warp 1)
+      ctx.bar_init(kBarReady + 1, kUpdWarps + (R == 1 ? 3 : 1));
     }
     for (int i = tid; i < kSmallFloats; i += kThreadsP) sm[kSmSmallP + i] = p.wpack[kSmallOff + i];
     for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsP) reinterpret_cast<double*>(sm + kSmPgP)[i] = 0.0;
     if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedP) = 0.0;
+    for (int i = tid; i < kSmPgP - kSmRefP; i += kThreadsP) sm[kSmRefP + i] = 0.f;   // per-row arrays (R == 4 uses 32 rows of 128)
     ctx.bar_init_fence();
     ctx.sync();
-    const int npairs = (p.num_tiles + kTiles - 1) / kTiles;
+    const int npairs = R == 1 ? (p.num_tiles + kTiles - 1) / kTiles : p.num_tiles;   // CTA work items
     if (tid == 0 && ctx.bid() < npairs) request_weights(false, 0);
     for (int pp = ctx.bid(); pp < npairs; pp += ctx.nblk()) {
       const bool more = pp + ctx.nblk() < npairs;
-      tile0 = pp * kTiles;
-      ntl = p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles;
+      tile0 = R == 1 ? pp * kTiles : pp;
+      ntl = R == 1 ? (p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles) : 1;
       if (scalar)
         for (int X = 0; X < ntl; ++X) {
           if (p.shadow) load_tile_shadow(X);
@@ -1049,7 +1231,7 @@ struct MpcPair {
             float* grow = w_grow(X);
             for (int k = 0; k < p.N; ++k)
 #pragma unroll
-              for (int f = 0; f < kFeat; ++f) grow[(size_t)(k * kFeat + f) * kTileP + row] = 0.f;
+              for (int f = 0; f < kFeat; ++f) grow[(size_t)(k * kFeat + f) * kTileP + traj] = 0.f;
           }
         zero_dg_padding();
         ctx.sync();

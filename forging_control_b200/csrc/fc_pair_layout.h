@@ -173,6 +173,11 @@ static_assert(kTileP * kKB <= kSmOpFloats, "dG operand of tile 1 does not fit th
 constexpr int kOpLoHalves = kTileP * kKF;                    // forward: lo image of a tile follows its hi image
 FC_HD int op_fwd_halves(int tile) { return tile * 2 * kTileP * kKF; }
 constexpr int kOpGLoHalves = kTileP * kKB;                   // backward: lo image of dG (tile 1) follows the hi image
+// replica mode (R = 4, one tile per CTA): read-out partial sums [12 update warps][4 outputs][32 trajectories] in the tail of the
+// operand region that neither the forward images of tile 0 nor the dG images reach
+constexpr int kSmExP = kSmOpP + kTileP * kKB;
+static_assert(kTileP * kKB + kUpdWarps * 4 * 32 <= kSmOpFloats, "exchange buffer of the replica mode does not fit");
+static_assert(kOpTileFloats <= kTileP * kKB, "exchange buffer overlaps the forward images of tile 0");
 
 FC_HD float acc_correction(int steps, float scale) { return scale * (0.17f + 0.135f * (float)steps) * 1.1920929e-7f; }
 

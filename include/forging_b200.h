@@ -59,9 +59,10 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
  *   du0 [B] = d loss / d output_controller), gl[250] = sum_b cost[b] / B_global (the loss).
  *   with_grad = 0 computes the forward only (du0 may be NULL, gl[0..249] are zero).              */
 size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad);
-/* Kernel behind fc_mpc_loss: 0 = automatic (2 .. #SMs tiles of 128 trajectories: the one-tile tcgen05 kernel,
- * otherwise the two-tile tcgen05 pair kernel; measured fastest), 1 = always the FP32 FFMA kernel, 2 = always the one-tile tcgen05 kernel,
- * 3 = always the pair kernel.  Also settable with the environment variable FC_MPC_KERNEL=ffma|tc|pair before
+/* Kernel behind fc_mpc_loss: 0 = automatic (B <= 32 x #SMs: the replica mode of the pair kernel, 32-trajectory tiles;
+ * up to #SMs tiles of 128 trajectories: the one-tile tcgen05 kernel; beyond: the two-tile tcgen05 pair kernel; measured
+ * fastest), 1 = always the FP32 FFMA kernel, 2 = always the one-tile tcgen05 kernel, 3 = always the pair kernel,
+ * 4 = always the replica mode.  Also settable with the environment variable FC_MPC_KERNEL=ffma|tc|pair|replica before
  * the first call.  All kernels meet the same parity bar.                                            */
 int fc_mpc_select_kernel(int mode);
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-config timings of the fused MPC loss (BASELINE.json configs 1-3 + the headline) for the three kernels,
+"""Per-config timings of the fused MPC loss (BASELINE.json configs 1-3 + the headline) for the selectable kernels,
 device-resident inputs, CUDA events, median of 5 after 3 warm-ups."""
 import json, os, sys
 import numpy as np, torch
@@ -22,7 +22,7 @@ for name, N, B in (("config1 Main.py batch", 10, 15), ("config2", 5, 4096), ("co
     X = (torch.rand(B, 3, generator=g) * 2 - 1).to(dev); Z = (torch.rand(B, 10, 5, generator=g) * 2 - 1).to(dev)
     with torch.no_grad():
         u0 = ctl(X).reshape(-1).contiguous()
-    for kname, mode in (("ffma", 1), ("tcgen05 one tile", 2), ("tcgen05 pair", 3)):
+    for kname, mode in (("ffma", 1), ("tcgen05 one tile", 2), ("tcgen05 pair", 3), ("replica (32-row tiles)", 4), ("auto", 0)):
         L.fc_mpc_select_kernel(mode)
         for _ in range(3):
             fb.mpc_loss_native(wp, X, u0, Z, N, 20.0, True)

@@ -51,6 +51,7 @@ struct EmuCtx {
   static float ldcg(const float* p) { return *p; }
   static void cp_async16(float* d, const float* s) { std::memcpy(d, s, 16); }
   static void cp_async4(float* d, const float* s) { std::memcpy(d, s, 4); }
+  static void cp_async8(float* d, const float* s) { std::memcpy(d, s, 8); }
   static void sts1(float* p, float v) { *p = v; }
   static void stg2(float* p, float a, float b) { p[0] = a; p[1] = b; }
   static void cp_commit() {}
@@ -296,7 +297,9 @@ void fc_emu_pack_weights_pair(const float* w_ih0, const float* w_hh0, const floa
   for (int j = 0; j < fc::kSmallFloats; ++j) out[fc::pr::kSmallOff + j] = fc::packed_value(w, fc::kFCW + j);
 }
 
-int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+}  // extern "C"
+template <int R>
+static int emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
                          long long B_global, int with_grad, int grid, float* cost, float* command, float* error,
                          float* pred, float* du0, float* gl /*[256]*/) {
   fc::MpcParams p;
@@ -308,8 +311,8 @@ int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const 
   p.noise_std = g_noise_std; p.noise_seed = g_noise_seed;
   p.acc_comp = 1.0f;
   { int e = (int)std::floor(std::log2((double)N * (double)B_global)); p.g_scale = (float)std::ldexp(1.0, e); p.g_unscale = (float)std::ldexp(1.0, -e); }
-  p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;
-  const int npairs = (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles;
+  p.num_tiles = (B + fc::pr::kTileP / R - 1) / (fc::pr::kTileP / R);
+  const int npairs = R == 1 ? (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles : p.num_tiles;
   if (grid > npairs) grid = npairs;
   fc::pr::WorkLayoutP wl = fc::pr::work_layout_p(N, with_grad);
   p.work_stride = fc::pr::kTiles * wl.total;
@@ -324,7 +327,7 @@ int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const 
     for (int t = 0; t < fc::pr::kThreadsP; ++t)
       th.emplace_back([&blk, &p, t]() {
         EmuCtxTC ctx(&blk, t);
-        fc::pr::MpcPair<EmuCtxTC> k(ctx, p);
+        fc::pr::MpcPair<EmuCtxTC, R> k(ctx, p);
         k.run();
       });
     for (auto& x : th) x.join();
@@ -338,7 +341,28 @@ int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const 
   return 0;
 }
 
-int fc_emu_lstm_shadow_pair(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, int grid,
+extern "C" {
+int fc_emu_mpc_loss_pair(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                         long long B_global, int with_grad, int grid, float* cost, float* command, float* error,
+                         float* pred, float* du0, float* gl /*[256]*/) {
+  return emu_mpc_loss_pair<1>(X, u0, Z, wpack, B, N, alpha, B_global, with_grad, grid, cost, command, error, pred, du0, gl);
+}
+// replica mode of the pair-kernel source (one 32-trajectory tile per CTA); same packed weights as the pair kernel
+int fc_emu_pack_floats_replica() { return fc::pr::kPackFloatsP; }
+void fc_emu_pack_weights_replica(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1,
+                                 const float* w_ih2, const float* w_hh2, const float* fc_w, const float* fc_b,
+                                 const float* inp_w, const float* inp_b, const float* out_w, float* out) {
+  fc_emu_pack_weights_pair(w_ih0, w_hh0, w_ih1, w_hh1, w_ih2, w_hh2, fc_w, fc_b, inp_w, inp_b, out_w, out);
+}
+int fc_emu_mpc_loss_replica(const float* X, const float* u0, const float* Z, const float* wpack, int B, int N, float alpha,
+                            long long B_global, int with_grad, int grid, float* cost, float* command, float* error,
+                            float* pred, float* du0, float* gl /*[256]*/) {
+  return emu_mpc_loss_pair<4>(X, u0, Z, wpack, B, N, alpha, B_global, with_grad, grid, cost, command, error, pred, du0, gl);
+}
+}  // extern "C"
+
+template <int R>
+static int emu_lstm_shadow_pair(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, int grid,
                             float* y /*[B][T][4]*/) {
   fc::MpcParams p;
   std::memset(&p, 0, sizeof(p));
@@ -347,8 +371,8 @@ int fc_emu_lstm_shadow_pair(const float* row0, const float* u, const float* rati
   p.acc_comp = 1.0f; p.g_scale = p.g_unscale = 1.0f;
   p.shadow = 1; p.sh_row0 = row0; p.sh_u = u; p.sh_y = y;
   for (int q = 0; q < 4; ++q) p.sh_ratio[q] = ratio[q];
-  p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;
-  const int npairs = (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles;
+  p.num_tiles = (B + fc::pr::kTileP / R - 1) / (fc::pr::kTileP / R);
+  const int npairs = R == 1 ? (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles : p.num_tiles;
   if (grid > npairs) grid = npairs;
   p.work_stride = fc::pr::kTiles * fc::pr::work_layout_p(T, 0).total;
   std::vector<float> work((size_t)grid * p.work_stride, 0.f);
@@ -362,12 +386,22 @@ int fc_emu_lstm_shadow_pair(const float* row0, const float* u, const float* rati
     for (int t = 0; t < fc::pr::kThreadsP; ++t)
       th.emplace_back([&blk, &p, t]() {
         EmuCtxTC ctx(&blk, t);
-        fc::pr::MpcPair<EmuCtxTC> k(ctx, p);
+        fc::pr::MpcPair<EmuCtxTC, R> k(ctx, p);
         k.run();
       });
     for (auto& x : th) x.join();
   }
   return 0;
+}
+
+extern "C" {
+int fc_emu_lstm_shadow_pair(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, int grid,
+                            float* y /*[B][T][4]*/) {
+  return emu_lstm_shadow_pair<1>(row0, u, ratio, wpack, B, T, grid, y);
+}
+int fc_emu_lstm_shadow_replica(const float* row0, const float* u, const float* ratio, const float* wpack, int B, int T, int grid,
+                               float* y /*[B][T][4]*/) {
+  return emu_lstm_shadow_pair<4>(row0, u, ratio, wpack, B, T, grid, y);
 }
 
 // one-tile tcgen05 kernel with a wide controller (width_dim > 1): gl_wide [2560] = d fc_int.weight | d fc_int.bias

@@ -126,7 +126,8 @@ def _check_v(o, out, g, tol=1e-5):
     assert rel_max(o["gl"][200:250], g["out_w"][0]) < tol
 
 
-@pytest.mark.parametrize("variant,name", [("tc", "n1_b3"), ("tc", "n2_b5"), ("pair", "n1_b3"), ("pair", "n2_b5")])
+@pytest.mark.parametrize("variant,name", [("tc", "n1_b3"), ("tc", "n2_b5"), ("pair", "n1_b3"), ("pair", "n2_b5"),
+                                          ("replica", "n1_b3"), ("replica", "n2_b5")])
 def test_emulated_tcgen05_kernels_match_oracle(emu, golden_cases, golden_weights, variant, name):
     C = golden_cases
     N, B, wd = (int(v) for v in C[f"{name}/meta"])
@@ -156,7 +157,24 @@ def test_emulated_pair_kernel_two_tiles_and_odd_tail(emu, golden_cases, golden_w
     _check_v(o, out, g)
 
 
-@pytest.mark.parametrize("variant", ["pair"])
+def test_emulated_replica_kernel_several_tiles_and_ragged_tail(emu, golden_cases, golden_weights):
+    """Replica mode of the pair-kernel source (32-trajectory tiles): B = 75 on two emulated CTAs = tiles 0 and 2 on CTA 0
+    (the second one ragged, 11 trajectories), tile 1 on CTA 1."""
+    C, name, rep = golden_cases, "n2_b5", 15
+    N = int(C[f"{name}/meta"][0])
+    lstm, fnn = state_dicts(golden_weights, str(C[f"{name}/ctl"]))
+    rng = np.random.default_rng(1)
+    X = np.ascontiguousarray(np.tile(C[f"{name}/X"], (rep, 1)), dtype=np.float32)
+    Z = np.tile(C[f"{name}/Z"], (rep, 1, 1))
+    Z = np.ascontiguousarray(Z * (1 + 0.05 * rng.standard_normal(Z.shape)), dtype=np.float32)
+    u0 = np.ascontiguousarray(np.tile(C[f"{name}/f32/u0"], rep))
+    o = _run_v(emu, "replica", _pack_v(emu, lstm, fnn, "replica"), X, u0, Z, N, 20.0, grid=2)
+    w = O.weights_from_state_dicts(lstm, fnn, np.float64)
+    out, g = O.mpc_loss_forward_backward(w, X.astype(np.float64), u0.astype(np.float64), Z.astype(np.float64), N, 20.0)
+    _check_v(o, out, g)
+
+
+@pytest.mark.parametrize("variant", ["pair", "replica"])
 def test_emulated_lstm_shadow_rollout_matches_oracle(emu, golden_weights, variant):
     """Forward-only shadow mode of the two-tile kernels (fc_lstm_shadow_rollout) against the oracle restatement of
     simulator_make_step / loop (UL/Functions.py:969-1011, :1196-1231)."""
@@ -174,7 +192,7 @@ def test_emulated_lstm_shadow_rollout_matches_oracle(emu, golden_weights, varian
     assert rel_max(y, ref) < 1e-5
 
 
-@pytest.mark.parametrize("variant", ["ffma", "pair"])
+@pytest.mark.parametrize("variant", ["ffma", "pair", "replica"])
 def test_emulated_enable_noise_matches_oracle_with_the_same_noise(emu, golden_cases, golden_weights, variant):
     """enable_noise (UL/Functions.py:1400-1402): the kernels' counter-based generator restated in the oracle
     (philox_normal4) gives the same roll-out, costs and gradients."""
