@@ -16,7 +16,7 @@ _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.environ.get("FC_LIB_PATH", os.path.join(_PKG_DIR, "libforging_b200.so"))   # override: development builds
 SOURCES = [os.path.join(_PKG_DIR, "csrc", f) for f in
            ("fc_api.cu", "fc_mpc_kernel.inl", "fc_layout.h", "fc_plant.cuh", "fc_mpc_tc_kernel.inl", "fc_tc_layout.h",
-            "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_lstm_train.cuh", "fc_fnn.cuh")]
+            "fc_mpc_pair_kernel.inl", "fc_pair_layout.h", "fc_lstm_train.cuh", "fc_fnn.cuh", "fc_lstm_train_tc.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -26,7 +26,7 @@ EXPORTS = ("fc_last_error", "fc_version", "fc_pack_floats", "fc_pack_weights",
            "fc_closed_loop_rk4_f64", "fc_fp32_peak", "fc_lstm_shadow_workspace_bytes", "fc_lstm_shadow_rollout",
            "fc_mpc_loss_noise", "fc_closed_loop_rk4_noise", "fc_closed_loop_rk4_f64_noise",
            "fc_build_windows", "fc_mpc_loss_wide_workspace_bytes", "fc_mpc_loss_wide",
-           "fc_closed_loop_rk4_ex", "fc_lstm_train_pack_floats", "fc_lstm_train_pack", "fc_lstm_window_workspace_bytes",
+           "fc_closed_loop_rk4_ex", "fc_lstm_train_select_path", "fc_lstm_train_path_for", "fc_lstm_train_pack_floats", "fc_lstm_train_pack", "fc_lstm_window_workspace_bytes",
            "fc_lstm_window_fwd", "fc_lstm_window_bwd", "fc_adamw_step", "fc_fnn_forward", "fc_fnn_backward_workspace_bytes",
            "fc_fnn_backward")
 
@@ -104,6 +104,10 @@ def lib() -> ctypes.CDLL:
                                         fp5, fp5, ctypes.c_ulonglong, vp]
     L.fc_build_windows.restype = i32
     L.fc_build_windows.argtypes = [vp, vp, vp, i64, i32, i32, vp, i64, vp, vp, vp, vp]
+    L.fc_lstm_train_select_path.restype = i32
+    L.fc_lstm_train_select_path.argtypes = [i32]
+    L.fc_lstm_train_path_for.restype = i32
+    L.fc_lstm_train_path_for.argtypes = [i32]
     L.fc_lstm_train_pack_floats.restype = sz
     L.fc_lstm_train_pack_floats.argtypes = []
     L.fc_lstm_train_pack.restype = i32

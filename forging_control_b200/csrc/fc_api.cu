@@ -345,6 +345,17 @@ __global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_pair_kernel(const M
   k.run();
 }
 
+// surrogate training mode of the same source (MpcParams::train), tanh with its small-argument polynomial
+__global__ void __launch_bounds__(pr::kThreadsP, 1) lstm_train_pair_kernel(const MpcParams p) {
+  DevCtxTC ctx;
+  pr::MpcPair<DevCtxTC, 1, true> k(ctx, p);
+  k.run();
+}
+
+}  // namespace fc
+#include "fc_lstm_train_tc.cuh"
+namespace fc {
+
 // replica mode of the same source: one 32-trajectory tile per CTA, the 50 hidden units of a trajectory split over
 // twelve threads (small / mid-size batches, fc_mpc_pair_kernel.inl)
 __global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_replica_kernel(const MpcParams p) {
@@ -354,10 +365,10 @@ __global__ void __launch_bounds__(pr::kThreadsP, 1) mpc_loss_replica_kernel(cons
 }
 
 // pair-kernel operand images behind the two others in the packed buffer
-__global__ void pack_weights_pair_kernel(RawWeights w, float* out) {
+__global__ void pack_weights_pair_kernel(RawWeights w, float* out, long base_off) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // half index
   const long n_halves = 2L * pr::kSmallOff;
-  float* base = out + kPackFloats + tc::kPackFloatsTC;
+  float* base = out + base_off;
   __half* oh = reinterpret_cast<__half*>(base);
   if (i < n_halves) {
     const pr::PrSlot s = pr::decode_half(i);
@@ -615,6 +626,10 @@ static int ensure_smem_attributes() {
           "cudaFuncSetAttribute(smem, pair)");
   FC_CUDA(cudaFuncSetAttribute(mpc_loss_replica_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
           "cudaFuncSetAttribute(smem, replica)");
+  FC_CUDA(cudaFuncSetAttribute(lstm_train_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
+          "cudaFuncSetAttribute(smem, training)");
+  FC_CUDA(cudaFuncSetAttribute(lt2::dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt2::kDwSmem),
+          "cudaFuncSetAttribute(smem, dw)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd),
           "cudaFuncSetAttribute(smem, lstm fwd)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd80_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd80),
@@ -650,7 +665,8 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
   FC_CUDA(cudaGetLastError(), "pack_weights_kernel launch");
   pack_weights_tc_kernel<<<(2 * tc::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, wpack);
   FC_CUDA(cudaGetLastError(), "pack_weights_tc_kernel launch");
-  pack_weights_pair_kernel<<<(2 * pr::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, wpack);
+  pack_weights_pair_kernel<<<(2 * pr::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w, wpack, (long)kPackFloats + tc::kPackFloatsTC);
   FC_CUDA(cudaGetLastError(), "pack_weights_pair_kernel launch");
   return FC_OK;
 }
@@ -961,7 +977,9 @@ int fc_fp32_peak(int iters, double* flops_host, void* stream) {
 // ---------------------------------------------------------------------------------------------------
 // surrogate training path + optimizer update (fc_lstm_train.cuh)
 // ---------------------------------------------------------------------------------------------------
-size_t fc_lstm_train_pack_floats(void) { return (size_t)lt::kPackFloatsL; }
+// pack = [FFMA weight images (lt::kPackFloatsL) | pad to 16 bytes | pair-kernel operand images (pr::kPackFloatsP)]
+static constexpr long kTrainPackPairOff = ((long)lt::kPackFloatsL + 3) / 4 * 4;
+size_t fc_lstm_train_pack_floats(void) { return (size_t)kTrainPackPairOff + (size_t)pr::kPackFloatsP; }
 
 int fc_lstm_train_pack(const float* w_ih0, const float* w_hh0, const float* w_ih1, const float* w_hh1, const float* w_ih2,
                        const float* w_hh2, float* pack, void* stream) {
@@ -972,6 +990,53 @@ int fc_lstm_train_pack(const float* w_ih0, const float* w_hh0, const float* w_ih
   w.w_ih[0] = w_ih0; w.w_hh[0] = w_hh0; w.w_ih[1] = w_ih1; w.w_hh[1] = w_hh1; w.w_ih[2] = w_ih2; w.w_hh[2] = w_hh2;
   lt::pack_lstm_train_kernel<<<(lt::kPackFloatsL + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, pack);
   FC_CUDA(cudaGetLastError(), "pack_lstm_train_kernel launch");
+  // operand images of the tensor-core path; its fc block is not used (the training mode reads fc.weight / fc.bias directly)
+  RawWeights rw;
+  for (int l = 0; l < kLayers; ++l) { rw.w_ih[l] = w.w_ih[l]; rw.w_hh[l] = w.w_hh[l]; }
+  rw.fc_w = rw.fc_b = rw.inp_w = rw.inp_b = rw.out_w = w_hh0;
+  pack_weights_pair_kernel<<<(2 * pr::kSmallOff + kSmallFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rw, pack, kTrainPackPairOff);
+  FC_CUDA(cudaGetLastError(), "pack_weights_pair_kernel (training) launch");
+  return FC_OK;
+}
+
+// ---- tensor-core path of the surrogate training step (fc_lstm_train_tc.cuh): pair kernel in training mode + dw_kernel.
+// Chosen for large batches (the FFMA kernels keep the small ones, where seven 40-sample tiles fill more SMs than one
+// 256-sample tile pair); FC_LSTM_TRAIN=tc|ffma forces one of them.
+static thread_local int g_lstm_mode = -1;
+static int lstm_tc_mode() {
+  if (g_lstm_mode < 0) {
+    const char* e = getenv("FC_LSTM_TRAIN");
+    g_lstm_mode = 0;
+    if (e && !strcmp(e, "ffma")) g_lstm_mode = 1;
+    if (e && !strcmp(e, "tc")) g_lstm_mode = 2;
+  }
+  return g_lstm_mode;
+}
+static bool lstm_use_tc(int B) { const int m = lstm_tc_mode(); return m == 2 || (m == 0 && B >= 8192); }
+
+static constexpr int kFcGradBlocksPerSm = 8;
+struct LstmTcPlan {
+  int tiles, grid, chunk_tiles;                 // 128-sample tiles, CTAs of the pair kernel, tiles per chunk of the backward
+  size_t scale, partial, work, hlast, dwp, fcp, scratch, floats;   // offsets in floats
+};
+static int lstm_tc_plan(int B, int save, LstmTcPlan* pl) {
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  pl->tiles = (B + pr::kTileP - 1) / pr::kTileP;
+  const int pairs = (pl->tiles + pr::kTiles - 1) / pr::kTiles;
+  pl->grid = pairs < sms ? pairs : sms;
+  pl->chunk_tiles = pl->tiles < 2 * pr::kTiles * sms ? pl->tiles : 2 * pr::kTiles * sms;   // two passes of the pair kernel per chunk
+  const size_t work_cta = pr::kTiles * (save ? pr::work_total_train() : pr::work_layout_p(1, 0).total);
+  size_t o = 0;
+  pl->scale = o;   o += 4;
+  pl->partial = o; o += (size_t)pl->grid * kPartialStride * 2;                      // doubles
+  pl->work = o;    o += (size_t)pl->grid * work_cta;
+  pl->hlast = o;   o += save ? ((size_t)B * kHid + 3) / 4 * 4 : 0;
+  pl->dwp = o;     o += save ? (size_t)sms * lt2::kDwPartialFloats : 0;
+  pl->fcp = o;     o += save ? (size_t)kFcGradBlocksPerSm * sms * 256 * 2 : 0;       // doubles
+  pl->scratch = o; o += save ? (size_t)pl->chunk_tiles * pr::kTrTileFloats : 0;
+  pl->floats = o + 4;
   return FC_OK;
 }
 
@@ -998,7 +1063,20 @@ static int lstm_train_plan(int B, int save, LstmTrainPlan* pl) {
   return FC_OK;
 }
 
+int fc_lstm_train_select_path(int mode) {
+  if (mode < 0 || mode > 2) return fail(FC_ERR_BAD_SHAPE, "fc_lstm_train_select_path: mode%s must be 0 (auto), 1 (FP32 FFMA kernels) or 2 (tensor-core path)");
+  g_lstm_mode = mode;
+  return FC_OK;
+}
+
+int fc_lstm_train_path_for(int B) { return lstm_use_tc(B) ? 2 : 1; }
+
 size_t fc_lstm_window_workspace_bytes(int B, int save) {
+  if (B > 0 && lstm_use_tc(B)) {
+    LstmTcPlan tp;
+    if (lstm_tc_plan(B, save, &tp)) return 0;
+    return tp.floats * sizeof(float);
+  }
   LstmTrainPlan pl;
   if (lstm_train_plan(B, save, &pl)) return 0;
   return pl.floats * sizeof(float);
@@ -1007,6 +1085,31 @@ size_t fc_lstm_window_workspace_bytes(int B, int save) {
 int fc_lstm_window_fwd(const float* X, const float* pack, const float* fc_w, const float* fc_b, int B, int save, float* out,
                        void* work, size_t work_bytes, void* stream) {
   if (!X || !pack || !fc_w || !fc_b || !out) return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_fwd: null pointer%s");
+  if (B > 0 && lstm_use_tc(B)) {
+    LstmTcPlan tp;
+    int rc = lstm_tc_plan(B, save, &tp);
+    if (rc) return rc;
+    if (!work) return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_fwd: workspace required%s");
+    if (work_bytes < tp.floats * sizeof(float))
+      return fail(FC_ERR_WORKSPACE, "fc_lstm_window_fwd: workspace too small%s (%lld < %lld bytes)", "", (long long)work_bytes,
+                  (long long)(tp.floats * sizeof(float)));
+    if (!aligned16(pack) || !aligned16(work)) return fail(FC_ERR_MISALIGNED, "fc_lstm_window_fwd: pack / work must be 16-byte aligned%s");
+    rc = ensure_smem_attributes();
+    if (rc) return rc;
+    float* wf = (float*)work;
+    MpcParams p;
+    memset(&p, 0, sizeof(p));
+    p.wpack = pack + kTrainPackPairOff;
+    p.partial = reinterpret_cast<double*>(wf + tp.partial);
+    p.work = wf + tp.work;
+    p.work_stride = pr::kTiles * (save ? pr::work_total_train() : pr::work_layout_p(1, 0).total);
+    p.B = B; p.N = 1; p.with_grad = 0; p.num_tiles = tp.tiles;
+    p.acc_comp = 1.3f; p.g_scale = p.g_unscale = 1.0f;
+    p.train = 1; p.tr_x = X; p.tr_y = out; p.tr_hlast = save ? wf + tp.hlast : nullptr; p.tr_fcw = fc_w; p.tr_fcb = fc_b;
+    lstm_train_pair_kernel<<<tp.grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
+    FC_CUDA(cudaGetLastError(), "lstm_train_pair_kernel (forward) launch");
+    return FC_OK;
+  }
   LstmTrainPlan pl;
   int rc = lstm_train_plan(B, save, &pl);
   if (rc) return rc;
@@ -1035,6 +1138,60 @@ int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, co
                        float* g_fc_w, float* g_fc_b, void* stream) {
   if (!X || !d_out || !pack || !fc_w || !work || !g_ih0 || !g_hh0 || !g_ih1 || !g_hh1 || !g_ih2 || !g_hh2 || !g_fc_w || !g_fc_b)
     return fail(FC_ERR_NULL_POINTER, "fc_lstm_window_bwd: null pointer%s");
+  if (B > 0 && lstm_use_tc(B)) {
+    LstmTcPlan tp;
+    int rc = lstm_tc_plan(B, 1, &tp);
+    if (rc) return rc;
+    if (work_bytes < tp.floats * sizeof(float))
+      return fail(FC_ERR_WORKSPACE, "fc_lstm_window_bwd: workspace too small%s (%lld < %lld bytes)", "", (long long)work_bytes,
+                  (long long)(tp.floats * sizeof(float)));
+    if (!aligned16(pack) || !aligned16(work)) return fail(FC_ERR_MISALIGNED, "fc_lstm_window_bwd: pack / work must be 16-byte aligned%s");
+    rc = ensure_smem_attributes();
+    if (rc) return rc;
+    int sms = 0;
+    rc = sm_count(&sms);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wf = (float*)work;
+    FC_CUDA(cudaMemsetAsync(wf + tp.scale, 0, 4 * sizeof(float), st), "cudaMemsetAsync(scale)");
+    lt2::grad_absmax_kernel<<<sms, 256, 0, st>>>(d_out, (long long)B * kOut, wf + tp.scale);
+    FC_CUDA(cudaGetLastError(), "grad_absmax_kernel launch");
+    lt2::grad_scale_kernel<<<1, 1, 0, st>>>(wf + tp.scale);
+    FC_CUDA(cudaGetLastError(), "grad_scale_kernel launch");
+    FC_CUDA(cudaMemsetAsync(wf + tp.dwp, 0, (size_t)sms * lt2::kDwPartialFloats * sizeof(float), st), "cudaMemsetAsync(dW partials)");
+    for (int t0 = 0; t0 < tp.tiles; t0 += tp.chunk_tiles) {
+      const int nt = tp.tiles - t0 < tp.chunk_tiles ? tp.tiles - t0 : tp.chunk_tiles;
+      const long long s0 = (long long)t0 * pr::kTileP;
+      const int nb = (int)((long long)B - s0 < (long long)nt * pr::kTileP ? (long long)B - s0 : (long long)nt * pr::kTileP);
+      const int pairs = (nt + pr::kTiles - 1) / pr::kTiles;
+      MpcParams p;
+      memset(&p, 0, sizeof(p));
+      p.wpack = pack + kTrainPackPairOff;
+      p.partial = reinterpret_cast<double*>(wf + tp.partial);
+      p.work = wf + tp.work;
+      p.work_stride = pr::kTiles * pr::work_total_train();
+      p.B = nb; p.N = 1; p.with_grad = 1; p.num_tiles = nt;
+      p.acc_comp = 1.3f; p.g_scale = p.g_unscale = 1.0f;
+      p.train = 2; p.tr_x = X + s0 * (kLook * kFeat); p.tr_dy = d_out + s0 * kOut; p.tr_fcw = fc_w; p.tr_fcb = fc_w;   // fc.bias is not needed
+      p.tr_scale = wf + tp.scale; p.tr_ws = wf + tp.scratch; p.tr_tile_base = 0;
+      lstm_train_pair_kernel<<<pairs < tp.grid ? pairs : tp.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+      FC_CUDA(cudaGetLastError(), "lstm_train_pair_kernel (forward + reverse sweep) launch");
+      lt2::DwParams d;
+      d.ws = wf + tp.scratch; d.tiles = nt; d.partial = wf + tp.dwp; d.acc_comp = 1.0f;
+      lt2::dw_kernel<<<sms, lt2::kDwThreads, lt2::kDwSmem, st>>>(d);
+      FC_CUDA(cudaGetLastError(), "dw_kernel launch");
+    }
+    lt2::DwGradOut g;
+    g.g_ih[0] = g_ih0; g.g_hh[0] = g_hh0; g.g_ih[1] = g_ih1; g.g_hh[1] = g_hh1; g.g_ih[2] = g_ih2; g.g_hh[2] = g_hh2;
+    lt2::dw_reduce_kernel<<<(kGates * kFeat + 5 * kGates * kHid + 255) / 256, 256, 0, st>>>(wf + tp.dwp, sms, wf + tp.scale, g);
+    FC_CUDA(cudaGetLastError(), "dw_reduce_kernel launch");
+    double* fcp = reinterpret_cast<double*>(wf + tp.fcp);
+    lt2::fc_grad_partial_kernel<<<kFcGradBlocksPerSm * sms, 256, 0, st>>>(wf + tp.hlast, d_out, B, fcp);
+    FC_CUDA(cudaGetLastError(), "fc_grad_partial_kernel launch");
+    lt2::fc_grad_reduce_kernel<<<1, 256, 0, st>>>(fcp, kFcGradBlocksPerSm * sms, g_fc_w, g_fc_b);
+    FC_CUDA(cudaGetLastError(), "fc_grad_reduce_kernel launch");
+    return FC_OK;
+  }
   LstmTrainPlan pl;
   int rc = lstm_train_plan(B, 1, &pl);
   if (rc) return rc;

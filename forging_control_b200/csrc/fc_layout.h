@@ -220,6 +220,19 @@ struct MpcParams {
   const float* sh_u;     // [B][N]  scaled commands; sh_u[b][m+1] closes the row appended after window m
   float* sh_y;           // [B][N][4] surrogate outputs (scaled)
   float sh_ratio[4];     // scale_out / scale_in: output -> next input row
+  // surrogate training on the pair kernel (Model_NN/Functions.py:313-340, :520-569; fc_lstm_train_tc.cuh): one window per
+  // sample, N = 1, every cell step recorded.  train = 1: forward only (y); train = 2: forward with records + reverse sweep
+  // seeded by d loss / d y, writing the gate gradients and the layer inputs in operand format for the weight-gradient kernel
+  int train;
+  const float* tr_x;     // [B][10][5] windows
+  float* tr_y;           // [B][4] outputs (train = 1)
+  float* tr_hlast;       // [B][50] top-layer hidden state of the last step (train = 1, may be null)
+  const float* tr_dy;    // [B][4] upstream gradient (train = 2)
+  const float* tr_fcw;   // fc.weight [4][50] (raw state_dict tensor)
+  const float* tr_fcb;   // fc.bias [4]
+  const float* tr_scale; // device: {scale, 1 / scale} of the gate gradients (power of two)
+  float* tr_ws;          // per-tile scratch for the weight-gradient kernel, see lt2::TileScratch
+  int tr_tile_base;      // index of this launch's first tile in tr_ws
 };
 
 // Four standard normals for (trajectory b, window m): Philox4x32-10 + Box-Muller.  Counter-based, so every kernel

@@ -29,7 +29,11 @@ namespace pr {
 // 6 for the last one) instead of three ways: the dependent chain of a step shrinks from ~5 000 to ~1 200 cycles, which is
 // what a latency-bound batch (B = 15 .. 4 736) needs.  Both operands come from shared memory in both directions (SS-mode
 // MMA); the per-trajectory scalar work runs on warp 1; read-out partial sums are exchanged through shared memory.
-template <class Ctx, int R = 1>
+// PT = true (surrogate training): tanh keeps its odd polynomial below |x| = 0.2.  With freshly initialised surrogate weights
+// the cell values are small and the weight gradients are differences of nearly equal terms, so the RELATIVE accuracy of
+// small tanh values shows (fc.weight gradient 2.7e-5 of the reference without it, 3e-7 with it); the roll-out kernels work
+// on a trained surrogate and do not need it (see tanh_from_).
+template <class Ctx, int R = 1, bool PT = false>
 struct MpcPair {
   static_assert(R == 1 || R == 4, "replica factor");
   static constexpr int kRowsT = kTileP / R;          // distinct trajectories per tile
@@ -94,7 +98,8 @@ struct MpcPair {
       scalar = warp == 1;
     }
     uw = service ? 0 : warp - 4;                             // index among the cell-update warps
-    tstride = work_layout_p(p.N, p.with_grad).total;
+    tstride = p.train == 2 ? work_total_train() : work_layout_p(p.N, p.with_grad).total;
+    gsc = p.g_scale;
     wbase = p.work + (size_t)ctx.bid() * p.work_stride;
     phF0 = phF1 = phR0 = phR1 = phW = 0;
     ntl = 0; tile0 = 0;
@@ -107,6 +112,15 @@ struct MpcPair {
     tlast = 0;
 #endif
   }
+
+  // window bookkeeping: the roll-out keeps steps t_min_of(m)..9 of window m; surrogate training has one window and keeps all
+  FC_HD_CTX int tmin_of(int m) const { return p.train ? 0 : t_min_of(m); }
+  FC_HD_CTX int kept_of(int m) const { return p.train ? kLook : steps_kept(m); }
+  FC_HD_CTX long recb_of(int m) const { return p.train ? 0 : rec_base(m); }
+  float gsc;             // scale of the gate gradients (roll-out: kernel parameter; training: device scalar)
+  // training: scratch of tile X for the weight-gradient kernel
+  FC_HD_CTX float* tr_tile(int X) const { return p.tr_ws + (size_t)(p.tr_tile_base + tile0 + X) * kTrTileFloats; }
+  FC_HD_CTX float* tr_hseq(int X, int l, int slot) const { return tr_tile(X) + kTrHseqOff + (size_t)(l * (kLook + 1) + slot) * kTrHseqSlot; }
 
   // workspace pointers of tile X
   FC_HD_CTX float* w_rows(int X) const { return wbase + X * tstride; }
@@ -137,7 +151,16 @@ struct MpcPair {
   // polynomial rounds 1 and 2 used below |x| = 0.2 for RELATIVE accuracy bought nothing measurable: summed gradients
   // 2e-7..5e-7 of the fp64 oracle without it against 1.4e-7..2.6e-7 with it (profiles/r02b_activation_variants.md),
   // for 12 of 62 instructions per cell unit
-  FC_HD_CTX static float tanh_from_(float, float rd) { return fmaf(-2.f, rd, 1.f); }
+  FC_HD_CTX static float tanh_from_(float x, float rd) {
+    const float big = fmaf(-2.f, rd, 1.f);
+    if constexpr (!PT) return big;
+    // below |x| = 0.2: odd Taylor polynomial up to x^7 (next term 62/2835 x^9: relative 6e-8 at 0.2)
+    const float x2 = x * x;
+    float pl = fmaf(x2, -0.053968253968253971f, 0.13333333333333333f);
+    pl = fmaf(x2, pl, -0.33333333333333331f);
+    pl = fmaf(x2 * x, pl, x);
+    return fabsf(x) < 0.2f ? pl : big;
+  }
   template <int NU>
   FC_HD_CTX static void tanh_batch(const float* x, float* y) {
     float d[NU], r[NU];
@@ -157,12 +180,13 @@ struct MpcPair {
   }
   // unscale, the accumulator compensation (1 + corr) and -log2(e) folded into ONE multiplier of the raw accumulator
   // value (rounded once: 6e-8 relative on the exponent argument, i.e. <= 2e-8 on a sigmoid)
-  struct ActK { float k1, k2; };
+  struct ActK { float k1, k2, kx; };
   FC_HD_CTX static ActK make_actk(float unscale, float corr) {
     ActK k;
     const float khi = -kLog2e * unscale;                    // exact: unscale is a power of two
     k.k1 = fmaf(khi, corr, khi);                            // sigmoid gates: exponent argument = raw * k1
     k.k2 = -2.f * k.k1;                                     // tanh gate: 2 log2(e) x
+    k.kx = fmaf(unscale, corr, unscale);                    // PT: the pre-activation itself
     return k;
   }
 
@@ -272,14 +296,19 @@ struct MpcPair {
   }
   // pieces <-> the hidden-sequence scratch of the layer below: [t][warp][piece*2 + hi/lo][lane] float4, thread-private
   FC_HD_CTX float* seq_ptr(int X, int t) const { return w_seq(X) + (size_t)t * kSlot + ((size_t)uw * 6 * 32 + lane) * 4; }
-  FC_HD_CTX void stg_pieces(int X, int t, const F4* hi4, const F4* lo4) {
-    float* sq = seq_ptr(X, t);
+  // piece ch (hi / lo) of the hidden state of layer l at step t: thread-private slot of the per-CTA scratch, or (training
+  // with the reverse sweep) its place in the operand-format hidden sequence kept for the weight-gradient kernel
+  FC_HD_CTX float* seq_piece(int X, int l, int t, int ch, int hl) const {
+    if (p.train == 2) return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kTileP * 4) + (size_t)((2 * th + ch) * kTileP + row) * 4;
+    return seq_ptr(X, t) + (ch * 2 + hl) * 128;
+  }
+  FC_HD_CTX void stg_pieces(int X, int l, int t, const F4* hi4, const F4* lo4) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
-      if (ch < 2 || last) { Ctx::stg4(sq + (ch * 2) * 128, hi4[ch]); Ctx::stg4(sq + (ch * 2 + 1) * 128, lo4[ch]); }
+      if (ch < 2 || last) { Ctx::stg4(seq_piece(X, l, t, ch, 0), hi4[ch]); Ctx::stg4(seq_piece(X, l, t, ch, 1), lo4[ch]); }
   }
   // asynchronous copy scratch -> input block of the operand images (cp.async, no registers); cp_wait before the arrive
-  FC_HD_CTX void copy_input(int X, int t) {
+  FC_HD_CTX void copy_input(int X, int l, int t) {            // input of layer l at step t = h of layer l - 1
     const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
     const float* sq = seq_ptr(X, t);
     if constexpr (R == 4) {
@@ -298,8 +327,8 @@ struct MpcPair {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
       if (ch < 2 || last) {
-        Ctx::cp_async16(op_ptr(img_hi, u_first + ch * 8), sq + (ch * 2) * 128);
-        Ctx::cp_async16(op_ptr(img_lo, u_first + ch * 8), sq + (ch * 2 + 1) * 128);
+        Ctx::cp_async16(op_ptr(img_hi, u_first + ch * 8), seq_piece(X, l - 1, t, ch, 0));
+        Ctx::cp_async16(op_ptr(img_lo, u_first + ch * 8), seq_piece(X, l - 1, t, ch, 1));
       }
     Ctx::cp_commit();
   }
@@ -317,8 +346,15 @@ struct MpcPair {
   }
 
   // hi/lo fp16 split of 2*NP values (already in the scaled domain) into NP consecutive TMEM operand columns of the own lane
+  // gp != nullptr (surrogate training): the pieces also go to the global dG image [26 pieces][128][16 B] (hi, then lo) of
+  // this (tile, layer, step); k0 = first k-slot (multiple of 8)
+  FC_HD_CTX void stg_dg_piece(float* gp, int k, F4 hi, F4 lo) const {
+    float* q = gp + (size_t)((k >> 3) * kTileP + row) * 4;
+    Ctx::stg4(q, hi);
+    Ctx::stg4(q + 26 * kTileP * 4, lo);
+  }
   template <int NP>
-  FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v) {
+  FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v, float* gp = nullptr, int k0 = 0) {
     float hi[NP], lo[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -326,10 +362,16 @@ struct MpcPair {
     }
     ctx.template tmem_st<NP>(col_hi, hi);
     ctx.template tmem_st<NP>(col_lo, lo);
+    if (gp) {
+#pragma unroll
+      for (int ch = 0; ch < NP / 4; ++ch)
+        stg_dg_piece(gp, k0 + ch * 8, F4{hi[ch * 4], hi[ch * 4 + 1], hi[ch * 4 + 2], hi[ch * 4 + 3]},
+                     F4{lo[ch * 4], lo[ch * 4 + 1], lo[ch * 4 + 2], lo[ch * 4 + 3]});
+    }
   }
   // the same into 2*NP halves of the shared-memory dG image (tile 1), k0 multiple of 8, NP multiple of 4
   template <int NP>
-  FC_HD_CTX void st_pairs_smem(int k0, const float* v) {
+  FC_HD_CTX void st_pairs_smem(int k0, const float* v, float* gp = nullptr) {
 #pragma unroll
     for (int ch = 0; ch < NP / 4; ++ch) {
       float hi[4], lo[4];
@@ -337,6 +379,7 @@ struct MpcPair {
       for (int i = 0; i < 4; ++i) {
         Ctx::split_h2(v[ch * 8 + 2 * i], v[ch * 8 + 2 * i + 1], hi[i], lo[i]);
       }
+      if (gp) stg_dg_piece(gp, k0 + ch * 8, F4{hi[0], hi[1], hi[2], hi[3]}, F4{lo[0], lo[1], lo[2], lo[3]});
       if constexpr (R == 1) {
         Ctx::sts4(op_ptr(0, k0 + ch * 8), F4{hi[0], hi[1], hi[2], hi[3]});
         Ctx::sts4(op_ptr(kOpGLoHalves, k0 + ch * 8), F4{lo[0], lo[1], lo[2], lo[3]});
@@ -403,6 +446,13 @@ struct MpcPair {
     const bool ok = b < p.B;
     float* rows = w_rows(X);
     const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
+    if (p.train) {                                           // surrogate training: the window is the sample itself
+      for (int r = 0; r < kLook; ++r)
+#pragma unroll
+        for (int f = 0; f < kFeat; ++f)
+          rows[(size_t)(r * kFeat + f) * kTileP + row] = ok ? p.tr_x[(size_t)b * (kLook * kFeat) + r * kFeat + f] : 0.f;
+      return;
+    }
     for (int r = 0; r < kLook; ++r)
 #pragma unroll
       for (int f = 0; f < kFeat; ++f) {
@@ -432,7 +482,7 @@ struct MpcPair {
       const float dg = denom_(g[i * 4 + 2] * ak.k2);
       float gi, gf, go, rg;
       quad_rcp(di, df, dq, dg, gi, gf, go, rg);
-      const float gg = tanh_from_(0.f, rg);
+      const float gg = tanh_from_(PT ? g[i * 4 + 2] * ak.kx : 0.f, rg);
       const float cp = first ? 0.f : c[j0 + i];
       cn[i] = fmaf(gf, cp, gi * gg);
       c[j0 + i] = cn[i];
@@ -488,12 +538,17 @@ struct MpcPair {
 #pragma unroll
     for (int f = 0; f < kFeat; ++f) xin[f] = Ctx::ldcg(rp + f * kTileP);
   }
-  FC_HD_CTX void store_features(int X, const float* xin) {
+  FC_HD_CTX void store_features(int X, const float* xin, int t) {
     const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
     float hi[4], lo[4];
     Ctx::split_h2(xin[0] * kScaleA, xin[1] * kScaleA, hi[0], lo[0]);
     Ctx::split_h2(xin[2] * kScaleA, xin[3] * kScaleA, hi[1], lo[1]);
     Ctx::split_h2(xin[4] * kScaleA, 0.f, hi[2], lo[2]);
+    if (p.train == 2) {                                      // layer-0 input of step t, kept for the weight-gradient kernel
+      float* fp = tr_tile(X) + kTrFeatOff + (size_t)t * kTrFeatSlot + (size_t)row * 4;
+      Ctx::stg4(fp, F4{hi[0], hi[1], hi[2], 0.f});
+      Ctx::stg4(fp + kTileP * 4, F4{lo[0], lo[1], lo[2], 0.f});
+    }
     if constexpr (R == 1) {
       Ctx::sts4(op_ptr(img_hi, 0), F4{hi[0], hi[1], hi[2], 0.f});
       Ctx::sts4(op_ptr(img_lo, 0), F4{lo[0], lo[1], lo[2], 0.f});
@@ -515,20 +570,26 @@ struct MpcPair {
     lap(18);
     if (!service) {
       st_units_zero(img_hi, img_lo, l == 0 ? kRec0 : kRec);
+      if constexpr (R == 1) if (p.train == 2) {               // slot 0 of the kept hidden sequence = zeros (h before step 0)
+        const F4 z = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          if (ch < 2 || last) { Ctx::stg4(seq_piece(X, l, -1, ch, 0), z); Ctx::stg4(seq_piece(X, l, -1, ch, 1), z); }
+      }
       if (l > 0) {
-        copy_input(X, 0);
+        copy_input(X, l, 0);
         Ctx::template cp_wait<0>();
       } else if (scalar) {
         float xin[kFeat];
         load_features(X, m, 0, xin);
-        store_features(X, xin);
+        store_features(X, xin, 0);
       }
       arrive_ready(X);
     } else if (scalar) {
       if (l == 0) {
         float xin[kFeat];
         load_features(X, m, 0, xin);
-        store_features(X, xin);
+        store_features(X, xin, 0);
       }
       arrive_ready(X);
     }
@@ -567,13 +628,13 @@ struct MpcPair {
     if (l == 0 && t + 1 < kLook) load_features(X, m, t + 1, xin);
     wait_full(X);
     if (t + 1 < kLook) {
-      if (l == 0) store_features(X, xin);
+      if (l == 0) store_features(X, xin, t + 1);
       arrive_ready(X);
     }
   }
 
   FC_HD_CTX void fwd_item(int X, int l, int m, int t) {
-    const int tmin = t_min_of(m);
+    const int tmin = tmin_of(m);
     float h[kOwn], xin[kFeat];
     lap(16);
     swap_cells();
@@ -584,7 +645,7 @@ struct MpcPair {
 #ifdef FC_ABL_NO_REC_TRAFFIC  // timing ablation only: every record lands in the same L2-resident slot
       rec_out = w_rec(X);
 #else
-      rec_out = w_rec(X) + (size_t)(rec_base(m) + (long)l * steps_kept(m) + (t - tmin)) * kRecFloatsP;
+      rec_out = w_rec(X) + (size_t)(recb_of(m) + (long)l * kept_of(m) + (t - tmin)) * kRecFloatsP;
 #endif
     const int ksteps = t == 0 ? (l == 0 ? 1 : 4) : kf_of(l) / 16;
     const float corr = Ctx::kAccTruncates ? acc_correction(ksteps, p.acc_comp) : 0.0f;
@@ -592,15 +653,15 @@ struct MpcPair {
     lap(17);
     wait_full(X);                                            // accumulator complete; operand free
     lap(1);
-    if (l > 0 && t + 1 < kLook) copy_input(X, t + 1);        // input block of step t+1: lands during the cell update
-    if (l == 0 && scalar && t + 1 < kLook) store_features(X, xin);
+    if (l > 0 && t + 1 < kLook) copy_input(X, l, t + 1);     // input block of step t+1: lands during the cell update
+    if (l == 0 && scalar && t + 1 < kLook) store_features(X, xin, t + 1);
     fwd_pointwise(X, t == 0, corr, h, rec_out);
     lap(24);
-    if (l + 1 < kLayers || t + 1 < kLook) {
+    if (l + 1 < kLayers || t + 1 < kLook || p.train == 2) {
       if constexpr (R == 1) {
         F4 hi4[3], lo4[3];
         split_units(h, kScaleA, hi4, lo4);
-        if (l + 1 < kLayers) stg_pieces(X, t, hi4, lo4);     // input of the layer above, already in operand format
+        if (l + 1 < kLayers || p.train == 2) stg_pieces(X, l, t, hi4, lo4);   // input of the layer above, already in operand format
         if (t + 1 < kLook) st_pieces(img_hi, img_lo, l == 0 ? kRec0 : kRec, hi4, lo4);
       } else {
         float w[6];
@@ -626,6 +687,13 @@ struct MpcPair {
 #pragma unroll
           for (int q = 0; q < 4; ++q) xq[q] = fmaf(fw[q * kHid + u_first + j], h[j], xq[q]);
         }
+      if (p.train == 1 && p.tr_hlast) {                       // top-layer hidden state of the last step: input of the fc gradients
+        const int b = (tile0 + X) * kRowsT + traj;
+        if (b < p.B)
+#pragma unroll
+          for (int j = 0; j < kOwn; ++j)
+            if (j < nown) p.tr_hlast[(size_t)b * kHid + u_first + j] = h[j];
+      }
       if constexpr (R == 1) {
         ctx.template tmem_st<4>(kColFcp + 12 * X + 4 * th, xq);
         ctx.tmem_st_wait();
@@ -652,7 +720,8 @@ struct MpcPair {
     ctx.tc_sync();                                           // read-out partial sums visible
     if (scalar)
       for (int X = 0; X < ntl; ++X) {
-        if (p.shadow) shadow_glue(X, m);
+        if (p.train) train_glue(X);
+        else if (p.shadow) shadow_glue(X, m);
         else fwd_glue(X, m);
       }
     lap(15);
@@ -662,6 +731,21 @@ struct MpcPair {
   // LSTM shadow roll-out (Functions.py:969-1011, 1196-1231): the window starts as ten copies of the first row; after
   // window m the surrogate output is logged and [output * scale_out / scale_in, u_{m+1}] becomes the newest row
   // ---------------------------------------------------------------------------------------------
+  // surrogate training: y = fc(h) of the window (Model_NN/Functions.py:338-340), and the seed of its reverse sweep
+  FC_HD_CTX void train_glue(int X) {
+    const float* sw = sm + kSmSmallP;
+    float fp[12];
+    readout_partials(X, fp);
+    const int b = (tile0 + X) * kRowsT + traj;
+    if (p.tr_y && b < p.B)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p.tr_y[(size_t)b * 4 + q] = ((fp[q] + fp[4 + q]) + fp[8 + q]) + sw[(kFCB - kFCW) + q];
+  }
+  FC_HD_CTX void train_seed(int X) {
+    const int b = (tile0 + X) * kRowsT + traj;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sm[kSmGxP + (X * 4 + q) * kTileP + traj] = b < p.B ? p.tr_dy[(size_t)b * 4 + q] : 0.f;
+  }
   FC_HD_CTX void load_tile_shadow(int X) {
     const int row = traj;                                    // per-trajectory arrays are indexed by the trajectory
     const int b = (tile0 + X) * kRowsT + traj;
@@ -899,7 +983,7 @@ struct MpcPair {
       if (t == kLook - 1) {
         float gxv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + traj] * p.g_scale;   // into the scaled domain
+        for (int q = 0; q < 4; ++q) gxv[q] = sm[kSmGxP + (X * 4 + q) * kTileP + traj] * gsc;   // into the scaled domain
 #pragma unroll
         for (int j = 0; j < kOwn; ++j) {
           const int u = u_first + j < kHid ? u_first + j : kHid - 1;
@@ -1010,21 +1094,22 @@ struct MpcPair {
   }
 
   FC_HD_CTX void bwd_item(int X, int l, int m, int t) {
-    const int tmin = t_min_of(m);
+    const int tmin = tmin_of(m);
     float dh[kOwn];
     lap(20);
     swap_cells();
     lap(11);
-    const float* rec_l = w_rec(X) + (size_t)(rec_base(m) + (long)l * steps_kept(m)) * kRecFloatsP;
+    const float* rec_l = w_rec(X) + (size_t)(recb_of(m) + (long)l * kept_of(m)) * kRecFloatsP;
     // HBM -> L2 for the next step of this tile (or the first step of the next layer / window)
     if (t - 1 >= tmin) prefetch_record(rec_l + (size_t)(t - 1 - tmin) * kRecFloatsP);
-    else if (l > 0) prefetch_record(w_rec(X) + (size_t)(rec_base(m) + (long)(l - 1) * steps_kept(m) + (kLook - 1 - tmin)) * kRecFloatsP);
+    else if (l > 0) prefetch_record(w_rec(X) + (size_t)(recb_of(m) + (long)(l - 1) * kept_of(m) + (kLook - 1 - tmin)) * kRecFloatsP);
     else if (m > 0) prefetch_record(w_rec(X) + (size_t)(rec_base(m - 1) + (long)(kLayers - 1) * steps_kept(m - 1) + (kLook - 1 - t_min_of(m - 1))) * kRecFloatsP);
 #ifdef FC_ABL_NO_REC_TRAFFIC
     const float* rp = w_rec(X) + ((size_t)uw * kRecF4 * 32 + lane) * 4;
 #else
     const float* rp = rec_l + (size_t)(t - tmin) * kRecFloatsP + ((size_t)uw * kRecF4 * 32 + lane) * 4;
 #endif
+    float* dg_out = p.train == 2 ? tr_tile(X) + kTrDgOff + (size_t)(l * kLook + t) * kTrDgSlot : nullptr;
     float rv[2][20];
     rec_load<4>(rp, 0, rv[0]);                             // first record group: in flight during the wait
     if constexpr (R == 4) { if (last) rec_load<2>(rp, 5, rv[1]); }
@@ -1039,7 +1124,7 @@ struct MpcPair {
         wait_full(X);                                      // MMA(X, l, t+1) complete
         lap(6);
         bwd_collect(X, l, t + 1, dh);
-        if (l == 0 && owner) bwd_collect_features(X, m, t + 1);
+        if (l == 0 && owner && !p.train) bwd_collect_features(X, m, t + 1);
 #pragma unroll
         for (int j = 0; j < kOwn; ++j) dh[j] += extra[j];
       }
@@ -1064,14 +1149,14 @@ struct MpcPair {
       else if (last) rec_load<2>(rp, 20, rv[(gi + 1) & 1]);
       float dg[16];
       bwd_units<4>(gi * 4, rv[gi & 1], dh, dg);
-      if (X == 0) st_pairs<8>(kColGhi + 2 * u_first + gi * 8, kColGlo + 2 * u_first + gi * 8, dg);
-      else st_pairs_smem<8>(4 * u_first + gi * 16, dg);
+      if (X == 0) st_pairs<8>(kColGhi + 2 * u_first + gi * 8, kColGlo + 2 * u_first + gi * 8, dg, dg_out, 4 * u_first + gi * 16);
+      else st_pairs_smem<8>(4 * u_first + gi * 16, dg, dg_out);
     }
     if (last) {
       float dg[8];
       bwd_units<2>(16, rv[0], dh, dg);
-      if (X == 0) st_pairs<4>(kColGhi + 2 * u_first + 32, kColGlo + 2 * u_first + 32, dg);
-      else st_pairs_smem<4>(4 * u_first + 64, dg);
+      if (X == 0) st_pairs<4>(kColGhi + 2 * u_first + 32, kColGlo + 2 * u_first + 32, dg, dg_out, 4 * u_first + 64);
+      else st_pairs_smem<4>(4 * u_first + 64, dg, dg_out);
     }
     if (X == 0) ctx.tmem_st_wait();
     lap(7);
@@ -1081,7 +1166,7 @@ struct MpcPair {
 
   // after the last step of a layer: collect the result of MMA(X, l, tmin)
   FC_HD_CTX void bwd_tail(int X, int l, int m, bool more_after) {
-    const int tmin = t_min_of(m);
+    const int tmin = tmin_of(m);
     if (service && warp != 0 && !scalar) return;
     lap(22);
     wait_full(X);
@@ -1095,7 +1180,7 @@ struct MpcPair {
       if (l > 0) {
         float dh[kOwn];
         bwd_collect(X, l, tmin, dh);                       // d(h) before the first kept step is not needed
-      } else if (owner) {
+      } else if (owner && !p.train) {
         bwd_collect_features(X, m, tmin);
       }
     }
@@ -1103,9 +1188,14 @@ struct MpcPair {
   }
 
   FC_HD_CTX void bwd_window(int m, bool more_after) {
-    const int tmin = t_min_of(m);
+    const int tmin = tmin_of(m);
     lap(21);
-    bwd_glue(m);
+    if (p.train) {
+      if (scalar)
+        for (int X = 0; X < ntl; ++X) train_seed(X);
+    } else {
+      bwd_glue(m);
+    }
     ctx.sync();
     lap(15);
     for (int l = kLayers - 1; l >= 0; --l) {
@@ -1205,7 +1295,10 @@ struct MpcPair {
       ctx.bar_init(kBarReady, kUpdWarps + (R == 1 ? 3 : 1));   // cell-update warps + warps 1..3 (R == 4: + warp 1)
       ctx.bar_init(kBarReady + 1, kUpdWarps + (R == 1 ? 3 : 1));
     }
-    for (int i = tid; i < kSmallFloats; i += kThreadsP) sm[kSmSmallP + i] = p.wpack[kSmallOff + i];
+    for (int i = tid; i < kSmallFloats; i += kThreadsP)
+      sm[kSmSmallP + i] = !p.train ? p.wpack[kSmallOff + i]
+                                   : (i < kOut * kHid ? p.tr_fcw[i] : (i < kOut * kHid + kOut ? p.tr_fcb[i - kOut * kHid] : 0.f));
+    if (p.train == 2) gsc = Ctx::ldcg(p.tr_scale);
     for (int i = tid; i < 4 * kNumFnnGrad; i += kThreadsP) reinterpret_cast<double*>(sm + kSmPgP)[i] = 0.0;
     if (tid == 0) *reinterpret_cast<double*>(sm + kSmRedP) = 0.0;
     for (int i = tid; i < kSmPgP - kSmRefP; i += kThreadsP) sm[kSmRefP + i] = 0.f;   // per-row arrays (R == 4 uses 32 rows of 128)
@@ -1224,9 +1317,9 @@ struct MpcPair {
         }
       ctx.sync();
       for (int m = 0; m < p.N; ++m) fwd_window(m, more);
-      if (!p.shadow) store_costs();
+      if (!p.shadow && !p.train) store_costs();
       if (p.with_grad) {
-        if (scalar)
+        if (scalar && !p.train)
           for (int X = 0; X < ntl; ++X) {
             float* grow = w_grow(X);
             for (int k = 0; k < p.N; ++k)
@@ -1236,7 +1329,7 @@ struct MpcPair {
         zero_dg_padding();
         ctx.sync();
         for (int m = p.N - 1; m >= 0; --m) bwd_window(m, more);
-        store_du0();
+        if (!p.train) store_du0();
       }
       ctx.tc_sync();
     }

@@ -150,6 +150,24 @@ FC_HD WorkLayoutP work_layout_p(int N, int with_grad) {
   return w;
 }
 
+// ---- surrogate training (MpcParams::train): per-TILE scratch handed to the weight-gradient kernel (fc_lstm_train_tc.cuh),
+// everything in operand format = [piece of 8 k-slots][128 samples][8 halves], hi image then lo image:
+//   hseq [3 layers][11 slots][2][7 pieces][128][16 B]   slot 0 = zeros (h before the first step), slot t + 1 = h_t
+//   feat [10 steps][2][128][16 B]                       the 5 window features of step t (k-slots 0..7 of layer 0)
+//   dG   [3 layers][10 steps][2][26 pieces][128][16 B]  gate gradients x g_scale, k = unit * 4 + gate
+constexpr int kTrHseqSlot = 2 * 7 * kTileP * 4;              // floats per (layer, slot)
+constexpr int kTrFeatSlot = 2 * kTileP * 4;
+constexpr int kTrDgSlot = 2 * 26 * kTileP * 4;
+constexpr size_t kTrHseqOff = 0;
+constexpr size_t kTrFeatOff = kTrHseqOff + (size_t)kLayers * (kLook + 1) * kTrHseqSlot;
+constexpr size_t kTrDgOff = kTrFeatOff + (size_t)kLook * kTrFeatSlot;
+constexpr size_t kTrTileFloats = kTrDgOff + (size_t)kLayers * kLook * kTrDgSlot;
+// per-tile workspace of the kernel itself in training mode: the roll-out layout with all 30 cell records of ONE window
+FC_HD size_t work_total_train() {
+  WorkLayoutP w = work_layout_p(1, 1);
+  return (w.rec + (size_t)kLayers * kLook * kRecFloatsP + 31) / 32 * 32;
+}
+
 // shared memory (floats)
 constexpr int kSmSmallP = 0;                                 // fc + fnn weights (456)
 constexpr int kSmRefP = kSmSmallP + kSmallFloats;            // [2][128]

@@ -91,6 +91,7 @@ class _LstmWindow(torch.autograd.Function):
                                       _native.ptr(out), _native.ptr(work), nbytes, _native.stream_ptr(dev))
         _native.check(rc, "fc_lstm_window_fwd")
         ctx.saved = save
+        ctx.path = int(L.fc_lstm_train_path_for(B))      # the backward may run on an autograd worker thread: same path there
         if save:
             ctx.save_for_backward(xc, pack, fc_w, work)
             ctx.shapes = [w.shape for w in ws]
@@ -107,9 +108,15 @@ class _LstmWindow(torch.autograd.Function):
         d = d_out.detach().to(torch.float32).contiguous()
         grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
         with torch.cuda.device(dev):
-            rc = L.fc_lstm_window_bwd(_native.ptr(xc), _native.ptr(d), _native.ptr(pack), _native.ptr(fc_w), B,
-                                      _native.ptr(work), work.numel(), *[_native.ptr(g) for g in grads],
-                                      _native.stream_ptr(dev))
+            prev = int(L.fc_lstm_train_path_for(B))
+            L.fc_lstm_train_select_path(ctx.path)
+            try:
+                rc = L.fc_lstm_window_bwd(_native.ptr(xc), _native.ptr(d), _native.ptr(pack), _native.ptr(fc_w), B,
+                                          _native.ptr(work), work.numel(), *[_native.ptr(g) for g in grads],
+                                          _native.stream_ptr(dev))
+            finally:
+                if prev != ctx.path:
+                    L.fc_lstm_train_select_path(0)
         _native.check(rc, "fc_lstm_window_bwd")
         return (None, None, *grads)
 

@@ -32,6 +32,17 @@ def cases():
     return np.load(os.path.join(GOLDEN, "surrogate_train_cases.npz"))
 
 
+@pytest.fixture(params=["ffma", "tensor-core"], autouse=True)
+def path(request):
+    """Every test runs against both implementations behind fc_lstm_window_fwd / _bwd: the FP32 FFMA kernels and the
+    tensor-core path (pair kernel in training mode + tcgen05 weight-gradient kernel); fc_lstm_train_select_path."""
+    from forging_control_b200 import _native
+    L = _native.lib()
+    assert L.fc_lstm_train_select_path({"ffma": 1, "tensor-core": 2}[request.param]) == 0
+    yield request.param
+    assert L.fc_lstm_train_select_path(0) == 0
+
+
 def _model(sd, dev):
     m = fb.LSTMModel(5, 50, 4, 3)
     m.load_state_dict({k: torch.tensor(np.asarray(v, np.float32)) for k, v in sd.items()}, strict=True)
