@@ -630,20 +630,25 @@ def run_ours(args):
         fp32 = {"achieved": achieved, "peak": fp32_peak / 1e12, "frac": achieved / (fp32_peak / 1e12), "unit": "TFLOP/s",
                 "peak_source": "fc_fp32_peak register-resident FFMA loop measured in this run (nominal 74.45)"}
         ncu = None
-        try:
-            ncu = json.load(open(os.path.join(REPO, "profiles", "r02_pair_kernel_ncu.json")))
-        except Exception:
-            pass
+        for f in ("r02b_pair_kernel_ncu.json", "r02_pair_kernel_ncu.json"):      # newest capture whose source hash matches
+            try:
+                c = json.load(open(os.path.join(REPO, "profiles", f)))
+            except Exception:
+                continue
+            if c.get("source_hash") == _source_hash():
+                ncu = c
+                break
         if use_tc:
             roof = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kind::f16 runs at the bf16 rate)"
                                     if peaks else "fallback 1.4 PFLOP/s dense bf16"),
                     "note": "gate contraction on tcgen05 with fp16 hi/lo split operands (three kind::f16 MMAs per fp32-accurate "
                             "product: the tensor pipe executes ~3.3x the algorithmic FLOPs, which caps this fraction near 0.30). "
-                            "What ncu says limits the kernel (profiles/r02_*): the per-trajectory cell update on the FP32/MUFU "
-                            "pipes runs with too few warps to cover its own latencies (mbarrier hand-shakes with the MMA of the "
-                            "other tile, TMEM round trips, activation-record loads in the reverse sweep), while the record "
-                            "traffic takes about half of the HBM peak (hbm.traffic_frac) and the tensor pipe is ~24 % active",
+                            "What the event trace and ncu say limits the kernel (profiles/r02b_*): the cell update on the FP32/MUFU "
+                            "pipes is bound by its instruction count (a sub-partition retires it at IPC ~0.7 whatever the warp "
+                            "count; 46 instructions per forward cell unit after the round-2 trim), its critical path is the "
+                            "18-unit warps (units split 16/16/18), the reverse sweep is co-bound by its 39-MMA chain; the record "
+                            "traffic takes about half of the HBM peak (hbm.traffic_frac) and the tensor pipe is ~25 % active",
                     "fp32_equivalent": fp32}
         else:
             roof = dict(fp32, bound="fp32")
@@ -694,41 +699,92 @@ def run_ours(args):
 
 
 def _extras(dev, fp32_peak):
-    """Secondary measurements of the widened rows, outside the timed regions of the headline metric: the
-    surrogate-training step (LSTMModel.forward + MSELoss + backward + DeviceAdamW through the module API, B = 65 536
-    device-resident samples, CUDA events, median of 5 after 2 warm-ups).  Never fatal for the bench line."""
+    """Secondary measurements of the widened rows and of the small-batch configurations, outside the timed
+    regions of the headline metric.  Never fatal for the bench line.
+      surrogate_train_step  LSTMModel.forward + MSELoss + backward + DeviceAdamW through the module API, B = 65 536
+                            device-resident samples, CUDA events, median of 5 after 2 warm-ups; automatic path (tensor cores
+                            for B >= 8192) and the FP32 FFMA kernels beside it
+      small_batches         BASELINE configs 1 (Main.py's own batch of 15, N = 10) and 2 (N = 5, B = 4096): one fused
+                            MPC-loss launch, automatic kernel choice (replica mode) and the one-tile kernel beside it"""
+    out = {}
     try:
-        import torch
         import forging_control_b200 as fb
+        from forging_control_b200 import _native
+        L = _native.lib()
         B = 65536
-        torch.manual_seed(0)
-        m = fb.LSTMModel(5, 50, 4, 3).to(dev)
-        opt = fb.DeviceAdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
-        mse = torch.nn.MSELoss()
         g = torch.Generator(device=dev).manual_seed(1)
         X = torch.rand(B, 10, 5, generator=g, device=dev) * 2 - 1
         y = torch.rand(B, 1, 4, generator=g, device=dev) * 2 - 1
-        ts = []
-        for i in range(7):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            opt.zero_grad()
-            loss = mse(m(X, dev), y.squeeze())
-            loss.backward()
-            opt.step()
-            e1.record()
-            torch.cuda.synchronize()
-            if i >= 2:
-                ts.append(e0.elapsed_time(e1))
-        ms = float(np.median(ts))
+        mse = torch.nn.MSELoss()
+        res = {}
+        for name, mode in (("auto", 0), ("ffma", 1)):
+            L.fc_lstm_train_select_path(mode)
+            torch.manual_seed(0)
+            m = fb.LSTMModel(5, 50, 4, 3).to(dev)
+            opt = fb.DeviceAdamW(m.parameters(), lr=1e-3, weight_decay=0.0)
+            ts = []
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                opt.zero_grad()
+                loss = mse(m(X, dev), y.squeeze())
+                loss.backward()
+                opt.step()
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            res[name] = (float(np.median(ts)), float(loss.item()), int(L.fc_lstm_window_workspace_bytes(B, 1)), int(L.fc_lstm_train_path_for(B)))
+        L.fc_lstm_train_select_path(0)
+        ms, lossv, wsb, path = res["auto"]
         flop = 3041200.0 * B
-        return {"surrogate_train_step": {"metric": "samples_per_s", "value": B / (ms * 1e-3), "ms_per_step": ms, "batch": B,
-                                         "loss": float(loss.item()), "fp32_roofline_frac": flop / (ms * 1e-3) / fp32_peak,
-                                         "flop_per_sample": 3041200.0,
-                                         "path": "LSTMModel.forward (fc_lstm_window_fwd) -> nn.MSELoss -> backward "
-                                                 "(fc_lstm_window_bwd) -> DeviceAdamW.step (fc_adamw_step)"}}
+        out["surrogate_train_step"] = {
+            "metric": "samples_per_s", "value": B / (ms * 1e-3), "ms_per_step": ms, "batch": B, "loss": lossv,
+            "fp32_equivalent_frac": flop / (ms * 1e-3) / fp32_peak, "flop_per_sample": 3041200.0,
+            "workspace_bytes_per_sample": wsb / B,
+            "path": ("tensor cores: fc::lstm_train_pair_kernel (forward; forward with records + reverse sweep) + fc::lt2::dw_kernel "
+                     "(tcgen05 weight gradients, MN-major operands)" if path == 2 else "FP32 FFMA kernels") +
+                    " behind LSTMModel.forward -> nn.MSELoss -> backward -> DeviceAdamW.step",
+            "ffma_kernels": {"value": B / (res["ffma"][0] * 1e-3), "ms_per_step": res["ffma"][0], "loss": res["ffma"][1],
+                             "fp32_roofline_frac": flop / (res["ffma"][0] * 1e-3) / fp32_peak}}
     except Exception as e:      # noqa: BLE001
-        return {"error": repr(e)[:300]}
+        out["surrogate_train_step"] = {"error": repr(e)[:300]}
+    try:
+        import forging_control_b200 as fb
+        from forging_control_b200 import _native
+        L = _native.lib()
+        lstm, fnn = _golden_weights()
+        sim = fb.LSTMModel(5, 50, 4, 3); sim.load_state_dict({k: torch.tensor(v) for k, v in lstm.items()})
+        ctl = fb.FNNModel(3, 50, 1, 1); ctl.load_state_dict({k: torch.tensor(v) for k, v in fnn.items()})
+        sim, ctl = sim.to(dev), ctl.to(dev)
+        wp = fb.pack_weights(sim, ctl)
+        rows = {}
+        for cname, N, B in (("config1_main_py_batch", 10, 15), ("config2", 5, 4096)):
+            g = torch.Generator().manual_seed(1)
+            X = (torch.rand(B, 3, generator=g) * 2 - 1).to(dev)
+            Z = (torch.rand(B, 10, 5, generator=g) * 2 - 1).to(dev)
+            with torch.no_grad():
+                u0 = ctl(X).reshape(-1).contiguous()
+            r = {"N": N, "B": B}
+            for kname, mode in (("auto", 0), ("one_tile_kernel", 2)):
+                L.fc_mpc_select_kernel(mode)
+                for _ in range(3):
+                    fb.mpc_loss_native(wp, X, u0, Z, N, ALPHA, True)
+                ts = []
+                for _ in range(7):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); o = fb.mpc_loss_native(wp, X, u0, Z, N, ALPHA, True); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                r[kname + "_ms"] = float(np.median(ts))
+                r[kname + "_loss"] = float(o["gl"][250])
+            L.fc_mpc_select_kernel(0)
+            r["trajectory_steps_per_s"] = B * N / (r["auto_ms"] * 1e-3)
+            rows[cname] = r
+        rows["kernel"] = "auto = replica mode of the pair kernel (32-trajectory tiles, fc::mpc_loss_replica_kernel) for B <= 32 x #SMs"
+        out["small_batches"] = rows
+    except Exception as e:      # noqa: BLE001
+        out["small_batches"] = {"error": repr(e)[:300]}
+    return out
 
 
 def main():

@@ -318,6 +318,14 @@ struct DevCtxTC : DevCtx {
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  // the same in two parts: announce the bytes once, then any number of copies onto the barrier
+  __device__ __forceinline__ void bulk_expect(int bar, int bytes) const {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + bar * 8), "r"((uint32_t)bytes) : "memory");
+  }
+  __device__ __forceinline__ void bulk_copy(float* dst, const float* src, int bytes, int bar) const {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"((uint32_t)bytes), "r"(bar0 + bar * 8) : "memory");
+  }
   // one thread: bulk (TMA) copy global -> shared, completion on an mbarrier
   __device__ __forceinline__ void bulk_load(float* dst, const float* src, int nfloats, int bar) const {
     const uint32_t baddr = bar0 + bar * 8;
@@ -518,7 +526,8 @@ static int ensure_smem_attributes();
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // kernel selection: 0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 kernel (one tile per CTA), 3 = tcgen05 pair kernel,
-// 4 = replica mode of the pair kernel (32-trajectory tiles).
+// 4 = replica mode of the pair kernel (32-trajectory tiles), 5 = pair kernel with the small-argument tanh polynomial (for a
+// surrogate whose cell values are tiny, e.g. freshly initialised weights: relative instead of absolute tanh accuracy, -7 %).
 // Thread-local: fc_mpc_select_kernel affects the calling thread's subsequent fc_mpc_loss* / workspace queries only
 // (no process-global state; the library stays re-entrant across threads and devices).
 static thread_local int g_mpc_mode = -1;
@@ -530,6 +539,7 @@ static int mpc_mode() {
     if (e && !strcmp(e, "tc")) g_mpc_mode = 2;
     if (e && !strcmp(e, "pair")) g_mpc_mode = 3;
     if (e && !strcmp(e, "replica")) g_mpc_mode = 4;
+    if (e && !strcmp(e, "pair-precise")) g_mpc_mode = 5;
   }
   return g_mpc_mode;
 }
@@ -537,6 +547,7 @@ static int mpc_mode() {
 struct MpcPlan {
   int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair, 3 = replica mode of the pair kernel
   int grid, tiles;
+  bool precise;         // pair kernel instantiation with the tanh polynomial
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
@@ -552,7 +563,8 @@ static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1)
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int mode = mpc_mode();
-  pl->kind = mode == 1 ? 0 : (mode == 3 ? 2 : (mode == 4 ? 3 : 1));
+  pl->kind = mode == 1 ? 0 : (mode == 3 || mode == 5 ? 2 : (mode == 4 ? 3 : 1));
+  pl->precise = mode == 5;
   {
     const int t128 = (B + tc::kTileTC - 1) / tc::kTileTC;
     // more tiles than SMs: two tiles per CTA overlap tensor and cell-update work; a single tile: the two-tile kernels'
@@ -560,7 +572,7 @@ static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1)
     if (mode == 0 && (t128 > sms || t128 == 1)) pl->kind = 2;
     if (mode == 0 && B <= (pr::kTileP / 4) * sms) pl->kind = 3;
   }
-  if (width_dim > 1) pl->kind = 1;        // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
+  if (width_dim > 1) { pl->kind = 1; pl->precise = false; }   // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
   const int tile = pl->kind == 3 ? pr::kTileP / 4 : (pl->kind ? tc::kTileTC : kTile);
   pl->tiles = (B + tile - 1) / tile;
   const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
@@ -672,8 +684,8 @@ int fc_pack_weights(const float* w_ih0, const float* w_hh0, const float* w_ih1, 
 }
 
 int fc_mpc_select_kernel(int mode) {
-  if (mode < 0 || mode > 4)
-    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05), 3 (tcgen05 pair) or 4 (replica)");
+  if (mode < 0 || mode > 5)
+    return fail(FC_ERR_BAD_SHAPE, "fc_mpc_select_kernel: mode%s must be 0 (auto), 1 (ffma), 2 (tcgen05), 3 (tcgen05 pair), 4 (replica) or 5 (pair, precise tanh)");
   g_mpc_mode = mode;
   return FC_OK;
 }
@@ -798,6 +810,7 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   p.noise_std = noise_std; p.noise_seed = noise_seed;
   cudaStream_t st = (cudaStream_t)stream;
   if (pl.kind == 3) mpc_loss_replica_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+  else if (pl.kind == 2 && pl.precise) lstm_train_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
   else if (pl.kind == 2) mpc_loss_pair_kernel<<<pl.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
   else if (pl.kind == 1) mpc_loss_tc_kernel<<<pl.grid, tc::kThreadsTC, width_dim > 1 ? tc::kSmBytesWide : tc::kSmBytesTC, st>>>(p);
   else mpc_loss_kernel<<<pl.grid, kThreads, kSmBytes, st>>>(p);
@@ -1026,7 +1039,7 @@ static int lstm_tc_plan(int B, int save, LstmTcPlan* pl) {
   pl->tiles = (B + pr::kTileP - 1) / pr::kTileP;
   const int pairs = (pl->tiles + pr::kTiles - 1) / pr::kTiles;
   pl->grid = pairs < sms ? pairs : sms;
-  pl->chunk_tiles = pl->tiles < 2 * pr::kTiles * sms ? pl->tiles : 2 * pr::kTiles * sms;   // two passes of the pair kernel per chunk
+  pl->chunk_tiles = pl->tiles < pr::kTiles * sms ? pl->tiles : pr::kTiles * sms;   // one pass of the pair kernel per chunk
   const size_t work_cta = pr::kTiles * (save ? pr::work_total_train() : pr::work_layout_p(1, 0).total);
   size_t o = 0;
   pl->scale = o;   o += 4;

@@ -62,8 +62,10 @@ size_t fc_mpc_loss_workspace_bytes(int B, int N, int with_grad);
 /* Kernel behind fc_mpc_loss: 0 = automatic (B <= 32 x #SMs: the replica mode of the pair kernel, 32-trajectory tiles;
  * up to #SMs tiles of 128 trajectories: the one-tile tcgen05 kernel; beyond: the two-tile tcgen05 pair kernel; measured
  * fastest), 1 = always the FP32 FFMA kernel, 2 = always the one-tile tcgen05 kernel, 3 = always the pair kernel,
- * 4 = always the replica mode.  Also settable with the environment variable FC_MPC_KERNEL=ffma|tc|pair|replica before
- * the first call.  All kernels meet the same parity bar.                                            */
+ * 4 = always the replica mode, 5 = the pair kernel with the small-argument tanh polynomial (relative instead of absolute
+ * tanh accuracy: for a surrogate with tiny cell values such as freshly initialised weights; 7 % slower).  Also settable
+ * with the environment variable FC_MPC_KERNEL=ffma|tc|pair|replica|pair-precise before the first call.  All kernels meet
+ * the same parity bar on the reference's shipped weights.                                              */
 int fc_mpc_select_kernel(int mode);
 
 /* Scratch traffic (bytes) of one with_grad launch for (B, N), computed from the workspace layout of the kernel the

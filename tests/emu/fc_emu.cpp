@@ -64,12 +64,14 @@ struct EmuCtx {
 struct EmuBlockTC : EmuBlock {
   std::vector<float> tmem;
   std::atomic<unsigned> bars[8];      // arrivals
+  std::atomic<int> tx[8];             // pending bytes of split bulk copies (bulk_expect / bulk_copy)
   unsigned counts[8];                 // arrivals per phase
   std::vector<std::unique_ptr<std::barrier<>>> wbar;   // one barrier per warp (__syncwarp)
   EmuBlockTC(int b, int n, int smem_floats = fc::tc::kSmFloatsTC, int nthreads = fc::tc::kThreadsTC)
       : EmuBlock(b, n, nthreads), tmem(128 * 512, 0.f) {
     smem.assign(smem_floats, 0.f);
     for (auto& x : bars) x.store(0);
+    for (auto& x : tx) x.store(0);
     for (auto& x : counts) x = 1;
     for (int w = 0; w < nthreads / 32; ++w) wbar.emplace_back(new std::barrier<>(32));
   }
@@ -146,6 +148,12 @@ struct EmuCtxTC : EmuCtx {
           s += (double)h_val(ah[(k / 8) * (128 * 8) + m * 8 + (k & 7)]) * (double)h_val(bh[(k / 8) * (n_img * 8) + j * 8 + (k & 7)]);
         tb->tmem[m * 512 + d_col + j] = (float)s;
       }
+  }
+  // transaction count of the mbarrier: the arrival is published when the announced bytes have landed
+  void bulk_expect(int bar, int bytes) const { tb->tx[bar].fetch_add(bytes); }
+  void bulk_copy(float* dst, const float* src, int bytes, int bar) const {
+    std::memcpy(dst, src, (size_t)bytes);
+    if (tb->tx[bar].fetch_sub(bytes) == bytes) tb->bars[bar].fetch_add(1);
   }
   void bulk_load(float* dst, const float* src, int nfloats, int bar) const {
     std::memcpy(dst, src, (size_t)nfloats * 4);
