@@ -1201,7 +1201,7 @@ int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, co
     double* fcp = reinterpret_cast<double*>(wf + tp.fcp);
     lt2::fc_grad_partial_kernel<<<kFcGradBlocksPerSm * sms, 256, 0, st>>>(wf + tp.hlast, d_out, B, fcp);
     FC_CUDA(cudaGetLastError(), "fc_grad_partial_kernel launch");
-    lt2::fc_grad_reduce_kernel<<<1, 256, 0, st>>>(fcp, kFcGradBlocksPerSm * sms, g_fc_w, g_fc_b);
+    lt2::fc_grad_reduce_kernel<<<lt2::kFcGradN, 64, 0, st>>>(fcp, kFcGradBlocksPerSm * sms, g_fc_w, g_fc_b);
     FC_CUDA(cudaGetLastError(), "fc_grad_reduce_kernel launch");
     return FC_OK;
   }

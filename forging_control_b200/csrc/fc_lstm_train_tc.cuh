@@ -21,12 +21,13 @@
 namespace fc {
 namespace lt2 {
 
-constexpr int kStageRows = 64;                       // samples per pipeline stage (half a tile)
+constexpr int kStageRows = 32;                       // samples per pipeline stage (a quarter of a tile)
+constexpr int kStagesPerTile = pr::kTileP / kStageRows;
 constexpr int kDgPieces = 26, kActPieces = 14;       // k-slot pieces of 8: 208 gate gradients; 56 input + 56 recurrent slots
 constexpr int kStDgBytes = kDgPieces * kStageRows * 16;     // one of hi / lo
 constexpr int kStActBytes = kActPieces * kStageRows * 16;
-constexpr int kStageBytes = 2 * (kStDgBytes + kStActBytes); // dG hi | dG lo | act hi | act lo = 81 920
-constexpr int kStages = 2;
+constexpr int kStageBytes = 2 * (kStDgBytes + kStActBytes); // dG hi | dG lo | act hi | act lo = 40 960
+constexpr int kStages = 5;                           // 200 KiB of operands in flight per SM (two 80 KiB stages left the HBM at 50 %)
 constexpr int kDwThreads = 320;                      // warps 0..7 epilogue, 8 producer, 9 MMA issuer
 constexpr int kDwSmem = kStages * kStageBytes + 1024;
 constexpr int kDwRows = 256, kDwCols = 112;          // partial [3 layers][256 operand rows][112]
@@ -36,7 +37,7 @@ constexpr size_t kDwPartialFloats = (size_t)kLayers * kDwRows * kDwCols;
 // cell steps (S = 48: 6.7 ulp, compensated to a fraction of an ulp) instead of once per (tile, layer) (S = 240: 33 ulp).
 constexpr int kSegSteps = 2;
 constexpr int kSegs = kLook / kSegSteps;             // accumulator segments per (tile, layer)
-constexpr int kAccSteps = kSegSteps * 2 * 4 * 3;     // MMA accumulation steps per segment: steps x 2 stages x 4 k-steps x 3 terms
+constexpr int kAccSteps = kSegSteps * (pr::kTileP / 16) * 3;   // MMA accumulation steps per segment: steps x 8 k-steps of 16 samples x 3 terms
 
 struct DwParams {
   const float* ws;        // per-tile scratch written by the pair kernel (pr::kTrTileFloats floats per tile)
@@ -70,10 +71,11 @@ __device__ __forceinline__ void umma_mn(uint32_t d, uint64_t ad, uint64_t bd, ui
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
 }
 
-// barriers: full[s] 0..1, empty[s] 2..3, dfull[b] 4..5, dempty[b] 6..7
+// barriers: full[s] 0..kStages-1, empty[s] kStages.., dfull[b], dempty[b]
+constexpr int kBarEmpty = kStages, kBarDFull = 2 * kStages, kBarDEmpty = 2 * kStages + 2, kDwBars = 2 * kStages + 4;
 __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
   extern __shared__ __align__(1024) unsigned char dsm[];
-  __shared__ __align__(8) unsigned long long bars[8];
+  __shared__ __align__(8) unsigned long long bars[kDwBars];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -83,8 +85,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar0 + s * 8, 1); mbar_init(bar0 + (2 + s) * 8, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar0 + (4 + b) * 8, 1); mbar_init(bar0 + (6 + b) * 8, 8); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar0 + s * 8, 1); mbar_init(bar0 + (kBarEmpty + s) * 8, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar0 + (kBarDFull + b) * 8, 1); mbar_init(bar0 + (kBarDEmpty + b) * 8, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -100,32 +102,29 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
       for (int i = 0; i < ntile; ++i) {
         const float* tw = p.ws + (size_t)(blockIdx.x + (size_t)i * gridDim.x) * pr::kTrTileFloats;
         for (int t = 0; t < kLook; ++t)
-          for (int h = 0; h < 2; ++h, ++it) {
-            const int s = it & 1;
-            const uint32_t full = bar0 + s * 8, empty = bar0 + (2 + s) * 8;
-            if (it >= kStages) mbar_wait(empty, ((it >> 1) - 1) & 1);
+          for (int h = 0; h < kStagesPerTile; ++h, ++it) {
+            const int s = it % kStages;
+            const uint32_t full = bar0 + s * 8, empty = bar0 + (kBarEmpty + s) * 8;
+            if (it >= kStages) mbar_wait(empty, ((it / kStages) - 1) & 1);
             const uint32_t st = sbase + s * kStageBytes;
             const int nin = l == 0 ? 1 : 7;                        // input pieces (layer 0: the feature piece)
-            const int ncopy = 2 * kDgPieces + 2 * (nin + 7);
-            if (lane == 0) mbar_expect(full, (uint32_t)ncopy * 1024u);
+            const uint32_t in_bytes = (uint32_t)nin * kStageRows * 16u, rc_bytes = 7u * kStageRows * 16u;
+            if (lane == 0) mbar_expect(full, 2u * kStDgBytes + 2u * (in_bytes + rc_bytes));
             __syncwarp();
+            // the pair kernel stores every image stage-major ([hi | lo][stage][piece][32 rows][16 B]): six bulk copies per stage
             const float* dgb = tw + pr::kTrDgOff + (size_t)(l * kLook + t) * pr::kTrDgSlot;
             const float* inb = l == 0 ? tw + pr::kTrFeatOff + (size_t)t * pr::kTrFeatSlot
                                       : tw + pr::kTrHseqOff + (size_t)((l - 1) * (kLook + 1) + t + 1) * pr::kTrHseqSlot;
             const float* rcb = tw + pr::kTrHseqOff + (size_t)(l * (kLook + 1) + t) * pr::kTrHseqSlot;       // h_{t-1} (slot 0 = zeros)
-            for (int c = lane; c < ncopy; c += 32) {
-              const float* src; uint32_t dst;
-              if (c < 2 * kDgPieces) {
-                const int hl = c / kDgPieces, P = c - hl * kDgPieces;
-                src = dgb + (size_t)hl * (kDgPieces * pr::kTileP * 4) + (size_t)(P * pr::kTileP + h * kStageRows) * 4;
-                dst = st + hl * kStDgBytes + P * 1024;
-              } else {
-                const int c2 = c - 2 * kDgPieces, hl = c2 / (nin + 7), P = c2 - hl * (nin + 7);
-                if (P < nin) src = inb + (size_t)hl * ((l == 0 ? 1 : 7) * pr::kTileP * 4) + (size_t)(P * pr::kTileP + h * kStageRows) * 4;
-                else src = rcb + (size_t)hl * (7 * pr::kTileP * 4) + (size_t)((P - nin) * pr::kTileP + h * kStageRows) * 4;
-                dst = st + 2 * kStDgBytes + hl * kStActBytes + P * 1024;
-              }
-              bulk_g2s(dst, src, 1024u, full);
+            if (lane < 2) {
+              bulk_g2s(st + lane * kStDgBytes, dgb + (size_t)lane * (kDgPieces * pr::kTileP * 4) + (size_t)h * (kDgPieces * kStageRows * 4),
+                       (uint32_t)kStDgBytes, full);
+            } else if (lane < 4) {
+              const int hl = lane - 2;
+              bulk_g2s(st + 2 * kStDgBytes + hl * kStActBytes, inb + (size_t)hl * (nin * pr::kTileP * 4) + (size_t)h * (nin * kStageRows * 4), in_bytes, full);
+            } else if (lane < 6) {
+              const int hl = lane - 4;
+              bulk_g2s(st + 2 * kStDgBytes + hl * kStActBytes + in_bytes, rcb + (size_t)hl * (7 * pr::kTileP * 4) + (size_t)h * (7 * kStageRows * 4), rc_bytes, full);
             }
           }
       }
@@ -137,15 +136,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int i = 0; i < ntile; ++i) {
         for (int t = 0; t < kLook; ++t)
-          for (int h = 0; h < 2; ++h, ++it) {
+          for (int h = 0; h < kStagesPerTile; ++h, ++it) {
             if (t % kSegSteps == 0 && h == 0) {                              // new accumulator segment
               if (t > 0 || i > 0 || l > 0) ++nd;
-              if (nd >= 2) mbar_wait(bar0 + (6 + (nd & 1)) * 8, ((nd >> 1) - 1) & 1);   // accumulator buffer drained
+              if (nd >= 2) mbar_wait(bar0 + (kBarDEmpty + (nd & 1)) * 8, ((nd >> 1) - 1) & 1);   // accumulator buffer drained
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const int b = nd & 1;
-            const int s = it & 1;
-            mbar_wait(bar0 + s * 8, (it >> 1) & 1);                           // stage landed
+            const int s = it % kStages;
+            mbar_wait(bar0 + s * 8, (it / kStages) & 1);                      // stage landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
               const uint32_t st = sbase + s * kStageBytes;
@@ -163,8 +162,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
 #pragma unroll
                 for (int ks = 0; ks < kStageRows / 16; ++ks) umma_mn(d, mn_desc(g_hi + moff + ks * 256), mn_desc(a_hi + ks * 256), idesc, 1u);
               }
-              umma_commit(bar0 + (2 + s) * 8);                                 // stage free once these MMAs have read it
-              if (t % kSegSteps == kSegSteps - 1 && h == 1) umma_commit(bar0 + (4 + b) * 8);   // accumulator segment complete
+              umma_commit(bar0 + (kBarEmpty + s) * 8);                         // stage free once these MMAs have read it
+              if (t % kSegSteps == kSegSteps - 1 && h == kStagesPerTile - 1) umma_commit(bar0 + (kBarDFull + b) * 8);   // segment complete
             }
             __syncwarp();
           }
@@ -183,7 +182,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
       for (int c = 0; c < kDwCols; ++c) acc[c] = 0.f;
       for (int i = 0; i < ntile * kSegs; ++i, ++nd) {
         const int b = nd & 1;
-        mbar_wait(bar0 + (4 + b) * 8, (nd >> 1) & 1);
+        mbar_wait(bar0 + (kBarDFull + b) * 8, (nd >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c0 = 0; c0 < kDwCols; c0 += 16) {
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + (6 + b) * 8);
+        if (lane == 0) mbar_arrive(bar0 + (kBarDEmpty + b) * 8);
       }
       float* o = out + ((size_t)l * kDwRows + (size_t)(128 * mh + 32 * q + lane)) * kDwCols;
 #pragma unroll
@@ -282,12 +281,18 @@ __global__ void __launch_bounds__(256) fc_grad_partial_kernel(const float* __res
     partial[(size_t)blockIdx.x * 256 + tid] = a;
   }
 }
-__global__ void fc_grad_reduce_kernel(const double* __restrict__ partial, int grid, float* __restrict__ g_fc_w, float* __restrict__ g_fc_b) {
-  const int tid = threadIdx.x;
-  if (tid >= kFcGradN) return;
+__global__ void __launch_bounds__(64) fc_grad_reduce_kernel(const double* __restrict__ partial, int grid, float* __restrict__ g_fc_w, float* __restrict__ g_fc_b) {
+  const int o = blockIdx.x;                                  // one block per output element
+  __shared__ double red[2];
   double a = 0.0;
-  for (int b = 0; b < grid; ++b) a += partial[(size_t)b * 256 + tid];
-  if (tid < kOut * kHid) g_fc_w[tid] = (float)a; else g_fc_b[tid - kOut * kHid] = (float)a;
+  for (int b = threadIdx.x; b < grid; b += 64) a += partial[(size_t)b * 256 + o];
+  for (int k = 16; k; k >>= 1) a += __shfl_xor_sync(0xffffffffu, a, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = red[0] + red[1];
+    if (o < kOut * kHid) g_fc_w[o] = (float)a; else g_fc_b[o - kOut * kHid] = (float)a;
+  }
 }
 
 }  // namespace lt2

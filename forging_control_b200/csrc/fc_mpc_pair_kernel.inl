@@ -312,7 +312,8 @@ struct MpcPair {
   // piece ch (hi / lo) of the hidden state of layer l at step t: thread-private slot of the per-CTA scratch, or (training
   // with the reverse sweep) its place in the operand-format hidden sequence kept for the weight-gradient kernel
   FC_HD_CTX float* seq_piece(int X, int l, int t, int ch, int hl) const {
-    if (p.train == 2) return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kTileP * 4) + (size_t)((2 * th + ch) * kTileP + row) * 4;
+    if (p.train == 2)   // [hi | lo][32-sample stage = TMEM quadrant][7 pieces][32 rows][16 B]: a stage of the weight-gradient kernel is contiguous
+      return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kTileP * 4) + (size_t)(quad * (7 * 32) + (2 * th + ch) * 32 + lane) * 4;
     return seq_ptr(X, t) + (ch * 2 + hl) * 128;
   }
   FC_HD_CTX void stg_pieces(int X, int l, int t, const F4* hi4, const F4* lo4) {
@@ -362,7 +363,7 @@ struct MpcPair {
   // gp != nullptr (surrogate training): the pieces also go to the global dG image [26 pieces][128][16 B] (hi, then lo) of
   // this (tile, layer, step); k0 = first k-slot (multiple of 8)
   FC_HD_CTX void stg_dg_piece(float* gp, int k, F4 hi, F4 lo) const {
-    float* q = gp + (size_t)((k >> 3) * kTileP + row) * 4;
+    float* q = gp + (size_t)(quad * (26 * 32) + (k >> 3) * 32 + lane) * 4;     // [stage][26 pieces][32 rows][16 B]
     Ctx::stg4(q, hi);
     Ctx::stg4(q + 26 * kTileP * 4, lo);
   }

@@ -152,9 +152,10 @@ FC_HD WorkLayoutP work_layout_p(int N, int with_grad) {
 
 // ---- surrogate training (MpcParams::train): per-TILE scratch handed to the weight-gradient kernel (fc_lstm_train_tc.cuh),
 // everything in operand format = [piece of 8 k-slots][128 samples][8 halves], hi image then lo image:
-//   hseq [3 layers][11 slots][2][7 pieces][128][16 B]   slot 0 = zeros (h before the first step), slot t + 1 = h_t
-//   feat [10 steps][2][128][16 B]                       the 5 window features of step t (k-slots 0..7 of layer 0)
-//   dG   [3 layers][10 steps][2][26 pieces][128][16 B]  gate gradients x g_scale, k = unit * 4 + gate
+//   hseq [3 layers][11 slots][2][4 stages][7 pieces][32][16 B]   slot 0 = zeros (h before the first step), slot t + 1 = h_t
+//   feat [10 steps][2][128][16 B]                                the 5 window features of step t (k-slots 0..7 of layer 0)
+//   dG   [3 layers][10 steps][2][4 stages][26 pieces][32][16 B]  gate gradients x g_scale, k = unit * 4 + gate
+// (stage = 32 samples = one TMEM quadrant: what one pipeline stage of the weight-gradient kernel loads is contiguous)
 constexpr int kTrHseqSlot = 2 * 7 * kTileP * 4;              // floats per (layer, slot)
 constexpr int kTrFeatSlot = 2 * kTileP * 4;
 constexpr int kTrDgSlot = 2 * 26 * kTileP * 4;
