@@ -1,4 +1,5 @@
-"""Randomised cross-check of the three kernels behind fc_mpc_loss (FFMA / one-tile tcgen05 / pair) on odd shapes:
+"""Randomised cross-check of the kernels behind fc_mpc_loss (FFMA / one-tile tcgen05 / pair / replica / pair with the tanh
+polynomial) on odd shapes:
 every output of every kernel must agree with the FFMA kernel to fp32 round-off (kink flips excepted on du0)."""
 import os, sys
 import numpy as np, torch
@@ -11,7 +12,7 @@ W = np.load(os.path.join(REPO, "tests/golden/weights.npz"))
 dev = torch.device("cuda:0")
 L = _native.lib()
 rng = np.random.default_rng(2025)
-shapes = [(1, 1), (2, 3), (127, 2), (128, 1), (129, 4), (255, 11), (256, 2), (257, 3), (300, 25), (1000, 1), (18943, 2), (18944, 3),
+shapes = [(1, 1), (2, 3), (31, 2), (32, 3), (33, 2), (65, 5), (127, 2), (128, 1), (129, 4), (255, 11), (256, 2), (257, 3), (300, 25), (1000, 1), (18943, 2), (18944, 3),
           (18945, 2), (37887, 2), (37889, 3), (50000, 7)]
 worst = 0.0
 for i, (B, N) in enumerate(shapes):
@@ -27,13 +28,13 @@ for i, (B, N) in enumerate(shapes):
     with torch.no_grad(): u0 = ctl(X).reshape(-1).contiguous()
     wg = bool(i % 5 != 4)
     outs = {}
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4, 5):
         L.fc_mpc_select_kernel(mode)
         outs[mode] = {k: (v.clone() if v is not None else None) for k, v in fb.mpc_loss_native(wp, X, u0, Z, N, 20.0, wg).items()}
     torch.cuda.synchronize()
     ref = outs[1]
     msg = [f"B={B} N={N} {tag} wg={wg}"]
-    for mode in (2, 3):
+    for mode in (2, 3, 4, 5):
         o = outs[mode]
         e = {k: float((o[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-30)) for k in ("cost", "pred", "command", "error")}
         e["loss"] = float(abs(o["gl"][250] - ref["gl"][250]) / abs(ref["gl"][250]))

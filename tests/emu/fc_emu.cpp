@@ -412,6 +412,44 @@ int fc_emu_lstm_shadow_replica(const float* row0, const float* u, const float* r
   return emu_lstm_shadow_pair<4>(row0, u, ratio, wpack, B, T, grid, y);
 }
 
+// surrogate training on the pair-kernel source (MpcParams::train): mode 1 = forward (y, h_last), mode 2 = forward with
+// records + reverse sweep seeded by dy, which fills the per-tile scratch (gate gradients / hidden sequences / features in
+// operand format) that the tcgen05 weight-gradient kernel consumes; ws must hold tiles * fc_emu_train_tile_floats() floats
+long fc_emu_train_tile_floats() { return (long)fc::pr::kTrTileFloats; }
+int fc_emu_lstm_train(int mode, const float* X, const float* dy, const float* wpack, const float* fc_w, const float* fc_b, int B,
+                      float g_scale, int grid, float* y /*[B][4]*/, float* hlast /*[B][50]*/, float* ws) {
+  fc::MpcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.wpack = wpack;
+  p.B = B; p.N = 1; p.with_grad = mode == 2 ? 1 : 0;
+  p.acc_comp = 1.0f; p.g_scale = p.g_unscale = 1.0f;
+  p.train = mode; p.tr_x = X; p.tr_y = mode == 1 ? y : nullptr; p.tr_hlast = mode == 1 ? hlast : nullptr; p.tr_dy = dy;
+  p.tr_fcw = fc_w; p.tr_fcb = fc_b;
+  float scale[2] = {g_scale, 1.0f / g_scale};
+  p.tr_scale = scale; p.tr_ws = ws; p.tr_tile_base = 0;
+  p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;
+  const int npairs = (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles;
+  if (grid > npairs) grid = npairs;
+  p.work_stride = fc::pr::kTiles * (mode == 2 ? fc::pr::work_total_train() : fc::pr::work_layout_p(1, 0).total);
+  std::vector<float> work((size_t)grid * p.work_stride, 0.f);
+  std::vector<double> partial((size_t)grid * fc::kPartialStride, 0.0);
+  p.work = work.data();
+  p.partial = partial.data();
+  for (int b = 0; b < grid; ++b) {
+    EmuBlockTC blk(b, grid, fc::pr::kSmFloatsP);
+    std::vector<std::thread> th;
+    th.reserve(fc::pr::kThreadsP);
+    for (int t = 0; t < fc::pr::kThreadsP; ++t)
+      th.emplace_back([&blk, &p, t]() {
+        EmuCtxTC ctx(&blk, t);
+        fc::pr::MpcPair<EmuCtxTC, 1, true> k(ctx, p);
+        k.run();
+      });
+    for (auto& x : th) x.join();
+  }
+  return 0;
+}
+
 // one-tile tcgen05 kernel with a wide controller (width_dim > 1): gl_wide [2560] = d fc_int.weight | d fc_int.bias
 int fc_emu_mpc_loss_tc_wide(const float* X, const float* u0, const float* Z, const float* wpack, const float* int_w,
                             const float* int_b, int width_dim, int B, int N, float alpha, long long B_global, int with_grad,
