@@ -360,6 +360,13 @@ __global__ void __launch_bounds__(pr::kThreadsP, 1) lstm_train_pair_kernel(const
   k.run();
 }
 
+// ... and its replica mode (32-sample tiles) for small training batches
+__global__ void __launch_bounds__(pr::kThreadsP, 1) lstm_train_replica_kernel(const MpcParams p) {
+  DevCtxTC ctx;
+  pr::MpcPair<DevCtxTC, 4, true> k(ctx, p);
+  k.run();
+}
+
 }  // namespace fc
 #include "fc_lstm_train_tc.cuh"
 namespace fc {
@@ -640,6 +647,8 @@ static int ensure_smem_attributes() {
           "cudaFuncSetAttribute(smem, replica)");
   FC_CUDA(cudaFuncSetAttribute(lstm_train_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
           "cudaFuncSetAttribute(smem, training)");
+  FC_CUDA(cudaFuncSetAttribute(lstm_train_replica_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::kSmBytesP),
+          "cudaFuncSetAttribute(smem, training replica)");
   FC_CUDA(cudaFuncSetAttribute(lt2::dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt2::kDwSmem),
           "cudaFuncSetAttribute(smem, dw)");
   FC_CUDA(cudaFuncSetAttribute(lt::lstm_window_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt::kSmemFwd),
@@ -1012,9 +1021,10 @@ int fc_lstm_train_pack(const float* w_ih0, const float* w_hh0, const float* w_ih
   return FC_OK;
 }
 
-// ---- tensor-core path of the surrogate training step (fc_lstm_train_tc.cuh): pair kernel in training mode + dw_kernel.
-// Chosen for large batches (the FFMA kernels keep the small ones, where seven 40-sample tiles fill more SMs than one
-// 256-sample tile pair); FC_LSTM_TRAIN=tc|ffma forces one of them.
+// ---- tensor-core path of the surrogate training step (fc_lstm_train_tc.cuh): pair kernel in training mode (its replica
+// mode with 32-sample tiles for B <= 32 x #SMs) + dw_kernel.  The automatic choice: measured faster than the FFMA kernels at
+// every batch size (whole training step B = 256: 0.48 ms against 0.63 ms, 4 096: 0.49 / 0.65, 8 192: 1.08 / 1.23, 65 536:
+// 2.7 / 7.1); FC_LSTM_TRAIN=tc|ffma or fc_lstm_train_select_path force one of them.
 static thread_local int g_lstm_mode = -1;
 static int lstm_tc_mode() {
   if (g_lstm_mode < 0) {
@@ -1025,30 +1035,35 @@ static int lstm_tc_mode() {
   }
   return g_lstm_mode;
 }
-static bool lstm_use_tc(int B) { const int m = lstm_tc_mode(); return m == 2 || (m == 0 && B >= 8192); }
+static bool lstm_use_tc(int B) { (void)B; return lstm_tc_mode() != 1; }
 
 static constexpr int kFcGradBlocksPerSm = 8;
 struct LstmTcPlan {
-  int tiles, grid, chunk_tiles;                 // 128-sample tiles, CTAs of the pair kernel, tiles per chunk of the backward
+  int replica;                                  // 32-sample tiles, one per CTA (B <= 32 x #SMs), else pairs of 128-sample tiles
+  int tiles, grid, chunk_tiles, dgrid;          // tiles, CTAs of the training kernel, tiles per chunk of the backward, CTAs of dw_kernel
   size_t scale, partial, work, hlast, dwp, fcp, scratch, floats;   // offsets in floats
 };
 static int lstm_tc_plan(int B, int save, LstmTcPlan* pl) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
-  pl->tiles = (B + pr::kTileP - 1) / pr::kTileP;
-  const int pairs = (pl->tiles + pr::kTiles - 1) / pr::kTiles;
-  pl->grid = pairs < sms ? pairs : sms;
-  pl->chunk_tiles = pl->tiles < pr::kTiles * sms ? pl->tiles : pr::kTiles * sms;   // one pass of the pair kernel per chunk
+  pl->replica = B <= (pr::kTileP / 4) * sms;
+  const int rows = pl->replica ? pr::kTileP / 4 : pr::kTileP;
+  pl->tiles = (B + rows - 1) / rows;
+  const int units = pl->replica ? pl->tiles : (pl->tiles + pr::kTiles - 1) / pr::kTiles;
+  pl->grid = units < sms ? units : sms;
+  const int pass_tiles = (pl->replica ? 1 : pr::kTiles) * sms;
+  pl->chunk_tiles = pl->tiles < pass_tiles ? pl->tiles : pass_tiles;               // one pass of the training kernel per chunk
   const size_t work_cta = pr::kTiles * (save ? pr::work_total_train() : pr::work_layout_p(1, 0).total);
   size_t o = 0;
   pl->scale = o;   o += 4;
   pl->partial = o; o += (size_t)pl->grid * kPartialStride * 2;                      // doubles
   pl->work = o;    o += (size_t)pl->grid * work_cta;
   pl->hlast = o;   o += save ? ((size_t)B * kHid + 3) / 4 * 4 : 0;
-  pl->dwp = o;     o += save ? (size_t)sms * lt2::kDwPartialFloats : 0;
+  pl->dgrid = pl->chunk_tiles < sms ? pl->chunk_tiles : sms;                        // CTAs of the weight-gradient kernel
+  pl->dwp = o;     o += save ? (size_t)pl->dgrid * lt2::kDwPartialFloats : 0;
   pl->fcp = o;     o += save ? (size_t)kFcGradBlocksPerSm * sms * 256 * 2 : 0;       // doubles
-  pl->scratch = o; o += save ? (size_t)pl->chunk_tiles * pr::kTrTileFloats : 0;
+  pl->scratch = o; o += save ? (size_t)pl->chunk_tiles * (pr::kTrTileFloats / (pl->replica ? 4 : 1)) : 0;
   pl->floats = o + 4;
   return FC_OK;
 }
@@ -1119,7 +1134,8 @@ int fc_lstm_window_fwd(const float* X, const float* pack, const float* fc_w, con
     p.B = B; p.N = 1; p.with_grad = 0; p.num_tiles = tp.tiles;
     p.acc_comp = 1.3f; p.g_scale = p.g_unscale = 1.0f;
     p.train = 1; p.tr_x = X; p.tr_y = out; p.tr_hlast = save ? wf + tp.hlast : nullptr; p.tr_fcw = fc_w; p.tr_fcb = fc_b;
-    lstm_train_pair_kernel<<<tp.grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
+    if (tp.replica) lstm_train_replica_kernel<<<tp.grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
+    else lstm_train_pair_kernel<<<tp.grid, pr::kThreadsP, pr::kSmBytesP, (cudaStream_t)stream>>>(p);
     FC_CUDA(cudaGetLastError(), "lstm_train_pair_kernel (forward) launch");
     return FC_OK;
   }
@@ -1171,12 +1187,13 @@ int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, co
     FC_CUDA(cudaGetLastError(), "grad_absmax_kernel launch");
     lt2::grad_scale_kernel<<<1, 1, 0, st>>>(wf + tp.scale);
     FC_CUDA(cudaGetLastError(), "grad_scale_kernel launch");
-    FC_CUDA(cudaMemsetAsync(wf + tp.dwp, 0, (size_t)sms * lt2::kDwPartialFloats * sizeof(float), st), "cudaMemsetAsync(dW partials)");
+    FC_CUDA(cudaMemsetAsync(wf + tp.dwp, 0, (size_t)tp.dgrid * lt2::kDwPartialFloats * sizeof(float), st), "cudaMemsetAsync(dW partials)");
     for (int t0 = 0; t0 < tp.tiles; t0 += tp.chunk_tiles) {
       const int nt = tp.tiles - t0 < tp.chunk_tiles ? tp.tiles - t0 : tp.chunk_tiles;
-      const long long s0 = (long long)t0 * pr::kTileP;
-      const int nb = (int)((long long)B - s0 < (long long)nt * pr::kTileP ? (long long)B - s0 : (long long)nt * pr::kTileP);
-      const int pairs = (nt + pr::kTiles - 1) / pr::kTiles;
+      const int rows = tp.replica ? pr::kTileP / 4 : pr::kTileP;
+      const long long s0 = (long long)t0 * rows;
+      const int nb = (int)((long long)B - s0 < (long long)nt * rows ? (long long)B - s0 : (long long)nt * rows);
+      const int pairs = tp.replica ? nt : (nt + pr::kTiles - 1) / pr::kTiles;
       MpcParams p;
       memset(&p, 0, sizeof(p));
       p.wpack = pack + kTrainPackPairOff;
@@ -1187,16 +1204,17 @@ int fc_lstm_window_bwd(const float* X, const float* d_out, const float* pack, co
       p.acc_comp = 1.3f; p.g_scale = p.g_unscale = 1.0f;
       p.train = 2; p.tr_x = X + s0 * (kLook * kFeat); p.tr_dy = d_out + s0 * kOut; p.tr_fcw = fc_w; p.tr_fcb = fc_w;   // fc.bias is not needed
       p.tr_scale = wf + tp.scale; p.tr_ws = wf + tp.scratch; p.tr_tile_base = 0;
-      lstm_train_pair_kernel<<<pairs < tp.grid ? pairs : tp.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+      if (tp.replica) lstm_train_replica_kernel<<<pairs < tp.grid ? pairs : tp.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
+      else lstm_train_pair_kernel<<<pairs < tp.grid ? pairs : tp.grid, pr::kThreadsP, pr::kSmBytesP, st>>>(p);
       FC_CUDA(cudaGetLastError(), "lstm_train_pair_kernel (forward + reverse sweep) launch");
       lt2::DwParams d;
-      d.ws = wf + tp.scratch; d.tiles = nt; d.partial = wf + tp.dwp; d.acc_comp = 1.0f;
-      lt2::dw_kernel<<<sms, lt2::kDwThreads, lt2::kDwSmem, st>>>(d);
+      d.ws = wf + tp.scratch; d.tiles = nt; d.spt = tp.replica ? 1 : lt2::kStagesPerTile; d.partial = wf + tp.dwp; d.acc_comp = 1.0f;
+      lt2::dw_kernel<<<tp.dgrid, lt2::kDwThreads, lt2::kDwSmem, st>>>(d);
       FC_CUDA(cudaGetLastError(), "dw_kernel launch");
     }
     lt2::DwGradOut g;
     g.g_ih[0] = g_ih0; g.g_hh[0] = g_hh0; g.g_ih[1] = g_ih1; g.g_hh[1] = g_hh1; g.g_ih[2] = g_ih2; g.g_hh[2] = g_hh2;
-    lt2::dw_reduce_kernel<<<(kGates * kFeat + 5 * kGates * kHid + 255) / 256, 256, 0, st>>>(wf + tp.dwp, sms, wf + tp.scale, g);
+    lt2::dw_reduce_kernel<<<(kGates * kFeat + 5 * kGates * kHid + 255) / 256, 256, 0, st>>>(wf + tp.dwp, tp.dgrid, wf + tp.scale, g);
     FC_CUDA(cudaGetLastError(), "dw_reduce_kernel launch");
     double* fcp = reinterpret_cast<double*>(wf + tp.fcp);
     lt2::fc_grad_partial_kernel<<<kFcGradBlocksPerSm * sms, 256, 0, st>>>(wf + tp.hlast, d_out, B, fcp);

@@ -22,7 +22,7 @@ namespace fc {
 namespace lt2 {
 
 constexpr int kStageRows = 32;                       // samples per pipeline stage (a quarter of a tile)
-constexpr int kStagesPerTile = pr::kTileP / kStageRows;
+constexpr int kStagesPerTile = pr::kTileP / kStageRows;      // of a 128-sample tile (DwParams::spt at run time)
 constexpr int kDgPieces = 26, kActPieces = 14;       // k-slot pieces of 8: 208 gate gradients; 56 input + 56 recurrent slots
 constexpr int kStDgBytes = kDgPieces * kStageRows * 16;     // one of hi / lo
 constexpr int kStActBytes = kActPieces * kStageRows * 16;
@@ -37,11 +37,12 @@ constexpr size_t kDwPartialFloats = (size_t)kLayers * kDwRows * kDwCols;
 // cell steps (S = 48: 6.7 ulp, compensated to a fraction of an ulp) instead of once per (tile, layer) (S = 240: 33 ulp).
 constexpr int kSegSteps = 2;
 constexpr int kSegs = kLook / kSegSteps;             // accumulator segments per (tile, layer)
-constexpr int kAccSteps = kSegSteps * (pr::kTileP / 16) * 3;   // MMA accumulation steps per segment: steps x 8 k-steps of 16 samples x 3 terms
+// MMA accumulation steps per segment: steps x stages x 2 k-steps of 16 samples x 3 terms (48 for 128-sample tiles)
 
 struct DwParams {
-  const float* ws;        // per-tile scratch written by the pair kernel (pr::kTrTileFloats floats per tile)
+  const float* ws;        // per-tile scratch written by the pair kernel (pr::kTrTileFloats / (4 / spt) floats per tile)
   int tiles;              // tiles in ws
+  int spt;                // 32-sample stages per tile: 4 (128-sample tiles of the pair kernel) or 1 (its replica mode)
   float* partial;         // [grid][3][256][112], accumulated across launches (chunks of the batch)
   float acc_comp;
 };
@@ -94,15 +95,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tbase = tmem_slot;
   const int ntile = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // tiles of this CTA
+  const int spt = p.spt, rdiv = kStagesPerTile / spt, rows = kStageRows * spt;     // stages, size divisor and samples of a tile
 
   if (warp == 8) {
     // ---- producer: 64-sample stages of (layer l, tile, step t, half h), pieces of 1 KiB
     uint32_t it = 0;
     for (int l = 0; l < kLayers; ++l)
       for (int i = 0; i < ntile; ++i) {
-        const float* tw = p.ws + (size_t)(blockIdx.x + (size_t)i * gridDim.x) * pr::kTrTileFloats;
+        const float* tw = p.ws + (size_t)(blockIdx.x + (size_t)i * gridDim.x) * (pr::kTrTileFloats / rdiv);
         for (int t = 0; t < kLook; ++t)
-          for (int h = 0; h < kStagesPerTile; ++h, ++it) {
+          for (int h = 0; h < spt; ++h, ++it) {
             const int s = it % kStages;
             const uint32_t full = bar0 + s * 8, empty = bar0 + (kBarEmpty + s) * 8;
             if (it >= kStages) mbar_wait(empty, ((it / kStages) - 1) & 1);
@@ -112,19 +114,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
             if (lane == 0) mbar_expect(full, 2u * kStDgBytes + 2u * (in_bytes + rc_bytes));
             __syncwarp();
             // the pair kernel stores every image stage-major ([hi | lo][stage][piece][32 rows][16 B]): six bulk copies per stage
-            const float* dgb = tw + pr::kTrDgOff + (size_t)(l * kLook + t) * pr::kTrDgSlot;
-            const float* inb = l == 0 ? tw + pr::kTrFeatOff + (size_t)t * pr::kTrFeatSlot
-                                      : tw + pr::kTrHseqOff + (size_t)((l - 1) * (kLook + 1) + t + 1) * pr::kTrHseqSlot;
-            const float* rcb = tw + pr::kTrHseqOff + (size_t)(l * (kLook + 1) + t) * pr::kTrHseqSlot;       // h_{t-1} (slot 0 = zeros)
+            const float* dgb = tw + pr::kTrDgOff / rdiv + (size_t)(l * kLook + t) * (pr::kTrDgSlot / rdiv);
+            const float* inb = l == 0 ? tw + pr::kTrFeatOff / rdiv + (size_t)t * (pr::kTrFeatSlot / rdiv)
+                                      : tw + pr::kTrHseqOff / rdiv + (size_t)((l - 1) * (kLook + 1) + t + 1) * (pr::kTrHseqSlot / rdiv);
+            const float* rcb = tw + pr::kTrHseqOff / rdiv + (size_t)(l * (kLook + 1) + t) * (pr::kTrHseqSlot / rdiv);       // h_{t-1} (slot 0 = zeros)
             if (lane < 2) {
-              bulk_g2s(st + lane * kStDgBytes, dgb + (size_t)lane * (kDgPieces * pr::kTileP * 4) + (size_t)h * (kDgPieces * kStageRows * 4),
+              bulk_g2s(st + lane * kStDgBytes, dgb + (size_t)lane * (kDgPieces * rows * 4) + (size_t)h * (kDgPieces * kStageRows * 4),
                        (uint32_t)kStDgBytes, full);
             } else if (lane < 4) {
               const int hl = lane - 2;
-              bulk_g2s(st + 2 * kStDgBytes + hl * kStActBytes, inb + (size_t)hl * (nin * pr::kTileP * 4) + (size_t)h * (nin * kStageRows * 4), in_bytes, full);
+              bulk_g2s(st + 2 * kStDgBytes + hl * kStActBytes, inb + (size_t)hl * (nin * rows * 4) + (size_t)h * (nin * kStageRows * 4), in_bytes, full);
             } else if (lane < 6) {
               const int hl = lane - 4;
-              bulk_g2s(st + 2 * kStDgBytes + hl * kStActBytes + in_bytes, rcb + (size_t)hl * (7 * pr::kTileP * 4) + (size_t)h * (7 * kStageRows * 4), rc_bytes, full);
+              bulk_g2s(st + 2 * kStDgBytes + hl * kStActBytes + in_bytes, rcb + (size_t)hl * (7 * rows * 4) + (size_t)h * (7 * kStageRows * 4), rc_bytes, full);
             }
           }
       }
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int i = 0; i < ntile; ++i) {
         for (int t = 0; t < kLook; ++t)
-          for (int h = 0; h < kStagesPerTile; ++h, ++it) {
+          for (int h = 0; h < spt; ++h, ++it) {
             if (t % kSegSteps == 0 && h == 0) {                              // new accumulator segment
               if (t > 0 || i > 0 || l > 0) ++nd;
               if (nd >= 2) mbar_wait(bar0 + (kBarDEmpty + (nd & 1)) * 8, ((nd >> 1) - 1) & 1);   // accumulator buffer drained
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
                 for (int ks = 0; ks < kStageRows / 16; ++ks) umma_mn(d, mn_desc(g_hi + moff + ks * 256), mn_desc(a_hi + ks * 256), idesc, 1u);
               }
               umma_commit(bar0 + (kBarEmpty + s) * 8);                         // stage free once these MMAs have read it
-              if (t % kSegSteps == kSegSteps - 1 && h == kStagesPerTile - 1) umma_commit(bar0 + (kBarDFull + b) * 8);   // segment complete
+              if (t % kSegSteps == kSegSteps - 1 && h == spt - 1) umma_commit(bar0 + (kBarDFull + b) * 8);   // segment complete
             }
             __syncwarp();
           }
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
     // ---- epilogue warps 0..7: operand row m = 128 (warp / 4) + 32 (warp % 4) + lane, all 112 columns in registers
     const int mh = warp >> 2, q = warp & 3;
     const uint32_t lane_addr = tbase + ((uint32_t)(32 * q) << 16);
-    const float comp = p.acc_comp * (0.17f + 0.135f * (float)kAccSteps) * 1.1920929e-7f;
+    const float comp = p.acc_comp * (0.17f + 0.135f * (float)(kSegSteps * spt * 2 * 3)) * 1.1920929e-7f;
     float* out = p.partial + (size_t)blockIdx.x * kDwPartialFloats;
     uint32_t nd = 0;
     for (int l = 0; l < kLayers; ++l) {

@@ -119,8 +119,16 @@ struct MpcPair {
   FC_HD_CTX long recb_of(int m) const { return p.train ? 0 : rec_base(m); }
   float gsc;             // scale of the gate gradients (roll-out: kernel parameter; training: device scalar)
   // training: scratch of tile X for the weight-gradient kernel
-  FC_HD_CTX float* tr_tile(int X) const { return p.tr_ws + (size_t)(p.tr_tile_base + tile0 + X) * kTrTileFloats; }
-  FC_HD_CTX float* tr_hseq(int X, int l, int slot) const { return tr_tile(X) + kTrHseqOff + (size_t)(l * (kLook + 1) + slot) * kTrHseqSlot; }
+  // (a tile of kRowsT samples holds kRowsT / 32 stages of every image: all sizes scale with 1 / R)
+  FC_HD_CTX float* tr_tile(int X) const { return p.tr_ws + (size_t)(p.tr_tile_base + tile0 + X) * (kTrTileFloats / R); }
+  FC_HD_CTX float* tr_hseq(int X, int l, int slot) const { return tr_tile(X) + kTrHseqOff / R + (size_t)(l * (kLook + 1) + slot) * (kTrHseqSlot / R); }
+  // R == 4: the thread's 8 bytes (4 units) of the hi / lo image of the hidden state of layer l at step t (slot t + 1)
+  FC_HD_CTX float* seq_half_r(int X, int l, int t, int hl) const {
+    return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kRowsT * 4) + (size_t)((u_first >> 3) * 32 + lane) * 4 + ((u_first & 7) >> 1);
+  }
+  FC_HD_CTX float* seq_tail_r(int X, int l, int t, int hl) const {      // piece 6: units 48..55
+    return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kRowsT * 4) + (size_t)(6 * 32 + lane) * 4;
+  }
 
   // workspace pointers of tile X
   FC_HD_CTX float* w_rows(int X) const { return wbase + X * tstride; }
@@ -280,7 +288,13 @@ struct MpcPair {
   }
   // ... and into the thread-private slots of the hidden-sequence scratch: slot 0 = {hi01, hi23, lo01, lo23}, the last
   // thread: slot 1 = {hi45, 0, 0, 0}, slot 2 = {lo45, 0, 0, 0}
-  FC_HD_CTX void stg_pieces_r(int X, int t, const float* w) {
+  FC_HD_CTX void stg_pieces_r(int X, int l, int t, const float* w) {
+    if (p.train == 2) {                                      // operand-format hidden sequence kept for the weight-gradient kernel
+      Ctx::stg2(seq_half_r(X, l, t, 0), w[0], w[1]);
+      Ctx::stg2(seq_half_r(X, l, t, 1), w[2], w[3]);
+      if (last) { Ctx::stg4(seq_tail_r(X, l, t, 0), F4{w[4], 0.f, 0.f, 0.f}); Ctx::stg4(seq_tail_r(X, l, t, 1), F4{w[5], 0.f, 0.f, 0.f}); }
+      return;
+    }
     float* sq = seq_ptr(X, t);
     Ctx::stg4(sq, F4{w[0], w[1], w[2], w[3]});
     if (last) { Ctx::stg4(sq + 128, F4{w[4], 0.f, 0.f, 0.f}); Ctx::stg4(sq + 256, F4{w[5], 0.f, 0.f, 0.f}); }
@@ -315,7 +329,7 @@ struct MpcPair {
   // with the reverse sweep) its place in the operand-format hidden sequence kept for the weight-gradient kernel
   FC_HD_CTX float* seq_piece(int X, int l, int t, int ch, int hl) const {
     if (p.train == 2)   // [hi | lo][32-sample stage = TMEM quadrant][7 pieces][32 rows][16 B]: a stage of the weight-gradient kernel is contiguous
-      return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kTileP * 4) + (size_t)(quad * (7 * 32) + (2 * th + ch) * 32 + lane) * 4;
+      return tr_hseq(X, l, t + 1) + (size_t)hl * (7 * kRowsT * 4) + (size_t)(quad * (7 * 32) + (2 * th + ch) * 32 + lane) * 4;
     return seq_ptr(X, t) + (ch * 2 + hl) * 128;
   }
   FC_HD_CTX void stg_pieces(int X, int l, int t, const F4* hi4, const F4* lo4) {
@@ -328,13 +342,18 @@ struct MpcPair {
     const int img_hi = op_fwd_halves(X), img_lo = img_hi + kOpLoHalves;
     const float* sq = seq_ptr(X, t);
     if constexpr (R == 4) {
+      const bool kept = p.train == 2;
+      const float* s_hi = kept ? seq_half_r(X, l - 1, t, 0) : sq;
+      const float* s_lo = kept ? seq_half_r(X, l - 1, t, 1) : sq + 2;
+      const float* t_hi = kept ? seq_tail_r(X, l - 1, t, 0) : sq + 128;
+      const float* t_lo = kept ? seq_tail_r(X, l - 1, t, 1) : sq + 256;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        Ctx::cp_async8(op_ptr_rep(img_hi, u_first, g), sq);
-        Ctx::cp_async8(op_ptr_rep(img_lo, u_first, g), sq + 2);
+        Ctx::cp_async8(op_ptr_rep(img_hi, u_first, g), s_hi);
+        Ctx::cp_async8(op_ptr_rep(img_lo, u_first, g), s_lo);
         if (last) {
-          Ctx::cp_async16(op_ptr_rep(img_hi, u_first + 4, g), sq + 128);
-          Ctx::cp_async16(op_ptr_rep(img_lo, u_first + 4, g), sq + 256);
+          Ctx::cp_async16(op_ptr_rep(img_hi, u_first + 4, g), t_hi);
+          Ctx::cp_async16(op_ptr_rep(img_lo, u_first + 4, g), t_lo);
         }
       }
       Ctx::cp_commit();
@@ -365,9 +384,9 @@ struct MpcPair {
   // gp != nullptr (surrogate training): the pieces also go to the global dG image [26 pieces][128][16 B] (hi, then lo) of
   // this (tile, layer, step); k0 = first k-slot (multiple of 8)
   FC_HD_CTX void stg_dg_piece(float* gp, int k, F4 hi, F4 lo) const {
-    float* q = gp + (size_t)(quad * (26 * 32) + (k >> 3) * 32 + lane) * 4;     // [stage][26 pieces][32 rows][16 B]
+    float* q = gp + (size_t)((R == 1 ? quad : 0) * (26 * 32) + (k >> 3) * 32 + lane) * 4;     // [stage][26 pieces][32 rows][16 B]
     Ctx::stg4(q, hi);
-    Ctx::stg4(q + 26 * kTileP * 4, lo);
+    Ctx::stg4(q + 26 * kRowsT * 4, lo);
   }
   template <int NP>
   FC_HD_CTX void st_pairs(int col_hi, int col_lo, const float* v, float* gp = nullptr, int k0 = 0) {
@@ -569,9 +588,9 @@ struct MpcPair {
     Ctx::split_h2(xin[2] * kScaleA, xin[3] * kScaleA, hi[1], lo[1]);
     Ctx::split_h2(xin[4] * kScaleA, 0.f, hi[2], lo[2]);
     if (p.train == 2) {                                      // layer-0 input of step t, kept for the weight-gradient kernel
-      float* fp = tr_tile(X) + kTrFeatOff + (size_t)t * kTrFeatSlot + (size_t)row * 4;
+      float* fp = tr_tile(X) + kTrFeatOff / R + (size_t)t * (kTrFeatSlot / R) + (size_t)traj * 4;
       Ctx::stg4(fp, F4{hi[0], hi[1], hi[2], 0.f});
-      Ctx::stg4(fp + kTileP * 4, F4{lo[0], lo[1], lo[2], 0.f});
+      Ctx::stg4(fp + kRowsT * 4, F4{lo[0], lo[1], lo[2], 0.f});
     }
     if constexpr (R == 1) {
       Ctx::sts4(op_ptr(img_hi, 0), F4{hi[0], hi[1], hi[2], 0.f});
@@ -594,11 +613,16 @@ struct MpcPair {
     lap(18);
     if (!service) {
       st_units_zero(img_hi, img_lo, l == 0 ? kRec0 : kRec);
-      if constexpr (R == 1) if (p.train == 2) {               // slot 0 of the kept hidden sequence = zeros (h before step 0)
+      if (p.train == 2) {                                     // slot 0 of the kept hidden sequence = zeros (h before step 0)
         const F4 z = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (R == 1) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-          if (ch < 2 || last) { Ctx::stg4(seq_piece(X, l, -1, ch, 0), z); Ctx::stg4(seq_piece(X, l, -1, ch, 1), z); }
+          for (int ch = 0; ch < 3; ++ch)
+            if (ch < 2 || last) { Ctx::stg4(seq_piece(X, l, -1, ch, 0), z); Ctx::stg4(seq_piece(X, l, -1, ch, 1), z); }
+        } else {
+          const float w0[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          stg_pieces_r(X, l, -1, w0);
+        }
       }
       if (l > 0) {
         copy_input(X, l, 0);
@@ -690,7 +714,7 @@ struct MpcPair {
       } else {
         float w[6];
         split_units_r(h, kScaleA, w);
-        if (l + 1 < kLayers) stg_pieces_r(X, t, w);
+        if (l + 1 < kLayers || p.train == 2) stg_pieces_r(X, l, t, w);
         if (t + 1 < kLook) st_pieces_r(img_hi, img_lo, l == 0 ? kRec0 : kRec, w);
       }
     }
@@ -1145,7 +1169,7 @@ struct MpcPair {
 #else
     const float* rp = rec_l + (size_t)(t - tmin) * kRecFloatsP + ((size_t)uw * kRecF4 * 32 + lane) * 4;
 #endif
-    float* dg_out = p.train == 2 ? tr_tile(X) + kTrDgOff + (size_t)(l * kLook + t) * kTrDgSlot : nullptr;
+    float* dg_out = p.train == 2 ? tr_tile(X) + kTrDgOff / R + (size_t)(l * kLook + t) * (kTrDgSlot / R) : nullptr;
     float rv[2][20];
     rec_load<4>(rp, 0, rv[0]);                             // first record group: in flight during the wait
     if constexpr (R == 4) { if (last) rec_load<2>(rp, 5, rv[1]); }
@@ -1168,10 +1192,10 @@ struct MpcPair {
     if constexpr (R == 4) {
       float dg[24];
       bwd_units<4>(0, rv[0], dh, dg);
-      st_pairs_smem<8>(4 * u_first, dg);
+      st_pairs_smem<8>(4 * u_first, dg, dg_out);
       if (last) {
         bwd_units<2>(4, rv[1], dh, dg + 16);
-        st_pairs_smem<4>(4 * u_first + 16, dg + 16);
+        st_pairs_smem<4>(4 * u_first + 16, dg + 16, dg_out);
       }
       lap(7);
       arrive_ready(X, true);

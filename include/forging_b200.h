@@ -174,9 +174,10 @@ int fc_closed_loop_rk4_ex(int f64, const void* x0, const void* ref, int n_ref, i
  *   fc_lstm_window_bwd        d_out [B,4] + the workspace of the matching forward call -> the eight gradient tensors
  *                             (overwritten, state_dict shapes: g_ih0 [200,5], g_hh* / g_ih1 / g_ih2 [200,50],
  *                             g_fc_w [4,50], g_fc_b [4]).                                                          */
-/* Path behind fc_lstm_window_fwd / _bwd: 0 = automatic (B >= 8192: the tensor-core path = the pair kernel in training mode
- * for the forward and the data-gradient reverse sweep + a tcgen05 weight-gradient kernel contracting over the samples;
- * smaller batches: the FP32 FFMA kernels), 1 = always FFMA, 2 = always the tensor-core path.  Thread-local; also
+/* Path behind fc_lstm_window_fwd / _bwd: 0 = automatic = 2 = the tensor-core path (the pair kernel in training mode -- its
+ * replica mode with 32-sample tiles for B <= 32 x #SMs -- for the forward and the data-gradient reverse sweep + a tcgen05
+ * weight-gradient kernel contracting over the samples; measured faster at every batch size), 1 = the FP32 FFMA kernels.
+ * Thread-local; also
  * FC_LSTM_TRAIN=ffma|tc before the first call.  The workspace size depends on the path: query it after selecting.   */
 int fc_lstm_train_select_path(int mode);
 /* The path (1 or 2) the calling thread's current selection takes for a batch of B samples.  A backward call that runs on

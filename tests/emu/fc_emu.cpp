@@ -416,7 +416,9 @@ int fc_emu_lstm_shadow_replica(const float* row0, const float* u, const float* r
 // records + reverse sweep seeded by dy, which fills the per-tile scratch (gate gradients / hidden sequences / features in
 // operand format) that the tcgen05 weight-gradient kernel consumes; ws must hold tiles * fc_emu_train_tile_floats() floats
 long fc_emu_train_tile_floats() { return (long)fc::pr::kTrTileFloats; }
-int fc_emu_lstm_train(int mode, const float* X, const float* dy, const float* wpack, const float* fc_w, const float* fc_b, int B,
+}  // extern "C"
+template <int R>
+static int emu_lstm_train(int mode, const float* X, const float* dy, const float* wpack, const float* fc_w, const float* fc_b, int B,
                       float g_scale, int grid, float* y /*[B][4]*/, float* hlast /*[B][50]*/, float* ws) {
   fc::MpcParams p;
   std::memset(&p, 0, sizeof(p));
@@ -427,8 +429,8 @@ int fc_emu_lstm_train(int mode, const float* X, const float* dy, const float* wp
   p.tr_fcw = fc_w; p.tr_fcb = fc_b;
   float scale[2] = {g_scale, 1.0f / g_scale};
   p.tr_scale = scale; p.tr_ws = ws; p.tr_tile_base = 0;
-  p.num_tiles = (B + fc::pr::kTileP - 1) / fc::pr::kTileP;
-  const int npairs = (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles;
+  p.num_tiles = (B + fc::pr::kTileP / R - 1) / (fc::pr::kTileP / R);
+  const int npairs = R == 1 ? (p.num_tiles + fc::pr::kTiles - 1) / fc::pr::kTiles : p.num_tiles;
   if (grid > npairs) grid = npairs;
   p.work_stride = fc::pr::kTiles * (mode == 2 ? fc::pr::work_total_train() : fc::pr::work_layout_p(1, 0).total);
   std::vector<float> work((size_t)grid * p.work_stride, 0.f);
@@ -442,12 +444,20 @@ int fc_emu_lstm_train(int mode, const float* X, const float* dy, const float* wp
     for (int t = 0; t < fc::pr::kThreadsP; ++t)
       th.emplace_back([&blk, &p, t]() {
         EmuCtxTC ctx(&blk, t);
-        fc::pr::MpcPair<EmuCtxTC, 1, true> k(ctx, p);
+        fc::pr::MpcPair<EmuCtxTC, R, true> k(ctx, p);
         k.run();
       });
     for (auto& x : th) x.join();
   }
   return 0;
+}
+
+extern "C" {
+// replica = 0: pairs of 128-sample tiles; replica = 1: 32-sample tiles (tile scratch = fc_emu_train_tile_floats() / 4)
+int fc_emu_lstm_train(int mode, const float* X, const float* dy, const float* wpack, const float* fc_w, const float* fc_b, int B,
+                      float g_scale, int grid, float* y /*[B][4]*/, float* hlast /*[B][50]*/, float* ws, int replica) {
+  return replica ? emu_lstm_train<4>(mode, X, dy, wpack, fc_w, fc_b, B, g_scale, grid, y, hlast, ws)
+                 : emu_lstm_train<1>(mode, X, dy, wpack, fc_w, fc_b, B, g_scale, grid, y, hlast, ws);
 }
 
 // one-tile tcgen05 kernel with a wide controller (width_dim > 1): gl_wide [2560] = d fc_int.weight | d fc_int.bias

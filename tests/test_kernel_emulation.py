@@ -255,46 +255,49 @@ def _decode_image(img, pieces, stage_rows=32, tile=128):
     return v.transpose(0, 2, 1, 3).reshape(tile, pieces * 8)
 
 
-def test_emulated_training_mode_forward_and_weight_gradient_operands(emu, golden_weights):
+@pytest.mark.parametrize("replica", [0, 1])
+def test_emulated_training_mode_forward_and_weight_gradient_operands(emu, golden_weights, replica):
     import lstm_train_oracle as T
     lstm, fnn = state_dicts(golden_weights, "c0")
     wp = _pack_v(emu, lstm, fnn, "pair")
     rng = np.random.default_rng(11)
-    B = 150                                                  # two tiles on one emulated CTA, the second ragged (22 samples)
+    rows = 32 if replica else 128
+    B = 150 if not replica else 75                           # one emulated CTA: two tiles (three in replica mode), the last ragged
+    ntile = -(-B // rows)
     X = np.ascontiguousarray(rng.uniform(-1, 1, (B, 10, 5)), dtype=np.float32)
     dy = np.ascontiguousarray(rng.standard_normal((B, 4)) / B, dtype=np.float32)
     fc_w = np.ascontiguousarray(lstm["fc.weight"], dtype=np.float32)
     fc_b = np.ascontiguousarray(lstm["fc.bias"], dtype=np.float32)
     emu.fc_emu_train_tile_floats.restype = ctypes.c_long
-    tile_floats = int(emu.fc_emu_train_tile_floats())
+    tile_floats = int(emu.fc_emu_train_tile_floats()) // (4 if replica else 1)
     y = np.zeros((B, 4), np.float32)
     hlast = np.zeros((B, 50), np.float32)
-    ws = np.zeros(2 * tile_floats, np.float32)
+    ws = np.zeros(ntile * tile_floats, np.float32)
     scale = 2.0 ** 16
-    emu.fc_emu_lstm_train(1, _p(X), _p(dy), _p(wp), _p(fc_w), _p(fc_b), B, ctypes.c_float(scale), 1, _p(y), _p(hlast), _p(ws))
-    emu.fc_emu_lstm_train(2, _p(X), _p(dy), _p(wp), _p(fc_w), _p(fc_b), B, ctypes.c_float(scale), 1, _p(y), _p(hlast), _p(ws))
+    for mode in (1, 2):
+        emu.fc_emu_lstm_train(mode, _p(X), _p(dy), _p(wp), _p(fc_w), _p(fc_b), B, ctypes.c_float(scale), 1, _p(y), _p(hlast), _p(ws), replica)
     w = O.weights_from_state_dicts(lstm, fnn, np.float64)
     _, out_o, grads_o = T.lstm_mse_forward_backward(w, X.astype(np.float64), np.zeros((B, 4)), d_out=dy.astype(np.float64))
     assert rel_max(y, out_o) < 1e-5
     assert rel_max(dy.astype(np.float64).T @ hlast.astype(np.float64), grads_o["fc.weight"]) < 1e-5
-    # layout constants of fc_pair_layout.h (kTr*)
-    hs_slot, ft_slot, dg_slot = 2 * 7 * 128 * 4, 2 * 128 * 4, 2 * 26 * 128 * 4
+    # layout constants of fc_pair_layout.h (kTr*), scaled with the samples of a tile
+    hs_slot, ft_slot, dg_slot = 2 * 7 * rows * 4, 2 * rows * 4, 2 * 26 * rows * 4
     hs_off, ft_off = 0, 3 * 11 * hs_slot
     dg_off = ft_off + 10 * ft_slot
     assert tile_floats == dg_off + 30 * dg_slot
     g_ih = [np.zeros((200, 5)), np.zeros((200, 50)), np.zeros((200, 50))]
     g_hh = [np.zeros((200, 50)) for _ in range(3)]
     perm = np.array([(m % 4) * 50 + m // 4 for m in range(200)])           # operand row m = unit * 4 + gate -> PyTorch row
-    for tile in range(2):
+    for tile in range(ntile):
         base = tile * tile_floats
         for l in range(3):
             for t in range(10):
-                dg = _decode_image(ws[base + dg_off + (l * 10 + t) * dg_slot:][:dg_slot], 26)[:, :200] / scale
-                rec = _decode_image(ws[base + hs_off + (l * 11 + t) * hs_slot:][:hs_slot], 7)[:, :50] / 1024.0      # h_{t-1}, slot 0 = 0
+                dg = _decode_image(ws[base + dg_off + (l * 10 + t) * dg_slot:][:dg_slot], 26, tile=rows)[:, :200] / scale
+                rec = _decode_image(ws[base + hs_off + (l * 11 + t) * hs_slot:][:hs_slot], 7, tile=rows)[:, :50] / 1024.0      # h_{t-1}, slot 0 = 0
                 if l == 0:
-                    inp = _decode_image(ws[base + ft_off + t * ft_slot:][:ft_slot], 1)[:, :5] / 1024.0
+                    inp = _decode_image(ws[base + ft_off + t * ft_slot:][:ft_slot], 1, tile=rows)[:, :5] / 1024.0
                 else:
-                    inp = _decode_image(ws[base + hs_off + ((l - 1) * 11 + t + 1) * hs_slot:][:hs_slot], 7)[:, :50] / 1024.0
+                    inp = _decode_image(ws[base + hs_off + ((l - 1) * 11 + t + 1) * hs_slot:][:hs_slot], 7, tile=rows)[:, :50] / 1024.0
                 g_ih[l][perm] += dg.T @ inp
                 g_hh[l][perm] += dg.T @ rec
     for l in range(3):
