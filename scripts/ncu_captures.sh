@@ -1,3 +1,4 @@
+# ncu launch lists and full captures kept under profiles/ (run through gpurun; each command exits 0 without ncu first)
 set -x
 cd $GRAFT_REPO_ROOT
 # (1) the commands exit 0 without ncu first

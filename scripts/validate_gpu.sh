@@ -2,7 +2,7 @@ cd $GRAFT_REPO_ROOT
 python -m pytest tests -m gpu -x -q > gpurun_out/r02b_pytest_gpu3.log 2>&1; tail -3 gpurun_out/r02b_pytest_gpu3.log
 python scripts/stress_kernels.py > gpurun_out/r02b_stress.log 2>&1; tail -3 gpurun_out/r02b_stress.log
 python __graft_entry__.py smoke 2>&1 | tail -2
-# memcheck of the new kernels on small problems
+# memcheck of the new kernels on small problems (compute-sanitizer is closed on this pool: prints a notice)
 cat > /tmp/mc.py <<'PY'
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.environ["GRAFT_REPO_ROOT"])
