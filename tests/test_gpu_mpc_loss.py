@@ -35,14 +35,14 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(params=["ffma", "tcgen05", "pair", "replica"], autouse=True)
+@pytest.fixture(params=["ffma", "tcgen05", "pair", "replica", "pair-precise"], autouse=True)
 def kernel(request):
-    """Every parity test runs against all four kernels behind fc_mpc_loss: the FP32 FFMA kernel, the one-tile
-    tcgen05 kernel, the two-tile tcgen05 pair kernel and its replica mode (32-trajectory tiles for small batches)
-    (fc_mpc_select_kernel; the automatic choice is restored afterwards)."""
+    """Every parity test runs against all kernels behind fc_mpc_loss: the FP32 FFMA kernel, the one-tile tcgen05 kernel,
+    the two-tile tcgen05 pair kernel, its replica mode (32-trajectory tiles for small batches) and its instantiation with
+    the small-argument tanh polynomial (fc_mpc_select_kernel; the automatic choice is restored afterwards)."""
     from forging_control_b200 import _native
     L = _native.lib()
-    assert L.fc_mpc_select_kernel({"ffma": 1, "tcgen05": 2, "pair": 3, "replica": 4}[request.param]) == 0
+    assert L.fc_mpc_select_kernel({"ffma": 1, "tcgen05": 2, "pair": 3, "replica": 4, "pair-precise": 5}[request.param]) == 0
     yield request.param
     assert L.fc_mpc_select_kernel(0) == 0
 
