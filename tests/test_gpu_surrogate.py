@@ -95,7 +95,9 @@ def test_three_epoch_steps_with_device_adamw_match_reference(dev, cases):
     assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 3.0
 
 
-@pytest.mark.parametrize("B", [1, 40, 41, 1003, 6007])      # 6007: more 40-sample tiles than SMs -> 80-sample forward
+# 6007: more 40-sample tiles than SMs -> 80-sample forward (FFMA path); tensor-core path: <= 4736 = 32 x 148 samples run the
+# replica instantiation (32-sample tiles), 4737 and 6007 pairs of 128-sample tiles
+@pytest.mark.parametrize("B", [1, 33, 40, 41, 1003, 4737, 6007])
 def test_ragged_batches_match_fp64_oracle_with_an_arbitrary_upstream_gradient(dev, B):
     g = torch.Generator().manual_seed(100 + B)
     torch.manual_seed(5)
