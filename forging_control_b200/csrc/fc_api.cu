@@ -555,6 +555,7 @@ struct MpcPlan {
   int kind;             // 0 = FFMA, 1 = tcgen05 (one tile per CTA), 2 = tcgen05 pair, 3 = replica mode of the pair kernel
   int grid, tiles;
   bool precise;         // pair kernel instantiation with the tanh polynomial
+  bool single;          // pair kernel with one tile per CTA (#tiles <= #SMs)
   size_t work_stride;   // floats per CTA
   size_t bytes;
 };
@@ -582,7 +583,8 @@ static int mpc_plan(int B, int N, int with_grad, MpcPlan* pl, int width_dim = 1)
   if (width_dim > 1) { pl->kind = 1; pl->precise = false; }   // hidden-layer repeats of the controller live in the one-tile tcgen05 kernel only
   const int tile = pl->kind == 3 ? pr::kTileP / 4 : (pl->kind ? tc::kTileTC : kTile);
   pl->tiles = (B + tile - 1) / tile;
-  const int units = pl->kind == 2 ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
+  pl->single = pl->kind == 2 && pl->tiles <= sms;
+  const int units = pl->kind == 2 && !pl->single ? (pl->tiles + pr::kTiles - 1) / pr::kTiles : pl->tiles;   // CTA work items
   pl->grid = units < sms ? units : sms;
   pl->work_stride = pl->kind == 2 ? pr::kTiles * pr::work_layout_p(N, with_grad).total
                     : pl->kind == 3 ? pr::work_layout_p(N, with_grad).total
@@ -804,6 +806,7 @@ static int mpc_loss_impl(const float* X, const float* u0, const float* Z, const 
   p.work = reinterpret_cast<float*>(after_partial);
   p.work_stride = pl.work_stride;
   p.B = B; p.N = N; p.with_grad = with_grad ? 1 : 0; p.num_tiles = pl.tiles;
+  p.single_tile = pl.single ? 1 : 0;
   p.alpha = alpha;
   p.grad_scale = (float)(1.0 / ((double)N * (double)B_global));
   // 1.0 = the law measured on iid data (scripts/micro/umma_test.cu); real LSTM partial sums are more coherent and

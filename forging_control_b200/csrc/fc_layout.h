@@ -223,6 +223,9 @@ struct MpcParams {
   // surrogate training on the pair kernel (Model_NN/Functions.py:313-340, :520-569; fc_lstm_train_tc.cuh): one window per
   // sample, N = 1, every cell step recorded.  train = 1: forward only (y); train = 2: forward with records + reverse sweep
   // seeded by d loss / d y, writing the gate gradients and the layer inputs in operand format for the weight-gradient kernel
+  // pair kernel with ONE tile per CTA (mid-size batches, #tiles <= #SMs: every tile gets an SM of its own and the dedicated
+  // issuer warp of the pair kernel is worth ~6 % over the one-tile kernel)
+  int single_tile;
   int train;
   const float* tr_x;     // [B][10][5] windows
   float* tr_y;           // [B][4] outputs (train = 1)

@@ -1364,12 +1364,13 @@ struct MpcPair {
     for (int i = tid; i < kSmPgP - kSmRefP; i += kThreadsP) sm[kSmRefP + i] = 0.f;   // per-row arrays (R == 4 uses 32 rows of 128)
     ctx.bar_init_fence();
     ctx.sync();
-    const int npairs = R == 1 ? (p.num_tiles + kTiles - 1) / kTiles : p.num_tiles;   // CTA work items
+    const bool one = R != 1 || p.single_tile;                // one tile per CTA work item
+    const int npairs = one ? p.num_tiles : (p.num_tiles + kTiles - 1) / kTiles;      // CTA work items
     if (tid == 0 && ctx.bid() < npairs) request_weights(false, 0);
     for (int pp = ctx.bid(); pp < npairs; pp += ctx.nblk()) {
       const bool more = pp + ctx.nblk() < npairs;
-      tile0 = R == 1 ? pp * kTiles : pp;
-      ntl = R == 1 ? (p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles) : 1;
+      tile0 = one ? pp : pp * kTiles;
+      ntl = one ? 1 : (p.num_tiles - tile0 < kTiles ? p.num_tiles - tile0 : kTiles);
       if (scalar)
         for (int X = 0; X < ntl; ++X) {
           if (p.shadow) load_tile_shadow(X);
