@@ -148,11 +148,12 @@ struct MpcPair {
 #else
   FC_HD_CTX static float denom_(float e2arg) { return 1.f + Ctx::ex2(fminf(e2arg, kExpMax)); }
 #endif
+  // four reciprocals from TWO MUFU operations (one per pair of denominators): 8 issue slots.  One reciprocal of the product
+  // of all four (9 multiplies, the one-tile kernel's form) costs 10 issue slots; with the cell update bound by its
+  // instruction count the pair form measured +0.6 % sustained / +1.1 % one pass (same-box A/B) at a quarter more XU load.
   FC_HD_CTX static void quad_rcp(float a, float b, float c, float d, float& ra, float& rb, float& rc, float& rd) {
-    const float ab = a * b, cd = c * d;
-    const float r = Ctx::rcp(ab * cd);
-    const float rab = r * cd, rcd = r * ab;
-    ra = rab * b; rb = rab * a; rc = rcd * d; rd = rcd * c;
+    const float r1 = Ctx::rcp(a * b), r2 = Ctx::rcp(c * d);
+    ra = r1 * b; rb = r1 * a; rc = r2 * d; rd = r2 * c;
   }
   // tanh(x) = 1 - 2 rd with rd = 1/(1 + e^{2x}): absolute error ~1e-7.  The gate pre-activations and cell states it is
   // applied to carry an absolute error of that size already (fp16 hi/lo product, fp32 cell recurrence), so the odd
@@ -239,19 +240,6 @@ struct MpcPair {
   FC_HD_CTX void wait_weights() { ctx.bar_wait(kBarWeightsP, phW); phW += 1; }                    // issuer warp
   FC_HD_CTX void request_weights(bool bwd, int l) {                                              // tid 0 only
     const int n = bwd ? bwd_img_halves(l) : fwd_img_halves(l);   // hi + lo images of halves = that many floats
-    if constexpr (R == 4) if (bwd) {
-      // replica mode: the hi and lo images are interleaved k-block by k-block, [k/8][hi rows | lo rows][8 halves], so that
-      // ONE MMA chain with N = 2 Nb computes dG_hi W_hi and dG_hi W_lo side by side (26 instead of 39 MMAs per step; the
-      // accumulator has the TMEM columns to spare with a single tile)
-      const int nb = nb_of(l);
-      const float* src = p.wpack + wb_off(l);
-      ctx.bulk_expect(kBarWeightsP, n * 4);
-      for (int kb = 0; kb < kKB / 8; ++kb) {
-        ctx.bulk_copy(sm + kSmWP + kb * (2 * nb * 4), src + kb * (nb * 4), nb * 16, kBarWeightsP);
-        ctx.bulk_copy(sm + kSmWP + kb * (2 * nb * 4) + nb * 4, src + n / 2 + kb * (nb * 4), nb * 16, kBarWeightsP);
-      }
-      return;
-    }
     ctx.bulk_load(sm + kSmWP, p.wpack + (bwd ? wb_off(l) : wf_off(l)), n, kBarWeightsP);
   }
 
@@ -451,14 +439,6 @@ struct MpcPair {
     const float* b_hi = sm + kSmWP;
     const float* b_lo = b_hi + bwd_img_halves(l) / 2;
     const int d = col_d_bwd(X);
-    if constexpr (R == 4) {
-      const float* a_hi = sm + kSmOpP;
-      const float* a_lo = a_hi + kOpGLoHalves / 2;
-      ctx.mma_ss(d, 2 * nb, a_hi, b_hi, 2 * nb, kKB / 16, false);     // [dG_hi W_hi | dG_hi W_lo]
-      ctx.mma_ss(d, nb, a_lo, b_hi, 2 * nb, kKB / 16, true);          // += dG_lo W_hi on the first Nb columns
-      ctx.commit(kBarFull + X);
-      return;
-    }
     if (R == 1 && X == 0) {
 #ifdef FC_ABL_ONE_TERM
       ctx.mma(d, nb, kColGhi, b_hi, nb, 0, kKB / 16, false);
@@ -1059,28 +1039,22 @@ struct MpcPair {
     if constexpr (R == 4) {
       // third th owns columns [36 th, 36 th + 36) (layer 0: [18 th, 18 th + 18)): 18 slots d(input unit), 18 slots
       // d(h_prev unit); this thread's units are slots 4 quad .. 4 quad + 3 (+ 2 for the last thread)
-      float di[kOwn], dr[kOwn], di2[kOwn], dr2[kOwn];        // ..2: the W_lo term, Nb columns further (see request_weights)
-      const int nb = nb_of(l);
+      float di[kOwn], dr[kOwn];
       const int cr = l > 0 ? dcol + 36 * th + 18 + 4 * quad : dcol + 18 * th + 4 * quad;
       if (l > 0) {
         ctx.template tmem_ld_nowait<4>(dcol + 36 * th + 4 * quad, di);
-        ctx.template tmem_ld_nowait<4>(nb + dcol + 36 * th + 4 * quad, di2);
-        if (last) {
-          ctx.template tmem_ld_nowait<2>(dcol + 36 * th + 4 * quad + 4, di + 4);
-          ctx.template tmem_ld_nowait<2>(nb + dcol + 36 * th + 4 * quad + 4, di2 + 4);
-        }
+        if (last) ctx.template tmem_ld_nowait<2>(dcol + 36 * th + 4 * quad + 4, di + 4);
       }
       ctx.template tmem_ld_nowait<4>(cr, dr);
-      ctx.template tmem_ld_nowait<4>(nb + cr, dr2);
-      if (last) { ctx.template tmem_ld_nowait<2>(cr + 4, dr + 4); ctx.template tmem_ld_nowait<2>(nb + cr + 4, dr2 + 4); }
+      if (last) ctx.template tmem_ld_nowait<2>(cr + 4, dr + 4);
       ctx.tmem_ld_wait();
       float* dq = w_dseq(X) + (size_t)t * kSlot + (size_t)uw * kMaxOwn * 32 + lane;
 #pragma unroll
       for (int j = 0; j < kOwn; ++j)
         if (j < nown) {
-          if (l > 0) { const float v = di[j] * unscale_b; dq[j * 32] = fmaf(v, corr_b, v) + di2[j] * unscale_b; }
+          if (l > 0) { const float v = di[j] * unscale_b; dq[j * 32] = fmaf(v, corr_b, v); }
           const float v = dr[j] * unscale_b;
-          dh[j] = fmaf(v, corr_b, v) + dr2[j] * unscale_b;
+          dh[j] = fmaf(v, corr_b, v);
         } else {
           dh[j] = 0.f;
         }
@@ -1117,12 +1091,6 @@ struct MpcPair {
     if (kr >= 0) {
       float df[8];
       ctx.template tmem_ld<8>(col_d_bwd(X) + 56, df);
-      if constexpr (R == 4) {                                // + the W_lo term (layer 0: Nb = 64 columns further)
-        float df2[8];
-        ctx.template tmem_ld<8>(col_d_bwd(X) + kNB0 + 56, df2);
-#pragma unroll
-        for (int f = 0; f < 8; ++f) df[f] += df2[f];
-      }
       float* gp = w_grow(X) + (size_t)kr * kFeat * kTileP + row;
 #pragma unroll
       for (int f = 0; f < kFeat; ++f) {
